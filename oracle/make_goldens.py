@@ -1,0 +1,161 @@
+"""Generate tests/golden/*.npz from the REAL reference (run in the build container).
+
+TEST INFRASTRUCTURE.  Usage:  python oracle/make_goldens.py
+Imports jiadongdan/motif-learn from /root/reference through oracle/ref_shim.py
+(the reference cannot travel to the GPU box), runs its own public API on small
+seeded inputs produced by its own dataset generators and stores inputs+outputs.
+Every array in the fixtures is an output of unmodified reference code.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+ref_shim.load_reference()
+from mtflearn.features import ZPs, zmoments, KeyPoints  # noqa: E402
+from mtflearn.features import construct_rot_maps_matrix, construct_complex_matrix, nm2j, nm2j_complex  # noqa: E402
+from mtflearn.datasets import HoneyCombLattice, get_zps_test_patches  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(arrays)} arrays")
+
+
+def golden_index():
+    n = np.array([0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 7, 12, 20])
+    m = np.array([0, -1, 1, -2, 0, 2, -3, -1, 1, 3, -4, -2, 0, 2, 4, -5, 6, -20])
+    z12 = ZPs(12, 16)
+    save("index.npz",
+         n=n, m=m, j=nm2j(n, m), jc=nm2j_complex(n, np.abs(m)),
+         n12=z12.n, m12=z12.m,
+         cmat12=construct_complex_matrix(z12.n, z12.m),
+         rotmat_a=construct_rot_maps_matrix([1, 2, 3], [2, 3, 4, 6]),
+         rotmat_12=construct_rot_maps_matrix([2, 3, 4, 6], z12.m))
+
+
+def golden_basis():
+    arrays = {}
+    for n_max, size in [(4, 8), (6, 9), (5, 11), (10, 32)]:
+        z = ZPs(n_max, size)
+        arrays[f"full_{n_max}_{size}"] = z.polynomials
+    rng = np.random.default_rng(1234)
+    for n_max, size in [(12, 48), (12, 64), (20, 64), (12, 33)]:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            z = ZPs(n_max, size)
+        flat = z.polynomials.ravel()
+        idx = rng.choice(flat.size, size=6000, replace=False)
+        arrays[f"idx_{n_max}_{size}"] = idx
+        arrays[f"val_{n_max}_{size}"] = flat[idx]
+        arrays[f"stat_{n_max}_{size}"] = np.array([flat.sum(), np.abs(flat).sum(),
+                                                    float(np.count_nonzero(z.polynomials[0]))])
+    save("basis.npz", **arrays)
+
+
+def _zm_outputs(prefix, o, arrays, full=True):
+    oc = o.to_complex()
+    arrays[prefix + "data"] = o.data
+    arrays[prefix + "n"] = o.n
+    arrays[prefix + "m"] = o.m
+    arrays[prefix + "cdata"] = oc.data
+    arrays[prefix + "cn"] = oc.n
+    arrays[prefix + "cm"] = oc.m
+    arrays[prefix + "rot"] = o.rot_maps([2, 3, 4, 6])
+    arrays[prefix + "rot_p1"] = o.rot_maps([3, 6], p=1)
+    arrays[prefix + "rot_unsel"] = o.rot_maps([2, 4], m_unselect=(0, 1, 2))
+    if full:
+        arrays[prefix + "real_back"] = oc.to_real().data
+        arrays[prefix + "norm2"] = o.normalize().data
+        arrays[prefix + "norm1"] = o.normalize(order=1).data
+        arrays[prefix + "norminf"] = o.normalize(order=np.inf).data
+        arrays[prefix + "rot30"] = o.rotate(30.0).data
+        arrays[prefix + "mirror"] = o.mirror_map()
+        sel = o.select([2, -3])
+        arrays[prefix + "sel_data"] = sel.data
+        arrays[prefix + "sel_m"] = sel.m
+        uns = o.unselect([0, 1])
+        arrays[prefix + "unsel_m"] = uns.m
+        arrays[prefix + "unsel_n"] = uns.n
+
+
+def golden_patches():
+    arrays = {}
+    p3 = get_zps_test_patches(size=64, n_fold=3, num_patches=10)
+    p4 = get_zps_test_patches(size=64, n_fold=4, num_patches=4, include_center=False)
+    p = np.concatenate([p3, p4]).astype(np.float32)
+    arrays["patches"] = p
+    arrays["patches_sha"] = np.array(sha(p))
+    o = ZPs(12, 64).transform(p)
+    _zm_outputs("z12_", o, arrays)
+    o20 = ZPs(20, 64).transform(p)
+    arrays["z20_data"] = o20.data
+    arrays["z20_cabs"] = np.abs(o20.to_complex().data)
+    arrays["z20_cang"] = np.angle(o20.to_complex().data)
+    save("patches_nfold.npz", **arrays)
+
+
+def golden_lattice():
+    arrays = {}
+    lat = HoneyCombLattice(size=256, l=12, seed=0)
+    img = lat.to_image()
+    pts = np.vstack(lat.get_points())
+    arrays["img"] = img
+    arrays["img_sha"] = np.array(sha(img))
+    arrays["pts"] = pts
+    for k in (32, 33):
+        kp = KeyPoints(pts, img, k)
+        patches = kp.extract_patches()
+        arrays[f"kept_{k}"] = kp.pts
+        arrays[f"patch_sha_{k}"] = np.array(sha(patches))
+        arrays[f"patch_head_{k}"] = patches[:4]
+        arrays[f"patch_sum_{k}"] = patches.astype(np.float64).sum(axis=(1, 2))
+        if k == 32:
+            flat = KeyPoints(pts, img, k).extract_patches(flat=True)
+            arrays["flat_shape_32"] = np.array(flat.shape)
+            o = ZPs(10, 32).transform(patches[:96])
+            _zm_outputs("z10_", o, arrays, full=False)
+    # dense map: non-square crop, even window, n_max=12 (config-2 family)
+    crop = img[:160, :192].astype(np.float64)
+    arrays["map_img"] = crop
+    o = ZPs(12, 48).transform(crop)
+    rng = np.random.default_rng(7)
+    ys = np.concatenate([rng.integers(0, 160, 500), [0, 0, 159, 159, 23, 24, 135, 136]])
+    xs = np.concatenate([rng.integers(0, 192, 500), [0, 191, 0, 191, 23, 24, 167, 168]])
+    arrays["map_ys"], arrays["map_xs"] = ys, xs
+    arrays["map_moments"] = o.data[:, ys, xs]
+    arrays["map_rot"] = o.rot_maps([2, 3, 4, 6])
+    arrays["map_valid"] = o.valid_mask
+    arrays["map_mirror_pts"] = o.mirror_map()[ys, xs]
+    arrays["map_cabs_pts"] = np.abs(o.to_complex().data)[:, ys, xs]
+    # odd window, smaller order
+    crop2 = img[40:140, 30:150].astype(np.float64)
+    o2 = ZPs(8, 33).transform(crop2)
+    arrays["map2_img"] = crop2
+    arrays["map2_moments"] = o2.data[:, ::7, ::5]
+    arrays["map2_rot"] = o2.rot_maps([3, 6])
+    arrays["map2_valid"] = o2.valid_mask
+    save("lattice.npz", **arrays)
+
+
+if __name__ == "__main__":
+    golden_index()
+    golden_basis()
+    golden_patches()
+    golden_lattice()
