@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200 Zernike hot path (one JSON line on stdout, rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload patches|map] [--impl reference]
+
+Workloads (BASELINE.json metric: "Zernike patches/sec (n_max=12, 64px) and symmetry-map
+Mpix/sec"):
+  patches  one step = ZPs(n_max=12, size=64) moments of a batch of synthetic 64x64 lattice
+           patches resident in HBM (batch >> L2, so every step streams from HBM)  [default]
+  map      one step = fused symmetry map (n-folds 2,3,4,6) of a 2048x2048 synthetic lattice
+           frame, n_max=12, 48-px window (BASELINE configs[1]); L2 is flushed between steps
+The default line carries the other workload under "also" so both headline numbers appear.
+Multi-GPU (torchrun): every rank runs the same step on its own shard (weak scaling), timed
+as max over ranks between barriers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_MAX = 12
+PATCH = 64
+MAP_SIZE = 2048
+MAP_WINDOW = 48
+FOLDS = [2, 3, 4, 6]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {
+                getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(pynvml, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            }
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons",
+                                  getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+            while not self._stop.is_set():
+                self.samples.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    mask = int(get_reasons(h))
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as exc:  # NVML missing: report that rather than fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_threads():
+    try:
+        import numpy  # noqa: F401  (loads the BLAS whose pool is queried)
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_patches(n_sample: int, repeats: int):
+    """The reference's CPU algorithm for the patch path (numpy.dot in float64, _zps.py:146-157),
+    through the oracle port, on n_sample patches of the bench batch.  Returns patches/s (best)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import zernike_oracle as zo
+    from motif_learn_b200.datasets import honeycomb_image
+    img, pts = honeycomb_image(1024, bond=12.0, seed=0)
+    kept = zo.clear_border(pts, img.shape, PATCH)
+    base = zo.extract_patches(img, kept, PATCH)
+    reps = -(-n_sample // len(base))
+    sample = np.concatenate([base] * reps)[:n_sample]
+    _, _, basis = zo.zernike_basis(N_MAX, PATCH)
+    zo.project_patches(sample[:256], basis)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        zo.project_patches(sample, basis)
+        times.append(time.perf_counter() - t0)
+    return n_sample / min(times), times
+
+
+def cpu_map(size: int, repeats: int = 1):
+    """The reference's CPU algorithm for the map path (scipy fftconvolve per mode + rot_maps,
+    _zps.py:159-193, _zmoments.py:420-462) through the oracle port on a size x size crop."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import zernike_oracle as zo
+    from motif_learn_b200.datasets import honeycomb_image
+    img, _ = honeycomb_image(size, bond=12.0, seed=0)
+    n, m, basis = zo.zernike_basis(N_MAX, MAP_WINDOW)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        z = zo.moment_map_fft(img.astype(np.float64), basis, n)
+        zo.rot_maps(z, n, m, FOLDS)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return size * size / 1e6 / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = cpu_threads()
+    if args.workload == "patches":
+        n_sample = 20000
+        per_step = []
+        for _ in range(args.warmup):
+            cpu_patches(n_sample, 1)
+        for _ in range(args.steps):
+            v, t = cpu_patches(n_sample, 1)
+            per_step.append(t[0])
+        total = sum(per_step)
+        value = n_sample * args.steps / total
+        line = {"metric": "zernike_patches_per_sec", "unit": "patches/s",
+                "config": {"workload": f"patches n_max={N_MAX} size={PATCH}", "batch": n_sample},
+                "sample": f"{n_sample} float32 64x64 lattice patches per step, numpy.dot float64 (reference algorithm)"}
+    else:
+        size = 512
+        per_step = []
+        for _ in range(min(args.warmup, 1)):
+            cpu_map(256)
+        for _ in range(args.steps):
+            _, dt = cpu_map(size)
+            per_step.append(dt)
+        total = sum(per_step)
+        value = size * size * args.steps / 1e6 / total
+        line = {"metric": "symmetry_map_mpix_per_sec", "unit": "Mpix/s",
+                "config": {"workload": f"symmetry map n_max={N_MAX} window={MAP_WINDOW} folds={FOLDS}",
+                           "image": f"{size}x{size} crop of the {MAP_SIZE}x{MAP_SIZE} frame"},
+                "sample": f"{size}x{size} crop per step: 91 scipy.fftconvolve (1 thread) + rot_maps"}
+    line.update({"impl": "reference", "value": value, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                 "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                 "cpu_baseline": {"value": value, "unit": line["unit"], "cores": cores, "kind": "port",
+                                  "sample": line.pop("sample")},
+                 "e2e": {"value": value, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def flush_l2(torch, scratch):
+    scratch.zero_()            # > L2 capacity: evicts the previous step's lines
+
+
+def timed(torch, dist, world, fn, steps, warmup, device_index, between=None):
+    """W warm-up steps, then exactly K timed steps with CUDA events on the launching stream,
+    barrier + synchronize on both sides, max over ranks.  Returns (ms_total, clocks, launches)."""
+    from motif_learn_b200 import _lib
+    for _ in range(warmup):
+        fn()
+        if between:
+            between()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    _lib.reset_launch_count()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    with ClockSampler(device_index) as clk:
+        for i in range(steps):
+            ev0[i].record()
+            fn()
+            ev1[i].record()
+            if between:
+                between()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    launches = _lib.launch_count()
+    # no L2 flush between steps: one interval over all K steps (launch gaps included);
+    # with a flush between steps: sum of the per-step intervals (the flush is not the workload)
+    ms = ev0[0].elapsed_time(ev1[-1]) if between is None else sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, clk.summary(), launches
+
+
+def bench_patches(torch, dist, rank, world, args, pk):
+    import numpy as np
+    from motif_learn_b200 import _lib
+    from motif_learn_b200.datasets import honeycomb_image
+    from motif_learn_b200.features import ZPs, KeyPoints
+    dev = torch.cuda.current_device()
+    zp = ZPs(N_MAX, PATCH, precision=args.precision)
+    prec = {0: "fp32", 1: "tf32", 2: "tf32x3"}[zp._precision_code()]
+    n_modes = len(zp.n)
+
+    # synthetic input: patches gathered at the atom sites of lattice frames (K2), tiled to the batch
+    img, pts = honeycomb_image(2048, bond=12.0, seed=rank)
+    kp = KeyPoints(pts, torch.from_numpy(img).cuda(), PATCH)
+    base = kp.extract_patches()                                   # ~21 k patches, device-resident
+    batch = args.batch
+    reps = -(-batch // base.shape[0])
+    patches = base.repeat(reps, 1, 1)[:batch].contiguous()        # batch*16 KiB >> 126 MB L2
+    del base
+    out_holder = {}
+
+    def step():
+        out_holder["z"] = zp.transform(patches).data
+
+    ms, clocks, launches = timed(torch, dist, world, step, args.steps, args.warmup, dev)
+    value = batch * world * args.steps / (ms / 1e3)
+    alg_bytes = batch * (PATCH * PATCH * 4 + n_modes * 4)
+    achieved = alg_bytes * args.steps / (ms / 1e3) / 1e9
+    flops = 2.0 * batch * PATCH * PATCH * n_modes
+    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+            "kernel": "project_tc_kernel" if prec != "fp32" else "project_simt_kernel",
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "tflops": flops * args.steps / (ms / 1e3) / 1e12}
+
+    # end to end: the numpy user's call, pinned host buffers, H2D + D2H inside the timed region
+    n_e2e = min(batch, args.e2e_batch)
+    host = torch.empty((n_e2e, PATCH, PATCH), dtype=torch.float32, pin_memory=True)
+    host.copy_(patches[:n_e2e])
+    host_np = host.numpy()
+    zp_host = ZPs(N_MAX, PATCH, precision=args.precision, output="numpy")
+    zp_host.transform(host_np[:1024])
+    e2e_steps = max(2, min(args.steps, 5))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = zp_host.transform(host_np)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    assert res.data.shape == (n_e2e, n_modes)
+    e2e = {"value": n_e2e * world * e2e_steps / dt, "unit": "patches/s",
+           "h2d_bytes_per_step": n_e2e * PATCH * PATCH * 4, "d2h_bytes_per_step": n_e2e * n_modes * 4,
+           "steps": e2e_steps, "api": "ZPs.transform(numpy pinned) -> zb200_project_patches_host"}
+    line = {"metric": "zernike_patches_per_sec", "value": value, "unit": "patches/s",
+            "ms_per_step": ms / args.steps, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)"}[prec],
+            "config": {"workload": f"patches n_max={N_MAX} size={PATCH} (metric shape)", "batch_per_gpu": batch,
+                       "modes": n_modes, "precision": prec, "l2": "input batch larger than L2 (no flush needed)",
+                       "parallelism": f"patch shards x{world}, no collective"},
+            "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    return line
+
+
+def bench_map(torch, dist, rank, world, args, pk):
+    import numpy as np
+    from motif_learn_b200.datasets import honeycomb_image
+    from motif_learn_b200.features import ZPs
+    dev = torch.cuda.current_device()
+    zp = ZPs(N_MAX, MAP_WINDOW, precision="fp32" if args.precision == "auto" else args.precision)
+    img, _ = honeycomb_image(MAP_SIZE, bond=12.0, seed=rank)
+    dimg = torch.from_numpy(img).cuda()
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    holder = {}
+
+    def step():
+        holder["s"] = zp.symmetry_map(dimg, FOLDS)
+
+    steps = max(2, min(args.steps, args.map_steps))
+    ms, clocks, launches = timed(torch, dist, world, step, steps, min(args.warmup, 3) if args.warmup >= 3 else 3, dev,
+                                 between=lambda: flush_l2(torch, scratch))
+    mpix = MAP_SIZE * MAP_SIZE / 1e6
+    value = mpix * world * steps / (ms / 1e3)
+    flops = 2.0 * MAP_SIZE * MAP_SIZE * MAP_WINDOW * MAP_WINDOW * len(zp.n)
+    ach = flops * steps / (ms / 1e3) / 1e12
+    tf32_peak = pk["bf16_tflops"] / 2.0
+    roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+            "traffic": None, "peak_source": pk["source"] + " bf16 / 2 (tf32 dense rate)",
+            "kernel": "map_simt_kernel<scores>", "algorithmic_flops_per_launch": flops}
+    # end to end: numpy frame in, numpy scores out
+    zp_host = ZPs(N_MAX, MAP_WINDOW, precision=zp.precision, output="numpy")
+    host = torch.empty((MAP_SIZE, MAP_SIZE), dtype=torch.float32, pin_memory=True)
+    host.copy_(dimg)
+    t0 = time.perf_counter()
+    e2e_steps = 2
+    for _ in range(e2e_steps):
+        res = zp_host.symmetry_map(host.numpy(), FOLDS)
+    dt = time.perf_counter() - t0
+    e2e = {"value": mpix * world * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": MAP_SIZE * MAP_SIZE * 4,
+           "d2h_bytes_per_step": int(res.size * 8), "steps": e2e_steps, "api": "ZPs.symmetry_map(numpy) -> numpy"}
+    return {"metric": "symmetry_map_mpix_per_sec", "value": value, "unit": "Mpix/s", "ms_per_step": ms / steps,
+            "steps": steps, "dtype": "f32",
+            "config": {"workload": f"symmetry map {MAP_SIZE}x{MAP_SIZE} n_max={N_MAX} window={MAP_WINDOW} "
+                                   f"folds={FOLDS} (BASELINE configs[1])", "l2": "256 MiB scratch write between steps",
+                       "parallelism": f"one frame per GPU x{world}, no collective"},
+            "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="patches", choices=["patches", "map"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
+    ap.add_argument("--batch", type=int, default=262144, help="patches per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=65536)
+    ap.add_argument("--map-steps", type=int, default=5)
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workload")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pk = peaks()
+    primary = bench_patches if args.workload == "patches" else bench_map
+    secondary = bench_map if args.workload == "patches" else bench_patches
+    line = primary(torch, dist, rank, world, args, pk)
+    line.setdefault("steps", args.steps)
+    line.update({"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                 "vs_baseline": None, "data": "synthetic"})
+    if not args.no_also:
+        try:
+            other = secondary(torch, dist, rank, world, args, pk)
+            line["also"] = {k: other[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "config",
+                                                  "roofline", "e2e", "gpu_launches")}
+        except Exception as exc:  # the secondary number must never sink the primary line
+            line["also"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if rank == 0 and not args.no_cpu:
+        cores = cpu_threads()
+        if args.workload == "patches":
+            v, times = cpu_patches(20000, 8)
+            line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
+                                    "sample": "20000 float32 64x64 patches, numpy.dot float64 (reference algorithm "
+                                              f"_zps.py:146-157 via oracle port), best of {len(times)}"}
+            if "also" in line and "error" not in line["also"]:
+                mv, dt = cpu_map(384)
+                line["also"]["cpu_baseline"] = {"value": mv, "unit": "Mpix/s", "cores": 1, "kind": "port",
+                                                "sample": f"384x384 crop, 91 scipy.fftconvolve + rot_maps, {dt:.1f} s"}
+        else:
+            mv, dt = cpu_map(512)
+            line["cpu_baseline"] = {"value": mv, "unit": "Mpix/s", "cores": 1, "kind": "port",
+                                    "sample": f"512x512 crop, 91 scipy.fftconvolve (1 thread, reference algorithm "
+                                              f"_zps.py:159-193 via oracle port) + rot_maps, {dt:.1f} s"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

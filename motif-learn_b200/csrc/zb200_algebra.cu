@@ -1,0 +1,372 @@
+// zmoments algebra on device-resident moment arrays: real<->complex packing, normalisation,
+// mode selection, rotation, n-fold and mirror scores.  Replaces the numpy passes of
+// mtflearn/features/_zmoments.py:300-493.  All HBM-bound element-wise / small-reduction work:
+// one thread per item (patch or pixel), items of a warp are consecutive so the planar (M,H,W)
+// layout is fully coalesced; the (N,M) layout walks a row per thread through L1.
+#include "zb200_common.cuh"
+
+#include <string.h>
+#include <vector>
+
+namespace zb200 {
+
+// stream-ordered scratch holding small host tables on the device for one call
+struct Scratch {
+    void* ptr = nullptr;
+    cudaStream_t s;
+    explicit Scratch(cudaStream_t st) : s(st) {}
+    ~Scratch() { if (ptr) cudaFreeAsync(ptr, s); }
+    int upload(const void* host, size_t bytes) {
+        ZB_CUDA(cudaMallocAsync(&ptr, bytes ? bytes : 1, s));
+        if (bytes) ZB_CUDA(cudaMemcpyAsync(ptr, host, bytes, cudaMemcpyHostToDevice, s));
+        return ZB200_OK;
+    }
+};
+
+template <typename T> struct Cx { T re, im; };
+
+static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)ceil_div(n, threads); }
+
+// ---- real -> complex: Zc[c] = Z[pos[c]] + i Z[neg[c]]  (_zmoments.py:111-132, 300-316) -------
+template <typename T>
+__global__ void to_complex_kernel(const T* __restrict__ in, long long n_items, long long iis, long long ims,
+                                  const int* __restrict__ pos, const int* __restrict__ neg, int n_c,
+                                  Cx<T>* __restrict__ out, long long ois, long long oms) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    for (int c = 0; c < n_c; ++c) {
+        Cx<T> v;
+        v.re = pos[c] >= 0 ? in[it * iis + pos[c] * ims] : (T)0;
+        v.im = neg[c] >= 0 ? in[it * iis + neg[c] * ims] : (T)0;
+        out[it * ois + c * oms] = v;
+    }
+}
+
+// ---- complex -> real: Z[j] = Re or Im of Zc[src[j]]  (_zmoments.py:134-196, 318-341) ---------
+template <typename T>
+__global__ void to_real_kernel(const Cx<T>* __restrict__ in, long long n_items, long long iis, long long ims,
+                               const int* __restrict__ src, const unsigned char* __restrict__ take_im, int n_r,
+                               T* __restrict__ out, long long ois, long long oms) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    for (int j = 0; j < n_r; ++j) {
+        const Cx<T> v = in[it * iis + src[j] * ims];
+        out[it * ois + j * oms] = take_im[j] ? v.im : v.re;
+    }
+}
+
+// ---- select: out[q] = in[index[q]]  (_zmoments.py:359-374) -----------------------------------
+template <typename E>
+__global__ void select_kernel(const E* __restrict__ in, long long n_items, long long iis, long long ims,
+                              const int* __restrict__ index, int n_out, E* __restrict__ out, long long ois,
+                              long long oms) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    for (int q = 0; q < n_out; ++q) out[it * ois + q * oms] = in[it * iis + index[q] * ims];
+}
+
+// ---- normalize: x / ||x||_p over modes  (_zmoments.py:344-356, np.linalg.norm semantics) ----
+template <typename T> __device__ __forceinline__ T mag(T v) { return fabs(v); }
+template <typename T> __device__ __forceinline__ T mag(Cx<T> v) { return hypot(v.re, v.im); }
+template <typename T> __device__ __forceinline__ T scale(T v, T s) { return v / s; }
+template <typename T> __device__ __forceinline__ Cx<T> scale(Cx<T> v, T s) { return Cx<T>{v.re / s, v.im / s}; }
+
+template <typename T>
+__device__ __forceinline__ void norm_accum(T a, int kind, double p, T& acc) {
+    switch (kind) {
+        case ZB200_NORM_L1: acc += a; break;
+        case ZB200_NORM_L2: acc += a * a; break;
+        case ZB200_NORM_INF: acc = a > acc ? a : acc; break;
+        default: acc += (T)pow((double)a, p); break;
+    }
+}
+template <typename T>
+__device__ __forceinline__ T norm_finish(T acc, int kind, double p) {
+    switch (kind) {
+        case ZB200_NORM_L1: return acc;
+        case ZB200_NORM_L2: return sqrt(acc);
+        case ZB200_NORM_INF: return acc;
+        default: return (T)pow((double)acc, 1.0 / p);
+    }
+}
+
+template <typename T, typename E>
+__global__ void normalize_kernel(const E* __restrict__ in, long long n_items, int n_modes, long long is,
+                                 long long ms, int kind, double p, E* __restrict__ out) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    T acc = 0;
+    for (int j = 0; j < n_modes; ++j) norm_accum<T>(mag(in[it * is + j * ms]), kind, p, acc);
+    const T nrm = norm_finish<T>(acc, kind, p);
+    for (int j = 0; j < n_modes; ++j) out[it * is + j * ms] = scale(in[it * is + j * ms], nrm);
+}
+
+// ---- rotate: Zc * exp(-i m theta)  (_zmoments.py:377-418) ------------------------------------
+template <typename T>
+__global__ void rotate_kernel(const Cx<T>* __restrict__ in, long long n_items, int n_modes, long long is,
+                              long long ms, const double* __restrict__ fac, Cx<T>* __restrict__ out) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    for (int j = 0; j < n_modes; ++j) {
+        const Cx<T> v = in[it * is + j * ms];
+        const T c = (T)fac[2 * j], s = (T)fac[2 * j + 1];       // exp(-i m theta) = c + i s
+        out[it * is + j * ms] = Cx<T>{v.re * c - v.im * s, v.re * s + v.im * c};
+    }
+}
+
+// ---- n-fold scores on real moments  (_zmoments.py:420-462) -----------------------------------
+template <typename T>
+__global__ void rot_scores_kernel(const T* __restrict__ in, long long n_items, int n_modes, long long is,
+                                  long long ms, const float* __restrict__ w, const unsigned char* __restrict__ sel,
+                                  int n_folds, int kind, T* __restrict__ out, long long ois, long long ofs) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    T s1 = 0, s2 = 0, sm = 0;
+    T num[kMaxFolds];
+    for (int f = 0; f < n_folds; ++f) num[f] = 0;
+    for (int j = 0; j < n_modes; ++j) {
+        if (!sel[j]) continue;
+        const T z = in[it * is + j * ms], z2 = z * z, a = fabs(z);
+        s1 += a;
+        s2 += z2;
+        sm = a > sm ? a : sm;
+        for (int f = 0; f < n_folds; ++f) num[f] += (T)w[f * n_modes + j] * z2;
+    }
+    T den = 1;
+    if (kind == ZB200_NORM_L1) den = s1 * s1;
+    else if (kind == ZB200_NORM_L2) den = s2;
+    else if (kind == ZB200_NORM_INF) den = sm * sm;
+    for (int f = 0; f < n_folds; ++f) out[it * ois + f * ofs] = num[f] / den;
+}
+
+// ---- mirror score: max_theta sum_c Re(Zc^2 e^{-i m_c theta})  (_zmoments.py:464-493) ---------
+// tab[t][c] = (cos(m_c theta_t), sin(m_c theta_t)); eight angles share each pass over the modes.
+template <typename T>
+__global__ void mirror_kernel(const Cx<T>* __restrict__ in, long long n_items, int n_c, long long is,
+                              long long ms, const float2* __restrict__ tab, int n_theta, T* __restrict__ out) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    T best = -INFINITY;
+    for (int t0 = 0; t0 < n_theta; t0 += 8) {
+        T acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0;
+        for (int c = 0; c < n_c; ++c) {
+            const Cx<T> v = in[it * is + c * ms];
+            const T p = v.re * v.re - v.im * v.im, q = (T)2 * v.re * v.im;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (t0 + u < n_theta) {
+                    const float2 cs = __ldg(&tab[(size_t)(t0 + u) * n_c + c]);
+                    acc[u] += p * (T)cs.x + q * (T)cs.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u < n_theta) best = acc[u] > best ? acc[u] : best;
+    }
+    out[it] = best;
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ in, D* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (D)in[i];
+}
+
+int upload_weights(const zb200_plan* p, const float* h_weights, const uint8_t* h_select, int n_folds,
+                   int n_cols, int cols_pad, cudaStream_t s) {
+    ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
+    ZB_CHECK_ARG(h_weights && h_select, "weights/select must not be null");
+    // stage through the plan's pinned buffer so the async copy is truly asynchronous
+    ZB_CUDA(cudaStreamSynchronize(s));   // previous use of the staging buffer has drained
+    float* hw = p->h_pin_w;
+    uint8_t* hs = reinterpret_cast<uint8_t*>(hw + (size_t)kMaxFolds * cols_pad);
+    for (int f = 0; f < n_folds; ++f)
+        for (int c = 0; c < cols_pad; ++c) hw[(size_t)f * cols_pad + c] = c < n_cols ? h_weights[(size_t)f * n_cols + c] : 0.f;
+    for (int c = 0; c < cols_pad; ++c) hs[c] = c < n_cols ? (h_select[c] ? 1 : 0) : 0;
+    ZB_CUDA(cudaMemcpyAsync(p->d_weights, hw, sizeof(float) * n_folds * cols_pad, cudaMemcpyHostToDevice, s));
+    ZB_CUDA(cudaMemcpyAsync(p->d_select, hs, cols_pad, cudaMemcpyHostToDevice, s));
+    return ZB200_OK;
+}
+
+}  // namespace zb200
+
+using namespace zb200;
+
+#define ZB_DISPATCH_DTYPE(dtype, ...)                                         \
+    if ((dtype) == ZB200_F32) { using T = float; __VA_ARGS__ }                \
+    else if ((dtype) == ZB200_F64) { using T = double; __VA_ARGS__ }          \
+    else { set_error("unknown dtype %d", (int)(dtype)); return ZB200_EINVAL; }
+
+extern "C" int zb200_to_complex(int dtype, const void* d_in, int64_t n_items, int64_t iis, int64_t ims,
+                                const int32_t* h_pos, const int32_t* h_neg, int n_c, void* d_out, int64_t ois,
+                                int64_t oms, void* stream) {
+    ZB_CHECK_ARG(d_in && d_out && h_pos && h_neg && n_c > 0 && n_items >= 0, "to_complex: bad arguments");
+    if (n_items == 0) return ZB200_OK;
+    cudaStream_t s = as_stream(stream);
+    Scratch sc(s);
+    std::vector<int32_t> tab(2 * (size_t)n_c);
+    for (int c = 0; c < n_c; ++c) { tab[c] = h_pos[c]; tab[n_c + c] = h_neg[c]; }
+    int rc = sc.upload(tab.data(), tab.size() * sizeof(int32_t));
+    if (rc) return rc;
+    const int* pos = static_cast<const int*>(sc.ptr);
+    ZB_DISPATCH_DTYPE(dtype, {
+        to_complex_kernel<T><<<grid_for(n_items, 256), 256, 0, s>>>(static_cast<const T*>(d_in), n_items, iis, ims, pos,
+                                                                  pos + n_c, n_c, static_cast<Cx<T>*>(d_out), ois, oms);
+    })
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+extern "C" int zb200_to_real(int dtype, const void* d_in, int64_t n_items, int64_t iis, int64_t ims,
+                             const int32_t* h_src, const uint8_t* h_take_imag, int n_r, void* d_out, int64_t ois,
+                             int64_t oms, void* stream) {
+    ZB_CHECK_ARG(d_in && d_out && h_src && h_take_imag && n_r > 0 && n_items >= 0, "to_real: bad arguments");
+    if (n_items == 0) return ZB200_OK;
+    cudaStream_t s = as_stream(stream);
+    Scratch sc(s);
+    std::vector<unsigned char> tab((size_t)n_r * 5);
+    memcpy(tab.data(), h_src, (size_t)n_r * 4);
+    memcpy(tab.data() + (size_t)n_r * 4, h_take_imag, n_r);
+    int rc = sc.upload(tab.data(), tab.size());
+    if (rc) return rc;
+    const int* src = static_cast<const int*>(sc.ptr);
+    const unsigned char* tk = static_cast<const unsigned char*>(sc.ptr) + (size_t)n_r * 4;
+    ZB_DISPATCH_DTYPE(dtype, {
+        to_real_kernel<T><<<grid_for(n_items, 256), 256, 0, s>>>(static_cast<const Cx<T>*>(d_in), n_items, iis, ims, src,
+                                                               tk, n_r, static_cast<T*>(d_out), ois, oms);
+    })
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+extern "C" int zb200_select_modes(int dtype, int is_complex, const void* d_in, int64_t n_items, int64_t iis,
+                                  int64_t ims, const int32_t* h_index, int n_out, void* d_out, int64_t ois,
+                                  int64_t oms, void* stream) {
+    ZB_CHECK_ARG(d_in && d_out && h_index && n_out > 0 && n_items >= 0, "select_modes: bad arguments");
+    if (n_items == 0) return ZB200_OK;
+    cudaStream_t s = as_stream(stream);
+    Scratch sc(s);
+    int rc = sc.upload(h_index, sizeof(int32_t) * n_out);
+    if (rc) return rc;
+    const int* idx = static_cast<const int*>(sc.ptr);
+    ZB_DISPATCH_DTYPE(dtype, {
+        if (is_complex)
+            select_kernel<Cx<T>><<<grid_for(n_items, 256), 256, 0, s>>>(static_cast<const Cx<T>*>(d_in), n_items, iis, ims,
+                                                                      idx, n_out, static_cast<Cx<T>*>(d_out), ois, oms);
+        else
+            select_kernel<T><<<grid_for(n_items, 256), 256, 0, s>>>(static_cast<const T*>(d_in), n_items, iis, ims, idx,
+                                                                  n_out, static_cast<T*>(d_out), ois, oms);
+    })
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+extern "C" int zb200_normalize(int dtype, int is_complex, const void* d_in, int64_t n_items, int n_modes,
+                               int64_t is, int64_t ms, int norm_kind, double order_p, void* d_out, void* stream) {
+    ZB_CHECK_ARG(d_in && d_out && n_modes > 0 && n_items >= 0, "normalize: bad arguments");
+    ZB_CHECK_ARG(norm_kind == ZB200_NORM_L1 || norm_kind == ZB200_NORM_L2 || norm_kind == ZB200_NORM_INF ||
+                     (norm_kind < 0 && order_p > 0),
+                 "normalize: unsupported norm kind %d (p=%g)", norm_kind, order_p);
+    if (n_items == 0) return ZB200_OK;
+    cudaStream_t s = as_stream(stream);
+    ZB_DISPATCH_DTYPE(dtype, {
+        if (is_complex)
+            normalize_kernel<T, Cx<T>><<<grid_for(n_items, 256), 256, 0, s>>>(static_cast<const Cx<T>*>(d_in), n_items,
+                                                                            n_modes, is, ms, norm_kind, order_p,
+                                                                            static_cast<Cx<T>*>(d_out));
+        else
+            normalize_kernel<T, T><<<grid_for(n_items, 256), 256, 0, s>>>(static_cast<const T*>(d_in), n_items, n_modes,
+                                                                        is, ms, norm_kind, order_p, static_cast<T*>(d_out));
+    })
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+extern "C" int zb200_rotate(int dtype, const void* d_in, int64_t n_items, int n_modes, int64_t is, int64_t ms,
+                            const int32_t* h_m, double theta_rad, void* d_out, void* stream) {
+    ZB_CHECK_ARG(d_in && d_out && h_m && n_modes > 0 && n_items >= 0, "rotate: bad arguments");
+    if (n_items == 0) return ZB200_OK;
+    cudaStream_t s = as_stream(stream);
+    std::vector<double> fac(2 * (size_t)n_modes);
+    for (int j = 0; j < n_modes; ++j) {   // exp(-1j * theta * m), _zmoments.py:401
+        fac[2 * j] = cos(-theta_rad * h_m[j]);
+        fac[2 * j + 1] = sin(-theta_rad * h_m[j]);
+    }
+    Scratch sc(s);
+    int rc = sc.upload(fac.data(), fac.size() * sizeof(double));
+    if (rc) return rc;
+    ZB_DISPATCH_DTYPE(dtype, {
+        rotate_kernel<T><<<grid_for(n_items, 256), 256, 0, s>>>(static_cast<const Cx<T>*>(d_in), n_items, n_modes, is, ms,
+                                                              static_cast<const double*>(sc.ptr),
+                                                              static_cast<Cx<T>*>(d_out));
+    })
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+extern "C" int zb200_rot_scores(int dtype, const void* d_in, int64_t n_items, int n_modes, int64_t is, int64_t ms,
+                                const float* h_weights, const uint8_t* h_select, int n_folds, int norm_kind,
+                                void* d_out, int64_t ois, int64_t ofs, void* stream) {
+    ZB_CHECK_ARG(d_in && d_out && h_weights && h_select && n_modes > 0 && n_items >= 0, "rot_scores: bad arguments");
+    ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "rot_scores: n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
+    ZB_CHECK_ARG(norm_kind >= ZB200_NORM_NONE && norm_kind <= ZB200_NORM_INF, "rot_scores: bad norm kind %d", norm_kind);
+    if (n_items == 0) return ZB200_OK;
+    cudaStream_t s = as_stream(stream);
+    const size_t wbytes = sizeof(float) * (size_t)n_folds * n_modes;
+    std::vector<unsigned char> tab(wbytes + n_modes);
+    memcpy(tab.data(), h_weights, wbytes);
+    memcpy(tab.data() + wbytes, h_select, n_modes);
+    Scratch sc(s);
+    int rc = sc.upload(tab.data(), tab.size());
+    if (rc) return rc;
+    const float* w = static_cast<const float*>(sc.ptr);
+    const unsigned char* sel = static_cast<const unsigned char*>(sc.ptr) + wbytes;
+    ZB_DISPATCH_DTYPE(dtype, {
+        rot_scores_kernel<T><<<grid_for(n_items, 128), 128, 0, s>>>(static_cast<const T*>(d_in), n_items, n_modes, is, ms,
+                                                                  w, sel, n_folds, norm_kind, static_cast<T*>(d_out), ois,
+                                                                  ofs);
+    })
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+extern "C" int zb200_mirror_scores(int dtype, const void* d_in, int64_t n_items, int n_c, int64_t is, int64_t ms,
+                                   const int32_t* h_m, const double* h_theta, int n_theta, void* d_out, void* stream) {
+    ZB_CHECK_ARG(d_in && d_out && h_m && h_theta && n_c > 0 && n_theta > 0 && n_items >= 0, "mirror_scores: bad arguments");
+    if (n_items == 0) return ZB200_OK;
+    cudaStream_t s = as_stream(stream);
+    std::vector<float2> tab((size_t)n_theta * n_c);
+    for (int t = 0; t < n_theta; ++t)
+        for (int c = 0; c < n_c; ++c)
+            tab[(size_t)t * n_c + c] = make_float2((float)cos(h_m[c] * h_theta[t]), (float)sin(h_m[c] * h_theta[t]));
+    Scratch sc(s);
+    int rc = sc.upload(tab.data(), tab.size() * sizeof(float2));
+    if (rc) return rc;
+    ZB_DISPATCH_DTYPE(dtype, {
+        mirror_kernel<T><<<grid_for(n_items, 128), 128, 0, s>>>(static_cast<const Cx<T>*>(d_in), n_items, n_c, is, ms,
+                                                              static_cast<const float2*>(sc.ptr), n_theta,
+                                                              static_cast<T*>(d_out));
+    })
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+extern "C" int zb200_cast(int src_dtype, const void* d_in, int dst_dtype, void* d_out, int64_t n, void* stream) {
+    ZB_CHECK_ARG(d_in && d_out && n >= 0, "cast: bad arguments");
+    if (n == 0) return ZB200_OK;
+    cudaStream_t s = as_stream(stream);
+    const unsigned g = grid_for(n, 256);
+    if (src_dtype == ZB200_F32 && dst_dtype == ZB200_F64)
+        cast_kernel<float, double><<<g, 256, 0, s>>>(static_cast<const float*>(d_in), static_cast<double*>(d_out), n);
+    else if (src_dtype == ZB200_F64 && dst_dtype == ZB200_F32)
+        cast_kernel<double, float><<<g, 256, 0, s>>>(static_cast<const double*>(d_in), static_cast<float*>(d_out), n);
+    else {
+        set_error("cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+        return ZB200_EINVAL;
+    }
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}

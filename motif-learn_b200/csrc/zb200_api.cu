@@ -1,0 +1,345 @@
+// C-ABI entry points: plan lifetime, projection / map dispatch, host-buffer pipeline.
+// See include/zernike_b200.h for the contract of every function.
+#include "zb200_common.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+namespace zb200 {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int check_device(int* sms, int* major, int* minor) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return ZB200_ENODEV;
+    }
+    int dev = 0;
+    ZB_CUDA(cudaGetDevice(&dev));
+    ZB_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+    ZB_CUDA(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
+    ZB_CUDA(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return ZB200_OK;
+}
+
+static int alloc_operand(Operand& op, int rows, int k_pad) {
+    op.rows = rows;
+    op.rows_pad = round_up(rows, 16);
+    const size_t bytes = sizeof(float) * (size_t)op.rows_pad * k_pad;
+    ZB_CUDA(cudaMalloc(&op.full, bytes));
+    ZB_CUDA(cudaMalloc(&op.hi, bytes));
+    ZB_CUDA(cudaMalloc(&op.lo, bytes));
+    ZB_CUDA(cudaMalloc(&op.t, bytes));
+    return ZB200_OK;
+}
+static void free_operand(Operand& op) {
+    cudaFree(op.full); cudaFree(op.hi); cudaFree(op.lo); cudaFree(op.t);
+    op = Operand();
+}
+
+}  // namespace zb200
+
+using namespace zb200;
+
+extern "C" int zb200_abi_version(void) { return ZB200_ABI_VERSION; }
+extern "C" const char* zb200_last_error(void) { return g_err; }
+extern "C" int64_t zb200_launch_count(void) { return g_launches.load(); }
+extern "C" void zb200_reset_launch_count(void) { g_launches.store(0); }
+
+extern "C" int zb200_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int s = 0, a = 0, b = 0;
+    int rc = check_device(&s, &a, &b);
+    if (rc) return rc;
+    if (sm_count) *sm_count = s;
+    if (cc_major) *cc_major = a;
+    if (cc_minor) *cc_minor = b;
+    return ZB200_OK;
+}
+
+extern "C" int zb200_num_modes(int n_max) {
+    if (n_max < 0) return ZB200_EINVAL;
+    return (n_max + 1) * (n_max + 2) / 2;
+}
+extern "C" int zb200_num_complex_modes(int n_max) {
+    if (n_max < 0) return ZB200_EINVAL;
+    int c = 0;
+    for (int n = 0; n <= n_max; ++n) c += n / 2 + 1;
+    return c;
+}
+extern "C" int zb200_mode_table(int n_max, int32_t* h_n, int32_t* h_m) {
+    ZB_CHECK_ARG(n_max >= 0 && h_n && h_m, "mode_table: bad arguments");
+    int j = 0;
+    for (int n = 0; n <= n_max; ++n)
+        for (int m = -n; m <= n; m += 2, ++j) { h_n[j] = n; h_m[j] = m; }
+    return j;
+}
+
+extern "C" void zb200_plan_destroy(zb200_plan* p) {
+    if (!p) return;
+    cudaFree(p->basis64);
+    cudaFree(p->d_n);
+    cudaFree(p->d_m);
+    free_operand(p->real);
+    free_operand(p->cplx);
+    cudaFree(p->d_weights);
+    cudaFree(p->d_select);
+    if (p->h_pin_w) cudaFreeHost(p->h_pin_w);
+    for (int i = 0; i < 2; ++i) {
+        if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
+        if (p->pin_out[i]) cudaFreeHost(p->pin_out[i]);
+        cudaFree(p->dev_in[i]);
+        cudaFree(p->dev_out[i]);
+        if (p->io_stream[i]) cudaStreamDestroy(p->io_stream[i]);
+    }
+    delete p;
+}
+
+extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
+    ZB_CHECK_ARG(out_plan, "plan_create: out_plan is null");
+    *out_plan = nullptr;
+    ZB_CHECK_ARG(n_max >= 0, "n_max must be non-negative.");
+    ZB_CHECK_ARG(size > 0, "size must be positive.");
+    ZB_CHECK_ARG(zb200_num_modes(n_max) <= kMaxModes, "n_max=%d gives more than %d modes", n_max, kMaxModes);
+    ZB_CHECK_ARG(size <= 4096, "size=%d too large", size);
+    int sms = 0, major = 0, minor = 0;
+    int rc = check_device(&sms, &major, &minor);
+    if (rc) return rc;
+    zb200_plan* p = new (std::nothrow) zb200_plan();
+    if (!p) { set_error("out of host memory"); return ZB200_ENOMEM; }
+    p->n_max = n_max;
+    p->size = size;
+    p->n_modes = zb200_num_modes(n_max);
+    p->n_complex = zb200_num_complex_modes(n_max);
+    p->kk = size * size;
+    p->k_pad = round_up(p->kk, 32);
+    p->sm_count = sms;
+    p->cc_major = major;
+    cudaGetDevice(&p->device);
+    p->inv_area = 1.0 / (M_PI * (double)size * (double)size / 4.0);    // area = pi k^2/4, _zps.py:154
+    zb200_mode_table(n_max, p->h_n, p->h_m);
+
+#define ZB_PLAN_TRY(expr)                      \
+    do {                                       \
+        int rc__ = (expr);                     \
+        if (rc__) { zb200_plan_destroy(p); return rc__; } \
+    } while (0)
+#define ZB_PLAN_CUDA(call)                                                             \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            set_error("%s failed: %s", #call, cudaGetErrorString(e__));                \
+            zb200_plan_destroy(p);                                                     \
+            return e__ == cudaErrorMemoryAllocation ? ZB200_ENOMEM : ZB200_ECUDA;      \
+        }                                                                              \
+    } while (0)
+
+    ZB_PLAN_CUDA(cudaMalloc(&p->basis64, sizeof(double) * (size_t)p->n_modes * p->kk));
+    ZB_PLAN_CUDA(cudaMalloc(&p->d_n, sizeof(int32_t) * p->n_modes));
+    ZB_PLAN_CUDA(cudaMalloc(&p->d_m, sizeof(int32_t) * p->n_modes));
+    ZB_PLAN_CUDA(cudaMemcpy(p->d_n, p->h_n, sizeof(int32_t) * p->n_modes, cudaMemcpyHostToDevice));
+    ZB_PLAN_CUDA(cudaMemcpy(p->d_m, p->h_m, sizeof(int32_t) * p->n_modes, cudaMemcpyHostToDevice));
+    ZB_PLAN_TRY(alloc_operand(p->real, p->n_modes, p->k_pad));
+    ZB_PLAN_TRY(alloc_operand(p->cplx, 2 * p->n_complex, p->k_pad));
+    const int wcols = p->cplx.rows_pad > p->real.rows_pad ? p->cplx.rows_pad : p->real.rows_pad;
+    ZB_PLAN_CUDA(cudaMalloc(&p->d_weights, sizeof(float) * kMaxFolds * wcols));
+    ZB_PLAN_CUDA(cudaMalloc(&p->d_select, wcols));
+    ZB_PLAN_CUDA(cudaMallocHost(&p->h_pin_w, sizeof(float) * kMaxFolds * wcols + wcols));
+    ZB_PLAN_TRY(launch_basis(p, nullptr));
+    ZB_PLAN_TRY(launch_pack(p, nullptr));
+    ZB_PLAN_CUDA(cudaDeviceSynchronize());
+    ZB_PLAN_TRY(init_tensor_maps(p));
+    *out_plan = p;
+    return ZB200_OK;
+}
+
+extern "C" int zb200_plan_n_max(const zb200_plan* p) { return p ? p->n_max : ZB200_EINVAL; }
+extern "C" int zb200_plan_size(const zb200_plan* p) { return p ? p->size : ZB200_EINVAL; }
+extern "C" const double* zb200_plan_basis_device(const zb200_plan* p) { return p ? p->basis64 : nullptr; }
+extern "C" int zb200_plan_basis_to_host(const zb200_plan* p, double* h_out) {
+    ZB_CHECK_ARG(p && h_out, "plan_basis_to_host: null argument");
+    ZB_CUDA(cudaMemcpy(h_out, p->basis64, sizeof(double) * (size_t)p->n_modes * p->kk, cudaMemcpyDeviceToHost));
+    return ZB200_OK;
+}
+extern "C" int zb200_plan_supports(const zb200_plan* p, int precision) {
+    if (!p) return 0;
+    if (precision == ZB200_PREC_FP32) return 1;
+    if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3) return tc_supported(p) ? 1 : 0;
+    return 0;
+}
+
+// ---- K3 ---------------------------------------------------------------------------------------
+static int project_any(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind,
+                       void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds,
+                       int norm_kind, cudaStream_t s) {
+    if (precision == ZB200_PREC_FP32) {
+        if (out_kind != ZB200_OUT_REAL || d_w) {
+            set_error("the fp32 SIMT projection only produces real moments (out_kind REAL)");
+            return ZB200_EUNSUP;
+        }
+        return project_simt(p, d_patches, n, static_cast<float*>(d_out), s);
+    }
+    if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3) {
+        if (!tc_supported(p)) {
+            set_error("tcgen05 projection unsupported for n_max=%d size=%d on this device (needs sm_100, even size, "
+                      "<=256 operand rows)", p->n_max, p->size);
+            return ZB200_EUNSUP;
+        }
+        return project_tc(p, d_patches, n, precision, out_kind, d_out, d_out2, d_w, d_sel, n_folds, norm_kind, s);
+    }
+    set_error("unknown precision %d", precision);
+    return ZB200_EINVAL;
+}
+
+extern "C" int zb200_project_patches_f32(const zb200_plan* p, const float* d_patches, int64_t n, int precision,
+                                         int out_kind, void* d_out, void* d_out2, void* stream) {
+    ZB_CHECK_ARG(p, "project: plan is null");
+    ZB_CHECK_ARG(n >= 0, "project: negative patch count");
+    ZB_CHECK_ARG(out_kind >= ZB200_OUT_REAL && out_kind <= ZB200_OUT_ABS_PHASE, "project: bad out_kind %d", out_kind);
+    if (n == 0) return ZB200_OK;
+    ZB_CHECK_ARG(d_patches && d_out, "project: null device pointer");
+    ZB_CHECK_ARG(out_kind != ZB200_OUT_ABS_PHASE || d_out2, "project: ABS_PHASE needs d_out2");
+    return project_any(p, d_patches, n, precision, out_kind, d_out, d_out2, nullptr, nullptr, 0, 0, as_stream(stream));
+}
+
+extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float* d_patches, int64_t n,
+                                                int precision, const float* h_weights, const uint8_t* h_select,
+                                                int n_folds, int norm_kind, float* d_scores, void* stream) {
+    ZB_CHECK_ARG(p, "project_scores: plan is null");
+    ZB_CHECK_ARG(n >= 0, "project_scores: negative patch count");
+    ZB_CHECK_ARG(norm_kind >= ZB200_NORM_NONE && norm_kind <= ZB200_NORM_INF, "project_scores: bad norm kind");
+    if (n == 0) return ZB200_OK;
+    ZB_CHECK_ARG(d_patches && d_scores, "project_scores: null device pointer");
+    cudaStream_t s = as_stream(stream);
+    int rc = upload_weights(p, h_weights, h_select, n_folds, p->n_modes, p->real.rows_pad, s);
+    if (rc) return rc;
+    if (precision == ZB200_PREC_FP32) {
+        // SIMT contraction into a temporary, then the score kernel (two launches, no fusion)
+        float* tmp = nullptr;
+        ZB_CUDA(cudaMallocAsync(&tmp, sizeof(float) * (size_t)n * p->n_modes, s));
+        rc = project_simt(p, d_patches, n, tmp, s);
+        if (!rc)
+            rc = zb200_rot_scores(ZB200_F32, tmp, n, p->n_modes, p->n_modes, 1, h_weights, h_select, n_folds,
+                                  norm_kind, d_scores, n_folds, 1, stream);
+        cudaFreeAsync(tmp, s);
+        return rc;
+    }
+    return project_any(p, d_patches, n, precision, ZB200_OUT_REAL, d_scores, nullptr, p->d_weights, p->d_select,
+                       n_folds, norm_kind, s);
+}
+
+// Host-buffer pipeline: chunks of patches flow  host -> (pinned) -> HBM -> kernel -> pinned -> host.
+static int ensure_host_pipeline(zb200_plan* p) {
+    if (p->host_chunk) return ZB200_OK;
+    const int64_t target = 64ll << 20;                        // 64 MiB of patches per chunk
+    int64_t chunk = target / ((int64_t)p->kk * sizeof(float));
+    if (chunk < 256) chunk = 256;
+    for (int i = 0; i < 2; ++i) {
+        ZB_CUDA(cudaMallocHost(&p->pin_in[i], sizeof(float) * chunk * p->kk));
+        ZB_CUDA(cudaMallocHost(&p->pin_out[i], sizeof(float) * chunk * p->n_modes));
+        ZB_CUDA(cudaMalloc(&p->dev_in[i], sizeof(float) * chunk * p->kk));
+        ZB_CUDA(cudaMalloc(&p->dev_out[i], sizeof(float) * chunk * p->n_modes));
+        ZB_CUDA(cudaStreamCreateWithFlags(&p->io_stream[i], cudaStreamNonBlocking));
+    }
+    p->host_chunk = chunk;
+    return ZB200_OK;
+}
+
+extern "C" int zb200_project_patches_host(const zb200_plan* plan, const float* h_patches, int64_t n, int precision,
+                                          double* h_out) {
+    ZB_CHECK_ARG(plan, "project_host: plan is null");
+    ZB_CHECK_ARG(n >= 0, "project_host: negative patch count");
+    if (n == 0) return ZB200_OK;
+    ZB_CHECK_ARG(h_patches && h_out, "project_host: null host pointer");
+    zb200_plan* p = const_cast<zb200_plan*>(plan);
+    int rc = ensure_host_pipeline(p);
+    if (rc) return rc;
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h_patches) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const int64_t chunk = p->host_chunk;
+    const int64_t n_chunks = ceil_div(n, chunk);
+    const int M = p->n_modes;
+    auto drain = [&](int64_t c) -> int {
+        const int b = (int)(c & 1);
+        const int64_t off = c * chunk, cnt = (n - off < chunk) ? n - off : chunk;
+        ZB_CUDA(cudaStreamSynchronize(p->io_stream[b]));
+        const float* src = static_cast<const float*>(p->pin_out[b]);
+        double* dst = h_out + off * M;
+        for (int64_t i = 0; i < cnt * M; ++i) dst[i] = (double)src[i];
+        return ZB200_OK;
+    };
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c & 1);
+        const int64_t off = c * chunk, cnt = (n - off < chunk) ? n - off : chunk;
+        if (c >= 2) { rc = drain(c - 2); if (rc) return rc; }
+        const size_t in_bytes = sizeof(float) * (size_t)cnt * p->kk;
+        const float* src = h_patches + off * p->kk;
+        if (!pinned) {
+            memcpy(p->pin_in[b], src, in_bytes);
+            src = static_cast<const float*>(p->pin_in[b]);
+        }
+        ZB_CUDA(cudaMemcpyAsync(p->dev_in[b], src, in_bytes, cudaMemcpyHostToDevice, p->io_stream[b]));
+        rc = project_any(p, static_cast<const float*>(p->dev_in[b]), cnt, precision, ZB200_OUT_REAL, p->dev_out[b],
+                         nullptr, nullptr, nullptr, 0, 0, p->io_stream[b]);
+        if (rc) return rc;
+        ZB_CUDA(cudaMemcpyAsync(p->pin_out[b], p->dev_out[b], sizeof(float) * (size_t)cnt * M, cudaMemcpyDeviceToHost,
+                                p->io_stream[b]));
+    }
+    for (int64_t c = (n_chunks >= 2 ? n_chunks - 2 : 0); c < n_chunks; ++c) { rc = drain(c); if (rc) return rc; }
+    return ZB200_OK;
+}
+
+// ---- K4 ---------------------------------------------------------------------------------------
+static int check_map_args(const zb200_plan* p, const float* d_img, int H, int W, int row0, int rows) {
+    ZB_CHECK_ARG(p && d_img, "map: null argument");
+    ZB_CHECK_ARG(H >= p->size && W >= p->size,
+                 "For FFT convolution, image size (%dx%d) must be at least as large as polynomial size (%dx%d)", H, W,
+                 p->size, p->size);
+    ZB_CHECK_ARG(row0 >= 0 && rows >= 0 && row0 + rows <= H, "map: row band [%d,%d) outside image of %d rows", row0,
+                 row0 + rows, H);
+    return ZB200_OK;
+}
+
+extern "C" int zb200_moment_map_f32(const zb200_plan* p, const float* d_img, int H, int W, int row0, int rows,
+                                    int precision, float* d_out, void* stream) {
+    int rc = check_map_args(p, d_img, H, W, row0, rows);
+    if (rc) return rc;
+    ZB_CHECK_ARG(d_out || rows == 0, "map: null output");
+    if (precision != ZB200_PREC_FP32) {
+        set_error("dense map: only ZB200_PREC_FP32 is implemented in this build");
+        return ZB200_EUNSUP;
+    }
+    return map_simt(p, d_img, H, W, row0, rows, d_out, nullptr, nullptr, nullptr, 0, 0, as_stream(stream));
+}
+
+extern "C" int zb200_symmetry_map_f32(const zb200_plan* p, const float* d_img, int H, int W, int row0, int rows,
+                                      int precision, const float* h_weights, const uint8_t* h_select, int n_folds,
+                                      int norm_kind, float* d_scores, void* stream) {
+    int rc = check_map_args(p, d_img, H, W, row0, rows);
+    if (rc) return rc;
+    ZB_CHECK_ARG(d_scores || rows == 0, "symmetry map: null output");
+    ZB_CHECK_ARG(norm_kind >= ZB200_NORM_NONE && norm_kind <= ZB200_NORM_INF, "symmetry map: bad norm kind");
+    if (precision != ZB200_PREC_FP32) {
+        set_error("dense map: only ZB200_PREC_FP32 is implemented in this build");
+        return ZB200_EUNSUP;
+    }
+    cudaStream_t s = as_stream(stream);
+    rc = upload_weights(p, h_weights, h_select, n_folds, p->n_modes, p->real.rows_pad, s);
+    if (rc) return rc;
+    return map_simt(p, d_img, H, W, row0, rows, nullptr, d_scores, p->d_weights, p->d_select, n_folds, norm_kind, s);
+}

@@ -1,0 +1,121 @@
+// Shared internals of libzernike_b200.so (sm_100a).  Not part of the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "zernike_b200.h"
+
+namespace zb200 {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define ZB_CHECK_ARG(cond, ...)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            ::zb200::set_error(__VA_ARGS__);                      \
+            return ZB200_EINVAL;                                  \
+        }                                                         \
+    } while (0)
+
+#define ZB_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            ::zb200::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,    \
+                               cudaGetErrorString(e__));                               \
+            return (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver)    \
+                       ? ZB200_ENODEV : ZB200_ECUDA;                                   \
+        }                                                                              \
+    } while (0)
+
+// call after every kernel launch: counts it and surfaces launch-config errors
+#define ZB_LAUNCHED()                                                                  \
+    do {                                                                               \
+        ::zb200::g_launches.fetch_add(1, std::memory_order_relaxed);                   \
+        ZB_CUDA(cudaGetLastError());                                                   \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- the plan: everything cached in HBM for one (n_max, size) -----------------
+// HBM layout (all allocations 256-B aligned by cudaMalloc):
+//   basis64   double [M][k][k]                the reference's ZPs.polynomials
+//   op_full   float  [rows_pad][k_pad]        K-major GEMM operand, value = V/area (fp32 RN)
+//   op_hi     float  [rows_pad][k_pad]        tf32-exact high part  (RN of V/area to 11 bits)
+//   op_lo     float  [rows_pad][k_pad]        tf32-exact low part   (RN of V/area - hi)
+//   op_t      float  [k_pad][rows_pad]        transpose of op_full for the SIMT kernels
+//   two row orders of each: REAL (row r = mode j) and CPLX (row 2c = (n,+m), 2c+1 = (n,-m))
+struct Operand {
+    int rows = 0;        // meaningful rows
+    int rows_pad = 0;    // padded to a multiple of 16 (UMMA N granularity at M=128)
+    float* full = nullptr;
+    float* hi = nullptr;
+    float* lo = nullptr;
+    float* t = nullptr;
+    CUtensorMap tmap_hi;     // TMA descriptors over [rows_pad][k_pad], box 32 x rows_pad/..., SW128
+    CUtensorMap tmap_lo;
+    bool has_tmap = false;
+};
+
+}  // namespace zb200
+
+struct zb200_plan {
+    int n_max = 0;
+    int size = 0;
+    int n_modes = 0;      // M
+    int n_complex = 0;    // Mc
+    int kk = 0;           // k*k
+    int k_pad = 0;        // kk rounded up to 32
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0;
+    double inv_area = 0.0;
+    double* basis64 = nullptr;
+    int32_t* d_n = nullptr;       // device copies of the mode table
+    int32_t* d_m = nullptr;
+    int32_t h_n[1024];
+    int32_t h_m[1024];
+    zb200::Operand real;          // real row order
+    zb200::Operand cplx;          // complex-interleaved row order
+    float* d_weights = nullptr;   // scratch for score weights  [ZB200_MAX_FOLDS][rows_pad]
+    uint8_t* d_select = nullptr;
+    float* h_pin_w = nullptr;     // pinned staging for the two above
+    void* pin_in[2] = {nullptr, nullptr};   // pinned staging for the host entry point
+    void* pin_out[2] = {nullptr, nullptr};
+    void* dev_in[2] = {nullptr, nullptr};
+    void* dev_out[2] = {nullptr, nullptr};
+    cudaStream_t io_stream[2] = {nullptr, nullptr};
+    int64_t host_chunk = 0;
+};
+
+namespace zb200 {
+constexpr int kMaxFolds = 16;
+constexpr int kMaxModes = 1024;   // n_max <= 43
+
+// kernels / launchers implemented across the .cu files
+int launch_basis(zb200_plan* plan, cudaStream_t s);
+int launch_pack(zb200_plan* plan, cudaStream_t s);
+int init_tensor_maps(zb200_plan* plan);
+
+int project_simt(const zb200_plan* plan, const float* d_patches, int64_t n, float* d_out_real, cudaStream_t s);
+int project_tc(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind,
+               void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
+               cudaStream_t s);
+bool tc_supported(const zb200_plan* plan);
+
+int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,
+             float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds,
+             int norm_kind, cudaStream_t s);
+
+int upload_weights(const zb200_plan* plan, const float* h_weights, const uint8_t* h_select, int n_folds,
+                   int n_cols, int cols_pad, cudaStream_t s);
+}  // namespace zb200

@@ -1,0 +1,127 @@
+// K3 (fp32 SIMT variant) -- patch-moment projection with FFMA.
+// Replaces ZPs._transform_dot_product (mtflearn/features/_zps.py:146-157):
+//   Z[N,M] = X[N,k^2] . V[M,k^2]^T / (pi k^2/4)        (1/area is folded into the operand)
+// This is the always-available fp32 path (any k, any n_max) and the on-device cross-check
+// of the tcgen05 kernels; the tensor-core kernels live in zb200_project_tc.cu.
+#include "zb200_common.cuh"
+
+namespace zb200 {
+
+constexpr int PS_BM = 128;   // patches per CTA
+constexpr int PS_BN = 64;    // modes per CTA
+constexpr int PS_BK = 16;    // k-slab
+constexpr int PS_THREADS = 256;
+
+// A: patches [N][kk] (K-major).  Bt: operand [k_pad][rows_pad] (mode-major rows of k).
+// Thread tile 8x4: rows {4*tm+i, 64+4*tm+i}, cols 4*tn+j  -> conflict-free LDS.128.
+template <bool kVecA>
+__global__ void __launch_bounds__(PS_THREADS)
+project_simt_kernel(const float* __restrict__ A, long long n_patches, int kk,
+                    const float* __restrict__ Bt, int rows_pad, int n_modes,
+                    float* __restrict__ C) {
+    __shared__ __align__(16) float As[2][PS_BK][PS_BM];
+    __shared__ __align__(16) float Bs[2][PS_BK][PS_BN];
+
+    const int tid = threadIdx.x;
+    const int tm = tid & 15, tn = tid >> 4;
+    const long long row0 = (long long)blockIdx.x * PS_BM;
+    const int n0 = blockIdx.y * PS_BN;
+
+    // global->smem assignment
+    const int a_row = tid >> 2;          // 0..63 (+64)
+    const int a_kq = (tid & 3) * 4;      // 0,4,8,12
+    const int b_k = tid >> 4;            // 0..15
+    const int b_c = (tid & 15) * 4;      // 0..60
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], rb;
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long r = row0 + a_row + 64 * h;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < n_patches) {
+                const float* src = A + r * (long long)kk + k0 + a_kq;
+                if (kVecA && k0 + a_kq + 3 < kk) {
+                    v = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                    if (k0 + a_kq + 0 < kk) v.x = __ldg(src + 0);
+                    if (k0 + a_kq + 1 < kk) v.y = __ldg(src + 1);
+                    if (k0 + a_kq + 2 < kk) v.z = __ldg(src + 2);
+                    if (k0 + a_kq + 3 < kk) v.w = __ldg(src + 3);
+                }
+            }
+            ra[h] = v;
+        }
+        rb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + b_c < rows_pad)   // rows_pad % 16 == 0 -> whole float4 in range; k rows padded to k_pad
+            rb = __ldg(reinterpret_cast<const float4*>(Bt + (long long)(k0 + b_k) * rows_pad + n0 + b_c));
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            As[buf][a_kq + 0][a_row + 64 * h] = ra[h].x;
+            As[buf][a_kq + 1][a_row + 64 * h] = ra[h].y;
+            As[buf][a_kq + 2][a_row + 64 * h] = ra[h].z;
+            As[buf][a_kq + 3][a_row + 64 * h] = ra[h].w;
+        }
+        *reinterpret_cast<float4*>(&Bs[buf][b_k][b_c]) = rb;
+    };
+
+    const int n_slabs = (kk + PS_BK - 1) / PS_BK;   // k_pad is a multiple of 32 >= kk, Bt rows exist
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    for (int s = 0; s < n_slabs; ++s) {
+        const int buf = s & 1;
+        if (s + 1 < n_slabs) load_tile((s + 1) * PS_BK);
+#pragma unroll
+        for (int q = 0; q < PS_BK; ++q) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][q][4 * tm]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][q][64 + 4 * tm]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][q][4 * tn]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (s + 1 < n_slabs) {
+            store_tile(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long r = row0 + (i < 4 ? 4 * tm + i : 64 + 4 * tm + (i - 4));
+        if (r >= n_patches) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + 4 * tn + j;
+            if (c < n_modes) C[r * n_modes + c] = acc[i][j];
+        }
+    }
+}
+
+int project_simt(const zb200_plan* p, const float* d_patches, int64_t n, float* d_out, cudaStream_t s) {
+    if (n == 0) return ZB200_OK;
+    dim3 grid((unsigned)ceil_div(n, PS_BM), (unsigned)ceil_div(p->real.rows_pad, PS_BN));
+    const bool vec = (p->kk % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_patches) & 15) == 0);
+    if (vec)
+        project_simt_kernel<true><<<grid, PS_THREADS, 0, s>>>(d_patches, (long long)n, p->kk, p->real.t,
+                                                              p->real.rows_pad, p->n_modes, d_out);
+    else
+        project_simt_kernel<false><<<grid, PS_THREADS, 0, s>>>(d_patches, (long long)n, p->kk, p->real.t,
+                                                               p->real.rows_pad, p->n_modes, d_out);
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+}  // namespace zb200

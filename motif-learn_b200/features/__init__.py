@@ -1,0 +1,10 @@
+"""Drop-in subset of ``mtflearn.features`` for the Zernike hot path (features/__init__.py:1-35
+of the reference): same names, same call signatures, CUDA kernels underneath."""
+from ._zps import ZPs
+from ._zmoments import zmoments
+from ._indexing import (construct_complex_matrix, construct_real_matrix, construct_rot_maps_matrix,
+                        nm2j, nm2j_complex)
+from ._keypoint import KeyPoints, clear_border
+
+__all__ = ["ZPs", "zmoments", "construct_rot_maps_matrix", "construct_complex_matrix", "construct_real_matrix",
+           "KeyPoints", "clear_border", "nm2j", "nm2j_complex"]

@@ -1,0 +1,289 @@
+"""``ZPs`` -- Zernike-polynomial transformer backed by sm_100a CUDA kernels.
+
+Host-side mirror of ``mtflearn.features.ZPs`` (mtflearn/features/_zps.py:11-197): same
+constructor arguments, validation messages, attributes (``n_max, size, n, m, polynomials``)
+and methods (``get_polynomials, fit, transform, fit_transform``), still an sklearn
+``BaseEstimator``/``TransformerMixin`` so ``get_params``/``clone``/pipelines keep working.
+
+Where the reference calls ``numpy.dot`` (3-D input) or ``scipy.signal.fftconvolve`` (2-D
+input), this class calls the C ABI of libzernike_b200.so: the basis is generated once in
+fp64 on the GPU and cached in HBM (plan), patch stacks go through the projection kernel,
+images through the sliding-window map kernel.  Extra, keyword-only options:
+
+``precision``  'auto' | 'fp32' | 'tf32x3' | 'tf32' -- arithmetic of the contraction.
+               'auto' picks the fp32-grade tensor-core path when the plan supports it,
+               otherwise the fp32 SIMT kernel.  Stated error bounds: DESIGN.md.
+``output``     'auto' | 'numpy' | 'torch' -- 'auto' returns what it was given: numpy in ->
+               float64 numpy out (like the reference); CUDA tensor in -> float32 CUDA tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import warnings
+from typing import Optional
+
+import numpy as np
+from sklearn.base import BaseEstimator, TransformerMixin
+
+from .. import _lib
+from ._device import is_torch, np_ptr
+from ._zmoments import norm_code, rot_weight_tables, zmoments
+
+def _host_f64(t):
+    """float32 CUDA tensor -> float64 numpy (cast kernel on the GPU, then one D2H copy)."""
+    torch = _lib.require_cuda()
+    wide = torch.empty(t.shape, dtype=torch.float64, device=t.device)
+    _lib.check(_lib.load().zb200_cast(_lib.F32, int(t.data_ptr()), _lib.F64, int(wide.data_ptr()), t.numel(),
+                                      C.c_void_p(_lib.current_stream_ptr())), "cast")
+    return wide.cpu().numpy()
+
+
+_plans: dict = {}
+_plans_lock = threading.Lock()
+
+
+def _plan_for(n_max: int, size: int):
+    """The HBM-resident plan (basis + packed operands) for (n_max, size) on the current device."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    key = (int(n_max), int(size), torch.cuda.current_device())
+    with _plans_lock:
+        plan = _plans.get(key)
+        if plan is None:
+            handle = C.c_void_p()
+            _lib.check(lib.zb200_plan_create(int(n_max), int(size), C.byref(handle)), "plan_create")
+            plan = handle
+            _plans[key] = plan
+    return plan
+
+
+def _mode_table(n_max: int):
+    lib = _lib.load()
+    count = lib.zb200_num_modes(int(n_max))
+    n = np.empty(count, dtype=np.int32)
+    m = np.empty(count, dtype=np.int32)
+    lib.zb200_mode_table(int(n_max), n.ctypes.data_as(C.POINTER(C.c_int32)), m.ctypes.data_as(C.POINTER(C.c_int32)))
+    return n.astype(int), m.astype(int)
+
+
+class ZPs(BaseEstimator, TransformerMixin):
+    """
+    Zernike Polynomials transformer for computing Zernike moments on a B200.
+
+    Parameters
+    ----------
+    n_max : int
+        Maximum radial order.
+    size : int
+        Size of the polynomial grid (size x size).
+    """
+
+    def __init__(self, n_max: int, size: int, *, precision: str = "auto", output: str = "auto"):
+        if n_max < 0:
+            raise ValueError("n_max must be non-negative.")
+        if size <= 0:
+            raise ValueError("size must be positive.")
+        if n_max > size:
+            raise ValueError(
+                f"n_max={n_max} exceeds size={size}. This will produce "
+                f"meaningless results. Use n_max <= {size//2} for accurate moments."
+            )
+        if n_max > size / 2:
+            recommended_max = size // 2
+            warnings.warn(
+                f"n_max={n_max} exceeds recommended limit of size/2≈{recommended_max}. "
+                f"High-order Zernike moments may suffer from aliasing and numerical "
+                f"errors. For accurate results, use n_max <= {size//2}; for maximum "
+                f"stability, use n_max <= {recommended_max}.",
+                UserWarning,
+                stacklevel=2
+            )
+        if precision not in ("auto", "fp32", "tf32", "tf32x3"):
+            raise ValueError("precision must be one of 'auto', 'fp32', 'tf32x3', 'tf32'")
+        if output not in ("auto", "numpy", "torch"):
+            raise ValueError("output must be one of 'auto', 'numpy', 'torch'")
+        self.n_max = n_max
+        self.size = size
+        self.precision = precision
+        self.output = output
+        self.n, self.m = _mode_table(n_max)
+        self._basis_host = None
+
+    # ------------------------------------------------------------------ basis
+    @property
+    def _plan(self):
+        return _plan_for(self.n_max, self.size)
+
+    @property
+    def polynomials(self) -> np.ndarray:
+        """(M, size, size) float64 basis, generated on the GPU (K1) and copied out on first use."""
+        if self._basis_host is None:
+            out = np.empty((len(self.n), self.size, self.size), dtype=np.float64)
+            _lib.check(_lib.load().zb200_plan_basis_to_host(self._plan, np_ptr(out)), "plan_basis_to_host")
+            self._basis_host = out
+        return self._basis_host
+
+    def get_polynomials(self) -> np.ndarray:
+        """Return the generated Zernike polynomials."""
+        return self.polynomials
+
+    def polynomials_device(self):
+        """The fp64 basis as a CUDA tensor (M, size, size)."""
+        torch = _lib.require_cuda()
+        return torch.from_numpy(self.polynomials).cuda()
+
+    # --------------------------------------------------------------- sklearn API
+    def fit(self, X, y: Optional[np.ndarray] = None) -> "ZPs":
+        """Fit method (no-op for compatibility with sklearn)."""
+        return self
+
+    def fit_transform(self, X, y: Optional[np.ndarray] = None) -> zmoments:
+        """Fit and transform (fit is no-op)."""
+        return self.fit(X).transform(X)
+
+    def transform(self, images) -> zmoments:
+        """2-D image -> dense moment map (M,H,W); 3-D patch stack (N,k,k) -> moments (N,M)."""
+        if images.ndim == 2:
+            return self._transform_map(images)
+        if images.ndim == 3:
+            return self._transform_patches(images)
+        raise ValueError("Images must be 2D or 3D array.")
+
+    # ------------------------------------------------------------------ checks
+    def _validate_size(self, images) -> None:
+        if images.ndim == 2:
+            height, width = images.shape
+        elif images.ndim == 3:
+            _, height, width = images.shape
+        else:
+            raise ValueError("Images must be 2D or 3D array.")
+        if images.ndim == 3:
+            if height != self.size or width != self.size:
+                raise ValueError(
+                    f"For batch processing, image size ({height}x{width}) must match "
+                    f"polynomial size ({self.size}x{self.size})"
+                )
+        elif height < self.size or width < self.size:
+            raise ValueError(
+                f"For FFT convolution, image size ({height}x{width}) must be at least "
+                f"as large as polynomial size ({self.size}x{self.size})"
+            )
+
+    def _precision_code(self, for_map: bool = False) -> int:
+        lib = _lib.load()
+        if self.precision == "auto":
+            if not for_map and lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3):
+                return _lib.PREC_TF32X3
+            return _lib.PREC_FP32
+        return _lib.PRECISIONS[self.precision]
+
+    def _want_host(self, given) -> bool:
+        if self.output == "auto":
+            return not (is_torch(given) and given.is_cuda)
+        return self.output == "numpy"
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(_lib.current_stream_ptr())
+
+    # ----------------------------------------------------- K3: patch projection
+    def _transform_patches(self, images) -> zmoments:
+        self._validate_size(images)
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        n_img = int(images.shape[0])
+        n_modes = len(self.n)
+        host_in = not is_torch(images)
+        if host_in and self._want_host(images):
+            # the numpy user's call: host buffers in, float64 host buffer out, chunked
+            # H2D/kernel/D2H pipeline inside the library
+            src = np.ascontiguousarray(images, dtype=np.float32)
+            out = np.empty((n_img, n_modes), dtype=np.float64)
+            _lib.check(lib.zb200_project_patches_host(self._plan, np_ptr(src), n_img, self._precision_code(),
+                                                      np_ptr(out)), "project_patches_host")
+            return zmoments(data=out, n=self.n, m=self.m, patch_size=self.size)
+        dev = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32)).cuda() if host_in else images
+        dev = dev.to(device="cuda", dtype=torch.float32).contiguous()
+        out = torch.empty((n_img, n_modes), dtype=torch.float32, device=dev.device)
+        _lib.check(lib.zb200_project_patches_f32(self._plan, int(dev.data_ptr()), n_img, self._precision_code(),
+                                                 _lib.OUT_REAL, int(out.data_ptr()), None, self._stream()),
+                   "project_patches")
+        data = _host_f64(out) if self._want_host(images) else out
+        return zmoments(data=data, n=self.n, m=self.m, patch_size=self.size)
+
+    def transform_features(self, images, kind: str = "abs"):
+        """Fused projection epilogues on a CUDA patch stack (tensor-core path only).
+
+        kind='complex' -> complex64 (N,Mc); 'abs' -> |Zc| (N,Mc) the rotation-invariant
+        features of notebook "2 How to use ZPs" cell 13; 'abs_phase' -> (|Zc|, angle(Zc))."""
+        self._validate_size(images)
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        code = {"complex": _lib.OUT_COMPLEX, "abs": _lib.OUT_ABS, "abs_phase": _lib.OUT_ABS_PHASE}[kind]
+        prec = self._precision_code()
+        if prec == _lib.PREC_FP32:
+            zc = self._transform_patches(images).to_complex()
+            if kind == "complex":
+                return zc.data
+            data = zc.data if is_torch(zc.data) else torch.from_numpy(zc.data)
+            return data.abs() if kind == "abs" else (data.abs(), data.angle())
+        dev = images if is_torch(images) else torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
+        dev = dev.to(device="cuda", dtype=torch.float32).contiguous()
+        n_img, n_c = int(dev.shape[0]), lib.zb200_num_complex_modes(self.n_max)
+        out2 = None
+        if kind == "complex":
+            out = torch.empty((n_img, n_c), dtype=torch.complex64, device=dev.device)
+        else:
+            out = torch.empty((n_img, n_c), dtype=torch.float32, device=dev.device)
+            if kind == "abs_phase":
+                out2 = torch.empty_like(out)
+        _lib.check(lib.zb200_project_patches_f32(self._plan, int(dev.data_ptr()), n_img, prec, code,
+                                                 int(out.data_ptr()), None if out2 is None else int(out2.data_ptr()),
+                                                 self._stream()), "project_patches")
+        return out if out2 is None else (out, out2)
+
+    # ------------------------------------------------------------ K4: dense map
+    def _image_on_device(self, image):
+        torch = _lib.require_cuda()
+        if is_torch(image):
+            return image.to(device="cuda", dtype=torch.float32).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).cuda()
+
+    def _transform_map(self, image, row0: int = 0, rows: Optional[int] = None) -> zmoments:
+        self._validate_size(image)
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = self._image_on_device(image)
+        h, w = int(dev.shape[0]), int(dev.shape[1])
+        rows = h - row0 if rows is None else rows
+        out = torch.empty((len(self.n), rows, w), dtype=torch.float32, device=dev.device)
+        _lib.check(lib.zb200_moment_map_f32(self._plan, int(dev.data_ptr()), h, w, row0, rows,
+                                            self._precision_code(for_map=True), int(out.data_ptr()), self._stream()),
+                   "moment_map")
+        data = _host_f64(out) if self._want_host(image) else out
+        return zmoments(data=data, n=self.n, m=self.m, patch_size=self.size)
+
+    def symmetry_map(self, image, n_folds, p=2, m_unselect=None, row0: int = 0, rows: Optional[int] = None):
+        """Fused ``transform(image).rot_maps(n_folds, p, m_unselect)`` that never writes the
+        (M,H,W) moment maps to HBM.  Returns (F, rows, W); ``row0/rows`` select a row band
+        (image-tile sharding across GPUs)."""
+        if image.ndim != 2:
+            raise ValueError("Images must be 2D or 3D array.")
+        self._validate_size(image)
+        if m_unselect is None:
+            m_unselect = (0, 1)
+        elif 0 not in m_unselect:
+            raise ValueError("m=0 must be included in m_unselect.")
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = self._image_on_device(image)
+        h, w = int(dev.shape[0]), int(dev.shape[1])
+        rows = h - row0 if rows is None else rows
+        wts, sel = rot_weight_tables(self.m, n_folds, m_unselect)
+        out = torch.empty((wts.shape[0], rows, w), dtype=torch.float32, device=dev.device)
+        _lib.check(lib.zb200_symmetry_map_f32(self._plan, int(dev.data_ptr()), h, w, row0, rows,
+                                              self._precision_code(for_map=True), np_ptr(wts), np_ptr(sel),
+                                              wts.shape[0], norm_code(p), int(out.data_ptr()), self._stream()),
+                   "symmetry_map")
+        return _host_f64(out) if self._want_host(image) else out

@@ -129,29 +129,31 @@ def zernike_basis(n_max: int, size: int):
     return n_arr, m_arr, planes
 
 
-def zernike_basis_exact(n_max: int, size: int):
-    """Same basis with EXACT integer coefficients (Python ints) and Horner
-    evaluation in rho^2 -- an independent accuracy yardstick (not the reference
-    algorithm): shows which of {reference, GPU recurrence} is closer to truth."""
+def zernike_basis_exact(n_max: int, size: int, points):
+    """V[:, y, x] at the given (row, col) points with the radial polynomial
+    evaluated EXACTLY (integer coefficients, rational arithmetic on the float64
+    rho, one final rounding).  Not the reference algorithm: an independent
+    yardstick that shows which of {reference power sum, GPU recurrence} is closer
+    to the true polynomial.  Slow -- sampled points only."""
+    from fractions import Fraction
     rho, theta = _grid(size)
-    inside = rho <= 1
-    r2 = rho * rho
     n_arr, m_arr = mode_table(n_max)
-    planes = np.empty((len(n_arr), size, size), dtype=np.float64)
-    for j, (n, m) in enumerate(zip(n_arr.tolist(), m_arr.tolist())):
-        am = abs(m)
-        half = (n - am) // 2
-        # R = rho^am * sum_{s} c_s rho^{2(half-s)}
-        coeffs = [(-1) ** s * math.factorial(n - s)
-                  // (math.factorial(s) * math.factorial((n + am) // 2 - s) * math.factorial(half - s))
-                  for s in range(half + 1)]
-        acc = np.zeros_like(rho)
-        for c in coeffs:            # Horner, highest power first
-            acc = acc * r2 + float(c)
-        rad = acc * rho ** am * math.sqrt(2 * (n + 1) / (1 + (m == 0)))
-        rad = np.where(inside, rad, 0)
-        planes[j] = rad * (np.sin(am * theta) if m < 0 else np.cos(am * theta))
-    return n_arr, m_arr, planes
+    out = np.zeros((len(n_arr), len(points)), dtype=np.float64)
+    for col, (r, c) in enumerate(points):
+        if not rho[r, c] <= 1:
+            continue
+        fr = Fraction(float(rho[r, c]))
+        for j, (n, m) in enumerate(zip(n_arr.tolist(), m_arr.tolist())):
+            am = abs(m)
+            half = (n - am) // 2
+            tot = Fraction(0)
+            for s in range(half + 1):
+                coef = ((-1) ** s * math.factorial(n - s)
+                        // (math.factorial(s) * math.factorial((n + am) // 2 - s) * math.factorial(half - s)))
+                tot += coef * fr ** (n - 2 * s)
+            rad = float(tot) * math.sqrt(2 * (n + 1) / (1 + (m == 0)))
+            out[j, col] = rad * (math.sin(am * theta[r, c]) if m < 0 else math.cos(am * theta[r, c]))
+    return n_arr, m_arr, out
 
 
 # --------------------------------------------------------------------------- #

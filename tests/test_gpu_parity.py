@@ -1,0 +1,338 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors
+of the live reference.  Runs on the B200 box: ``pytest -m gpu``.
+
+Tolerances (DESIGN.md "Numerics"):
+  * basis (fp64)            |ours - ref| <= 5e-12 (n_max<=12), 1e-8 (n_max=20: the REFERENCE's own
+                            float-factorial error, ours is 2e-14 from exact)
+  * fp32-grade contraction  allclose(rtol=1e-4, atol=1e-6*max|ref|)      (fp32 SIMT, tf32x3)
+  * 1xTF32 contraction      |err| <= 1e-3*max|ref|                        (stated bound, fast mode)
+  * n-fold scores           |err| <= 1e-5 (fp32-grade) on items with non-zero norm, NaN pattern equal
+  * gather / index work     bit-exact
+"""
+import hashlib
+import warnings
+
+import numpy as np
+import pytest
+
+import zernike_oracle as zo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def api():
+    from motif_learn_b200 import features
+    return features
+
+
+def fp32_close(got, ref, rtol=1e-4, scale=1e-6):
+    ref = np.asarray(ref)
+    np.testing.assert_allclose(np.asarray(got), ref, rtol=rtol, atol=scale * np.abs(ref).max())
+
+
+def precisions(api, n_max, size):
+    from motif_learn_b200 import _lib
+    z = api.ZPs(n_max, size)
+    out = ["fp32"]
+    if _lib.load().zb200_plan_supports(z._plan, _lib.PREC_TF32X3):
+        out += ["tf32x3", "tf32"]
+    return out
+
+
+# ---- K1 basis ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_max,size,tol", [(4, 8, 1e-13), (6, 9, 1e-13), (5, 11, 1e-13), (10, 32, 2e-12),
+                                            (12, 48, 5e-12), (12, 64, 5e-12), (20, 64, 1e-8), (12, 33, 5e-12),
+                                            (0, 1, 0), (3, 5, 1e-13)])
+def test_basis_vs_oracle(api, n_max, size, tol):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        z = api.ZPs(n_max, size)
+    n, m, ref = zo.zernike_basis(n_max, size)
+    got = z.polynomials
+    assert got.shape == ref.shape and got.dtype == np.float64
+    np.testing.assert_array_equal(z.n, n)
+    np.testing.assert_array_equal(z.m, m)
+    np.testing.assert_array_equal(got == 0, ref == 0)
+    assert np.abs(got - ref).max() <= tol
+
+
+def test_basis_golden_and_exact(api, golden):
+    g = golden("basis.npz")
+    np.testing.assert_allclose(api.ZPs(10, 32).polynomials, g["full_10_32"], rtol=0, atol=2e-12)
+    for n_max, size, tol in [(12, 48, 5e-12), (12, 64, 5e-12), (20, 64, 1e-8)]:
+        flat = api.ZPs(n_max, size).polynomials.ravel()
+        np.testing.assert_allclose(flat[g[f"idx_{n_max}_{size}"]], g[f"val_{n_max}_{size}"], rtol=0, atol=tol)
+    # SURVEY 8c known answers of the reference
+    p = api.ZPs(10, 32).polynomials
+    assert abs(p.sum() - 430.9346046698769) < 1e-8 and abs(p[4, 16, 16] + 1.7248414389629714) < 1e-12
+    assert np.count_nonzero(p[0]) == 740 and np.all(p[0][p[0] != 0] == 1.0)
+    # closer to the exact polynomial than the reference algorithm itself
+    pts = [(r, c) for r in range(1, 64, 8) for c in range(3, 64, 10)]
+    _, _, ex = zo.zernike_basis_exact(20, 64, pts)
+    got = api.ZPs(20, 64).polynomials
+    assert max(np.abs(got[:, r, c] - ex[:, i]).max() for i, (r, c) in enumerate(pts)) < 1e-12
+
+
+# ---- K2 gather -----------------------------------------------------------------------------------
+def test_gather_golden(api, golden, torch):
+    g = golden("lattice.npz")
+    img, pts = g["img"], g["pts"]
+    for k in (32, 33):
+        kp = api.KeyPoints(pts, img, k)
+        np.testing.assert_array_equal(kp.pts, g[f"kept_{k}"])
+        patches = kp.extract_patches()
+        assert patches.dtype == np.float32 and patches.shape == (len(kp.pts), k, k)
+        assert hashlib.sha256(np.ascontiguousarray(patches).tobytes()).hexdigest()[:16] == str(g[f"patch_sha_{k}"])
+        np.testing.assert_array_equal(patches, zo.extract_patches(img, kp.pts, k))
+    flat = api.KeyPoints(pts, img, 32).extract_patches(flat=True)
+    np.testing.assert_array_equal(flat.shape, g["flat_shape_32"])
+    # device-resident image keeps the result in HBM; half-to-even rounding of .5 coordinates
+    dimg = torch.from_numpy(img).cuda()
+    odd = np.array([[40.5, 41.5], [100.5, 64.5], [77.49999, 90.50001]])
+    kp = api.KeyPoints(odd, dimg, 16)
+    out = kp.extract_patches()
+    assert out.is_cuda
+    np.testing.assert_array_equal(out.cpu().numpy(), zo.extract_patches(img, odd, 16))
+    empty = api.KeyPoints(np.zeros((0, 2)), img, 16).extract_patches()
+    assert empty.shape == (0, 16, 16)
+
+
+# ---- K3 projection ---------------------------------------------------------------------------------
+def test_projection_golden(api, golden):
+    g = golden("patches_nfold.npz")
+    p = g["patches"]
+    for n_max, key in [(12, "z12_data"), (20, "z20_data")]:
+        for prec in precisions(api, n_max, 64):
+            got = api.ZPs(n_max, 64, precision=prec).transform(p)
+            assert got.data.dtype == np.float64 and got.data.shape == g[key].shape
+            if prec == "tf32":
+                assert np.abs(got.data - g[key]).max() <= 1e-3 * np.abs(g[key]).max()
+            else:
+                fp32_close(got.data, g[key])
+    got = api.ZPs(12, 64).fit_transform(p)
+    np.testing.assert_allclose(got.data[0, :4], [2.985956997797e-01, 6.946528841105e-03, 6.458243044575e-03,
+                                                 2.461357425825e-03], rtol=1e-4)
+
+
+def test_projection_config1_vs_oracle(api, torch):
+    """BASELINE config 1: ZPs(n_max=10) on 10,000 32x32 patches of a hexagonal lattice."""
+    from motif_learn_b200.datasets import honeycomb_image
+    img, pts = honeycomb_image(1536, bond=12.0, seed=0)
+    patches = api.KeyPoints(pts, img, 32).extract_patches()[:10000]
+    assert patches.shape == (10000, 32, 32)
+    _, _, v = zo.zernike_basis(10, 32)
+    ref = zo.project_patches(patches.astype(np.float64), v)
+    for prec in precisions(api, 10, 32):
+        z = api.ZPs(10, 32, precision=prec)
+        host = z.transform(patches).data                                   # host pipeline (chunked)
+        dev = z.transform(torch.from_numpy(patches).cuda()).data            # device-resident
+        assert dev.is_cuda and dev.dtype == torch.float32
+        for got in (host, dev.cpu().numpy()):
+            if prec == "tf32":
+                assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max()
+            else:
+                fp32_close(got, ref)
+
+
+@pytest.mark.parametrize("n_max,size,count", [(12, 64, 1000), (20, 64, 300), (8, 33, 257), (3, 6, 5), (12, 48, 129),
+                                              (0, 4, 3), (21, 64, 130), (23, 64, 100)])
+def test_projection_shapes_vs_oracle(api, n_max, size, count):
+    rng = np.random.default_rng(n_max * 100 + size)
+    patches = rng.random((count, size, size), dtype=np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, _, v = zo.zernike_basis(n_max, size)
+        ref = zo.project_patches(patches.astype(np.float64), v)
+        for prec in precisions(api, n_max, size):
+            got = api.ZPs(n_max, size, precision=prec).transform(patches).data
+            if prec == "tf32":
+                assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max()
+            else:
+                fp32_close(got, ref, rtol=2e-4, scale=2e-6)
+
+
+def test_projection_edge_cases(api, torch):
+    z = api.ZPs(4, 8)
+    out = z.transform(np.zeros((0, 8, 8), dtype=np.float32))
+    assert out.data.shape == (0, 15)
+    one = z.transform(np.ones((1, 8, 8), dtype=np.float64))        # float64 input is accepted
+    _, _, v = zo.zernike_basis(4, 8)
+    fp32_close(one.data, zo.project_patches(np.ones((1, 8, 8)), v))
+    # linearity on the device path (size-independent property)
+    rng = np.random.default_rng(5)
+    a = torch.from_numpy(rng.random((300, 8, 8), dtype=np.float32)).cuda()
+    b = torch.from_numpy(rng.random((300, 8, 8), dtype=np.float32)).cuda()
+    za, zb, zab = (z.transform(t).data for t in (a, b, 2 * a - 3 * b))
+    assert (zab - (2 * za - 3 * zb)).abs().max().item() < 1e-5
+
+
+def test_fused_epilogues(api, golden, torch):
+    g = golden("patches_nfold.npz")
+    p = torch.from_numpy(g["patches"]).cuda()
+    for n_max, cabs in [(12, np.abs(g["z12_cdata"])), (20, g["z20_cabs"])]:
+        for prec in precisions(api, n_max, 64):
+            z = api.ZPs(n_max, 64, precision=prec)
+            tol = 1e-3 if prec == "tf32" else 2e-6
+            got = z.transform_features(p, "abs").cpu().numpy()
+            assert np.abs(got - cabs).max() <= tol * cabs.max()
+            zc = z.transform_features(p, "complex").cpu().numpy()
+            if n_max == 12:
+                assert np.abs(zc - g["z12_cdata"]).max() <= tol * cabs.max()
+            mag, ang = z.transform_features(p, "abs_phase")
+            rebuilt = (mag * torch.exp(1j * ang)).cpu().numpy()
+            assert np.abs(rebuilt - zc).max() <= 10 * tol * cabs.max()
+
+
+# ---- zmoments algebra --------------------------------------------------------------------------------
+def test_algebra_float64_matches_reference_golden(api, golden):
+    """numpy float64 in -> float64 kernels -> numpy out: matches the live reference tightly."""
+    g = golden("patches_nfold.npz")
+    n, m = zo.mode_table(12)
+    z = api.zmoments(g["z12_data"], n, m, patch_size=64)
+    zc = z.to_complex()
+    assert zc.is_complex and zc.data.dtype == np.complex128
+    np.testing.assert_array_equal(zc.n, g["z12_cn"])
+    np.testing.assert_array_equal(zc.m, g["z12_cm"])
+    np.testing.assert_allclose(zc.data, g["z12_cdata"], rtol=1e-14, atol=0)
+    assert zc.to_complex() is zc and z.to_real() is z
+    back = zc.to_real()
+    np.testing.assert_array_equal(back.m, m)
+    np.testing.assert_allclose(back.data, g["z12_real_back"], rtol=1e-14, atol=0)
+    np.testing.assert_allclose(z.normalize().data, g["z12_norm2"], rtol=1e-13)
+    np.testing.assert_allclose(z.normalize(order=1).data, g["z12_norm1"], rtol=1e-13)
+    np.testing.assert_allclose(z.normalize(order=np.inf).data, g["z12_norminf"], rtol=1e-13)
+    np.testing.assert_allclose(z.normalize(order=3).data, zo.normalize(g["z12_data"], 3), rtol=1e-12)
+    np.testing.assert_allclose(z.rotate(30.0).data, g["z12_rot30"], rtol=1e-12, atol=1e-16)
+    np.testing.assert_allclose(z.rot_maps([2, 3, 4, 6]), g["z12_rot"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(z.rot_maps([3, 6], p=1), g["z12_rot_p1"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(z.rot_maps([2, 4], m_unselect=(0, 1, 2)), g["z12_rot_unsel"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(z.rot_maps([2, 3], p=None), zo.rot_maps(g["z12_data"], n, m, [2, 3], p=None),
+                               rtol=1e-11, atol=1e-16)
+    np.testing.assert_allclose(z.rot_maps([2, 3], p=np.inf), zo.rot_maps(g["z12_data"], n, m, [2, 3], p=np.inf),
+                               rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(z.mirror_map(), g["z12_mirror"], rtol=1e-6)      # float32 cos/sin table
+    sel = z.select([2, -3])
+    np.testing.assert_array_equal(sel.m, g["z12_sel_m"])
+    np.testing.assert_array_equal(sel.data, g["z12_sel_data"])
+    uns = z.unselect([0, 1])
+    np.testing.assert_array_equal(uns.m, g["z12_unsel_m"])
+    np.testing.assert_array_equal(uns.n, g["z12_unsel_n"])
+    # complex normalisation and zero-norm -> NaN like numpy
+    np.testing.assert_allclose(zc.normalize().data, zo.normalize(g["z12_cdata"]), rtol=1e-13)
+    zero = api.zmoments(np.zeros((2, len(n))), n, m)
+    assert np.isnan(zero.rot_maps([3])).all() and np.isnan(zero.normalize().data).all()
+
+
+def test_algebra_device_float32_and_planar_layout(api, golden, torch):
+    g = golden("lattice.npz")
+    n, m = zo.mode_table(10)
+    ref = g["z10_data"]
+    z = api.zmoments(torch.from_numpy(ref.astype(np.float32)).cuda(), n, m, patch_size=32)
+    zc = z.to_complex()
+    assert zc.data.is_cuda and zc.data.dtype == torch.complex64
+    assert np.abs(zc.data.cpu().numpy() - g["z10_cdata"]).max() < 1e-6
+    rot = z.rot_maps([2, 3, 4, 6])
+    assert rot.is_cuda and np.abs(rot.cpu().numpy() - g["z10_rot"]).max() < 1e-5
+    # same data laid out as a (M, H, W) map: 96 patches -> an 8 x 12 "image"
+    planar = np.ascontiguousarray(ref.T.reshape(len(n), 8, 12))
+    zp = api.zmoments(planar, n, m, patch_size=32)
+    np.testing.assert_allclose(zp.rot_maps([2, 3, 4, 6]), g["z10_rot"].T.reshape(4, 8, 12), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(zp.to_complex().data, g["z10_cdata"].T.reshape(-1, 8, 12), rtol=1e-14)
+    np.testing.assert_allclose(zp.mirror_map(), zo.mirror_map(planar, n, m), rtol=1e-6)
+    np.testing.assert_allclose(zp.to_complex().to_real().data, planar, rtol=1e-14)
+    assert zp.valid_mask.shape == (8, 12)
+    # ctor permutation on device data
+    perm = np.random.default_rng(0).permutation(len(n))
+    zs = api.zmoments(z.data[:, torch.from_numpy(perm).cuda()], n[perm], m[perm])
+    np.testing.assert_array_equal(zs.m, m)
+    assert torch.equal(zs.data, z.data)
+
+
+# ---- K4 dense map --------------------------------------------------------------------------------------
+def test_map_golden(api, golden, torch):
+    g = golden("lattice.npz")
+    img = g["map_img"]
+    z = api.ZPs(12, 48)
+    zm = z.transform(img)
+    assert zm.data.shape == (91, 160, 192) and zm.data.dtype == np.float64
+    ys, xs = g["map_ys"], g["map_xs"]
+    fp32_close(zm.data[:, ys, xs], g["map_moments"])
+    np.testing.assert_array_equal(zm.valid_mask, g["map_valid"])
+    rot = zm.rot_maps([2, 3, 4, 6])
+    assert np.abs(rot - g["map_rot"]).max() < 1e-5
+    assert np.abs(np.abs(zm.to_complex().data)[:, ys, xs] - g["map_cabs_pts"]).max() < 1e-6
+    assert np.abs(zm.mirror_map()[ys, xs] - g["map_mirror_pts"]).max() < 1e-5
+    # fused map -> scores (never materialises the moments)
+    fused = z.symmetry_map(img, [2, 3, 4, 6])
+    assert fused.shape == (4, 160, 192) and np.abs(fused - g["map_rot"]).max() < 1e-5
+    assert np.abs(z.symmetry_map(img, [3, 6], p=1) - zo.rot_maps(zm.data, z.n, z.m, [3, 6], p=1)).max() < 1e-5
+    # row bands (image-tile sharding) reproduce the full result exactly
+    dimg = torch.from_numpy(img.astype(np.float32)).cuda()
+    full = z.symmetry_map(dimg, [2, 3, 4, 6])
+    parts = [z.symmetry_map(dimg, [2, 3, 4, 6], row0=r0, rows=r) for r0, r in [(0, 50), (50, 37), (87, 73)]]
+    assert torch.equal(torch.cat(parts, dim=1), full)
+    band = z._transform_map(dimg, row0=100, rows=9).data
+    assert torch.equal(band, z.transform(dimg).data[:, 100:109])
+
+
+def test_map_odd_window_golden(api, golden):
+    g = golden("lattice.npz")
+    img = g["map2_img"]
+    z = api.ZPs(8, 33)
+    zm = z.transform(img)
+    fp32_close(zm.data[:, ::7, ::5], g["map2_moments"])
+    assert np.abs(zm.rot_maps([3, 6]) - g["map2_rot"]).max() < 1e-5
+    assert np.abs(z.symmetry_map(img, [3, 6]) - g["map2_rot"]).max() < 1e-5
+    np.testing.assert_array_equal(zm.valid_mask, g["map2_valid"])
+
+
+def test_map_vs_oracle_fft_nonmultiple_width(api):
+    """Width not a multiple of the 128-pixel tile nor of 4; zero-norm pixels give NaN scores."""
+    from motif_learn_b200.datasets import honeycomb_image
+    img, _ = honeycomb_image((150, 203), bond=12.0, seed=4, angle=11.0, vacancy_frac=0.02)
+    img[:, 150:] = 0.0                                   # a dead region: windows there are all-zero
+    n, m, v = zo.zernike_basis(6, 20)
+    z = api.ZPs(6, 20)
+    ref = zo.moment_map_fft(img.astype(np.float64), v, n)
+    fp32_close(z.transform(img).data, ref)
+    got = z.symmetry_map(img, [2, 3, 6])
+    want = zo.rot_maps(zo.moment_map_direct(img.astype(np.float64), v), n, m, [2, 3, 6])
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    assert np.isnan(want).any()
+    ok = ~np.isnan(want) & (np.abs(ref[3:]).sum(axis=0) > 1e-3)[None]
+    assert np.abs(got - want)[ok].max() < 1e-4
+
+
+def test_map_equals_gather_plus_projection_at_config2_size(api, torch):
+    """BASELINE config 2 geometry (2048x2048, n_max=12, 48-px window): the dense map at a pixel
+    equals the projection of the patch gathered at that pixel (K4 == K2+K3), everywhere incl.
+    tile seams, and the fused scores equal rot_maps of those projections."""
+    from motif_learn_b200.datasets import honeycomb_image
+    img, _ = honeycomb_image(2048, bond=12.0, seed=0)
+    dimg = torch.from_numpy(img).cuda()
+    z = api.ZPs(12, 48, precision="fp32")
+    scores = z.symmetry_map(dimg, [2, 3, 4, 6])
+    assert scores.shape == (4, 2048, 2048)
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([rng.integers(30, 2018, 400), [127, 128, 129, 1023, 1024, 2000]])
+    ys = np.concatenate([rng.integers(30, 2018, 400), [127, 128, 129, 1023, 1024, 2000]])
+    pts = np.stack([xs, ys], axis=1).astype(np.float64)
+    patches = zo.extract_patches(img, pts, 48)
+    n, m, v = zo.zernike_basis(12, 48)
+    zref = zo.project_patches(patches.astype(np.float64), v)
+    want = zo.rot_maps(zref, n, m, [2, 3, 4, 6])
+    got = scores[:, torch.from_numpy(ys).cuda(), torch.from_numpy(xs).cuda()].cpu().numpy().T
+    assert np.abs(got - want).max() < 1e-5
+    band = z._transform_map(dimg, row0=1000, rows=48).data
+    sel = (ys >= 1000) & (ys < 1048)
+    if sel.any():
+        gotm = band[:, torch.from_numpy(ys[sel] - 1000).cuda(), torch.from_numpy(xs[sel]).cuda()].cpu().numpy().T
+        fp32_close(gotm, zref[sel])
