@@ -38,7 +38,7 @@ SIGNATURES = {
     "zb200_device_info": (_int, [C.POINTER(_int)] * 3),
     "zb200_launch_count": (_i64, []),
     "zb200_reset_launch_count": (None, []),
-    "zb200_plan_supports": (_int, [_vp, _int]),
+    "zb200_plan_supports": (_int, [_vp, _int, _int]),
     "zb200_num_modes": (_int, [_int]),
     "zb200_num_complex_modes": (_int, [_int]),
     "zb200_mode_table": (_int, [_int, _i32p, _i32p]),

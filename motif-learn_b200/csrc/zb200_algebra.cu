@@ -117,7 +117,7 @@ __global__ void rotate_kernel(const Cx<T>* __restrict__ in, long long n_items, i
 // ---- n-fold scores on real moments  (_zmoments.py:420-462) -----------------------------------
 template <typename T>
 __global__ void rot_scores_kernel(const T* __restrict__ in, long long n_items, int n_modes, long long is,
-                                  long long ms, const float* __restrict__ w, const unsigned char* __restrict__ sel,
+                                  long long ms, const double* __restrict__ w, const unsigned char* __restrict__ sel,
                                   int n_folds, int kind, T* __restrict__ out, long long ois, long long ofs) {
     const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n_items) return;
@@ -308,21 +308,21 @@ extern "C" int zb200_rotate(int dtype, const void* d_in, int64_t n_items, int n_
 }
 
 extern "C" int zb200_rot_scores(int dtype, const void* d_in, int64_t n_items, int n_modes, int64_t is, int64_t ms,
-                                const float* h_weights, const uint8_t* h_select, int n_folds, int norm_kind,
+                                const double* h_weights, const uint8_t* h_select, int n_folds, int norm_kind,
                                 void* d_out, int64_t ois, int64_t ofs, void* stream) {
     ZB_CHECK_ARG(d_in && d_out && h_weights && h_select && n_modes > 0 && n_items >= 0, "rot_scores: bad arguments");
     ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "rot_scores: n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
     ZB_CHECK_ARG(norm_kind >= ZB200_NORM_NONE && norm_kind <= ZB200_NORM_INF, "rot_scores: bad norm kind %d", norm_kind);
     if (n_items == 0) return ZB200_OK;
     cudaStream_t s = as_stream(stream);
-    const size_t wbytes = sizeof(float) * (size_t)n_folds * n_modes;
+    const size_t wbytes = sizeof(double) * (size_t)n_folds * n_modes;
     std::vector<unsigned char> tab(wbytes + n_modes);
     memcpy(tab.data(), h_weights, wbytes);
     memcpy(tab.data() + wbytes, h_select, n_modes);
     Scratch sc(s);
     int rc = sc.upload(tab.data(), tab.size());
     if (rc) return rc;
-    const float* w = static_cast<const float*>(sc.ptr);
+    const double* w = static_cast<const double*>(sc.ptr);
     const unsigned char* sel = static_cast<const unsigned char*>(sc.ptr) + wbytes;
     ZB_DISPATCH_DTYPE(dtype, {
         rot_scores_kernel<T><<<grid_for(n_items, 128), 128, 0, s>>>(static_cast<const T*>(d_in), n_items, n_modes, is, ms,

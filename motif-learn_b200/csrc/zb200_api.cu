@@ -174,10 +174,11 @@ extern "C" int zb200_plan_basis_to_host(const zb200_plan* p, double* h_out) {
     ZB_CUDA(cudaMemcpy(h_out, p->basis64, sizeof(double) * (size_t)p->n_modes * p->kk, cudaMemcpyDeviceToHost));
     return ZB200_OK;
 }
-extern "C" int zb200_plan_supports(const zb200_plan* p, int precision) {
-    if (!p) return 0;
-    if (precision == ZB200_PREC_FP32) return 1;
-    if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3) return tc_supported(p) ? 1 : 0;
+extern "C" int zb200_plan_supports(const zb200_plan* p, int precision, int out_kind) {
+    if (!p || out_kind < ZB200_OUT_REAL || out_kind > ZB200_OUT_ABS_PHASE) return 0;
+    if (precision == ZB200_PREC_FP32) return out_kind == ZB200_OUT_REAL ? 1 : 0;
+    if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3)
+        return tc_supported(p, precision, out_kind != ZB200_OUT_REAL) ? 1 : 0;
     return 0;
 }
 
@@ -193,11 +194,6 @@ static int project_any(const zb200_plan* p, const float* d_patches, int64_t n, i
         return project_simt(p, d_patches, n, static_cast<float*>(d_out), s);
     }
     if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3) {
-        if (!tc_supported(p)) {
-            set_error("tcgen05 projection unsupported for n_max=%d size=%d on this device (needs sm_100, even size, "
-                      "<=256 operand rows)", p->n_max, p->size);
-            return ZB200_EUNSUP;
-        }
         return project_tc(p, d_patches, n, precision, out_kind, d_out, d_out2, d_w, d_sel, n_folds, norm_kind, s);
     }
     set_error("unknown precision %d", precision);
@@ -231,9 +227,12 @@ extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float
         float* tmp = nullptr;
         ZB_CUDA(cudaMallocAsync(&tmp, sizeof(float) * (size_t)n * p->n_modes, s));
         rc = project_simt(p, d_patches, n, tmp, s);
-        if (!rc)
-            rc = zb200_rot_scores(ZB200_F32, tmp, n, p->n_modes, p->n_modes, 1, h_weights, h_select, n_folds,
+        if (!rc) {
+            std::vector<double> wd((size_t)n_folds * p->n_modes);
+            for (size_t i = 0; i < wd.size(); ++i) wd[i] = h_weights[i];
+            rc = zb200_rot_scores(ZB200_F32, tmp, n, p->n_modes, p->n_modes, 1, wd.data(), h_select, n_folds,
                                   norm_kind, d_scores, n_folds, 1, stream);
+        }
         cudaFreeAsync(tmp, s);
         return rc;
     }

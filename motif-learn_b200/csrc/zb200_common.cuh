@@ -110,7 +110,7 @@ int project_simt(const zb200_plan* plan, const float* d_patches, int64_t n, floa
 int project_tc(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind,
                void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
                cudaStream_t s);
-bool tc_supported(const zb200_plan* plan);
+bool tc_supported(const zb200_plan* plan, int precision, bool complex_order);
 
 int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,
              float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds,

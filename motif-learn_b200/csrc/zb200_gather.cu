@@ -45,10 +45,10 @@ gather_kernel(const float* __restrict__ img, int H, int W, const double* __restr
 extern "C" int zb200_gather_patches_f32(const float* d_img, int H, int W, const double* d_pts_xy,
                                         int64_t n_pts, int k, float* d_out, void* stream) {
     using namespace zb200;
-    ZB_CHECK_ARG(d_img && d_out && (d_pts_xy || n_pts == 0), "gather: null pointer");
     ZB_CHECK_ARG(H > 0 && W > 0 && k > 0 && n_pts >= 0, "gather: bad shape H=%d W=%d k=%d n=%lld", H, W, k,
                  (long long)n_pts);
     if (n_pts == 0) return ZB200_OK;
+    ZB_CHECK_ARG(d_img && d_out && d_pts_xy, "gather: null pointer");
     int dev = 0, sms = 148;
     ZB_CUDA(cudaGetDevice(&dev));
     ZB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -210,15 +210,15 @@ class zmoments:
 
 
 def rot_weight_tables(m_all, n_folds, m_unselect):
-    """(W[F, M] float32 over ALL modes with zeros on unselected ones, select[M] uint8)."""
+    """(W[F, M] float64 over ALL modes with zeros on unselected ones, select[M] uint8)."""
     m_all = np.asarray(m_all)
     keep = ix.select_index(m_all, m_unselect, invert=True)
     sel = np.zeros(len(m_all), dtype=np.uint8)
     sel[keep] = 1
-    w = np.zeros((len(ix.check_array1d(n_folds)), len(m_all)), dtype=np.float32)
+    w = np.zeros((len(ix.check_array1d(n_folds)), len(m_all)), dtype=np.float64)
     if len(keep):
         w[:, keep] = ix.construct_rot_maps_matrix(n_folds, m_all[keep])
-    return f32(w), u8(sel)
+    return np.ascontiguousarray(w), u8(sel)
 
 
 def norm_code(p):

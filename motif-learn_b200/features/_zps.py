@@ -173,7 +173,7 @@ class ZPs(BaseEstimator, TransformerMixin):
     def _precision_code(self, for_map: bool = False) -> int:
         lib = _lib.load()
         if self.precision == "auto":
-            if not for_map and lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3):
+            if not for_map and lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3, _lib.OUT_REAL):
                 return _lib.PREC_TF32X3
             return _lib.PREC_FP32
         return _lib.PRECISIONS[self.precision]
@@ -222,7 +222,9 @@ class ZPs(BaseEstimator, TransformerMixin):
         lib = _lib.load()
         code = {"complex": _lib.OUT_COMPLEX, "abs": _lib.OUT_ABS, "abs_phase": _lib.OUT_ABS_PHASE}[kind]
         prec = self._precision_code()
-        if prec == _lib.PREC_FP32:
+        if not lib.zb200_plan_supports(self._plan, prec, code):
+            # the fused epilogue is not available for this shape/precision: real moments from the
+            # projection kernel, then the packing kernel (two launches, still all on the GPU)
             zc = self._transform_patches(images).to_complex()
             if kind == "complex":
                 return zc.data
@@ -282,6 +284,7 @@ class ZPs(BaseEstimator, TransformerMixin):
         rows = h - row0 if rows is None else rows
         wts, sel = rot_weight_tables(self.m, n_folds, m_unselect)
         out = torch.empty((wts.shape[0], rows, w), dtype=torch.float32, device=dev.device)
+        wts = np.ascontiguousarray(wts, dtype=np.float32)
         _lib.check(lib.zb200_symmetry_map_f32(self._plan, int(dev.data_ptr()), h, w, row0, rows,
                                               self._precision_code(for_map=True), np_ptr(wts), np_ptr(sel),
                                               wts.shape[0], norm_code(p), int(out.data_ptr()), self._stream()),
