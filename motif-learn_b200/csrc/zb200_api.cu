@@ -43,11 +43,12 @@ static int alloc_operand(Operand& op, int rows, int k_pad) {
     ZB_CUDA(cudaMalloc(&op.full, bytes));
     ZB_CUDA(cudaMalloc(&op.hi, bytes));
     ZB_CUDA(cudaMalloc(&op.lo, bytes));
+    ZB_CUDA(cudaMalloc(&op.cb, bytes));
     ZB_CUDA(cudaMalloc(&op.t, bytes));
     return ZB200_OK;
 }
 static void free_operand(Operand& op) {
-    cudaFree(op.full); cudaFree(op.hi); cudaFree(op.lo); cudaFree(op.t);
+    cudaFree(op.full); cudaFree(op.hi); cudaFree(op.lo); cudaFree(op.cb); cudaFree(op.t);
     op = Operand();
 }
 

@@ -4,6 +4,8 @@
 #include "zb200_common.cuh"
 #include "zb200_basis_math.h"
 
+#include <cuda_bf16.h>
+
 namespace zb200 {
 
 // One thread per (pixel, |m|).  Each thread walks n = |m|, |m|+2, ... with the Jacobi
@@ -42,7 +44,7 @@ __device__ __forceinline__ float to_tf32_rn(float f) {
 __global__ void pack_kernel(const double* __restrict__ basis, const int* __restrict__ row_map,
                             int rows_pad, int kk, int k_pad, double inv_area,
                             float* __restrict__ full, float* __restrict__ hi, float* __restrict__ lo,
-                            float* __restrict__ tr) {
+                            __nv_bfloat16* __restrict__ cb, float* __restrict__ tr) {
     const int kidx = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (kidx >= k_pad) return;
@@ -56,6 +58,10 @@ __global__ void pack_kernel(const double* __restrict__ basis, const int* __restr
     full[o] = f;
     hi[o] = h;
     lo[o] = l;
+    // correction operand: 16 bf16 per group of 8 k -- slots 0..7 pair with Xlo, slots 8..15 with Xhi
+    const size_t cbo = (size_t)r * 2 * k_pad + (size_t)(kidx >> 3) * 16 + (kidx & 7);
+    cb[cbo] = __float2bfloat16_rn(f);
+    cb[cbo + 8] = __float2bfloat16_rn((float)(v - (double)h));
     tr[(size_t)kidx * rows_pad + r] = f;
 }
 
@@ -74,7 +80,7 @@ static int pack_one(zb200_plan* p, Operand& op, const int* h_map, cudaStream_t s
     ZB_CUDA(cudaMemcpyAsync(d_map, h_map, sizeof(int) * op.rows_pad, cudaMemcpyHostToDevice, s));
     dim3 grid((unsigned)ceil_div(p->k_pad, 128), (unsigned)op.rows_pad);
     pack_kernel<<<grid, 128, 0, s>>>(p->basis64, d_map, op.rows_pad, p->kk, p->k_pad, p->inv_area,
-                                     op.full, op.hi, op.lo, op.t);
+                                     op.full, op.hi, op.lo, reinterpret_cast<__nv_bfloat16*>(op.cb), op.t);
     ZB_LAUNCHED();
     ZB_CUDA(cudaStreamSynchronize(s));
     ZB_CUDA(cudaFree(d_map));

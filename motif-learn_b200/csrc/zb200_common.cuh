@@ -52,6 +52,8 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 //   op_full   float  [rows_pad][k_pad]        K-major GEMM operand, value = V/area (fp32 RN)
 //   op_hi     float  [rows_pad][k_pad]        tf32-exact high part  (RN of V/area to 11 bits)
 //   op_lo     float  [rows_pad][k_pad]        tf32-exact low part   (RN of V/area - hi)
+//   op_cb     bf16   [rows_pad][2*k_pad]      correction operand of the fp32-grade tensor path: per
+//                                             group of 8 k: 8 x bf16(V/area) then 8 x bf16(V/area - hi)
 //   op_t      float  [k_pad][rows_pad]        transpose of op_full for the SIMT kernels
 //   two row orders of each: REAL (row r = mode j) and CPLX (row 2c = (n,+m), 2c+1 = (n,-m))
 struct Operand {
@@ -60,9 +62,13 @@ struct Operand {
     float* full = nullptr;
     float* hi = nullptr;
     float* lo = nullptr;
+    uint32_t* cb = nullptr;  // bf16 pairs, same byte geometry as one fp32 row per operand row
     float* t = nullptr;
-    CUtensorMap tmap_hi;     // TMA descriptors over [rows_pad][k_pad], box 32 x rows_pad/..., SW128
-    CUtensorMap tmap_lo;
+    // TMA descriptors over [rows_pad][k_pad] 4-byte words, SW128, box 32 x rows_pad/C for cluster
+    // sizes C = 1, 2, 4 (index log2 C): each CTA of a cluster fetches 1/C of the rows and multicasts
+    CUtensorMap tmap_hi[3];
+    CUtensorMap tmap_cb[3];
+    int max_cluster = 1;     // largest C with rows_pad % (8 C) == 0
     bool has_tmap = false;
 };
 

@@ -16,9 +16,12 @@
 // (n_pad x 16 KiB) is re-streamed per tile from L2.
 //
 // tf32x3 (fp32-grade) is a second kernel, project_tc3_kernel, with two more ideas:
-//   * operand split  X.B ~= Xhi.Bhi + Xlo.Bhi + Xhi.Blo  where the tensor core itself truncates the
-//     raw fp32 X to Xhi and a splitter warpgroup writes Xlo = x - trunc_tf32(x) straight into TMEM
-//     (tcgen05.st), from where the MMA reads it as its A operand (no second copy of X in smem);
+//   * operand split  X.B ~= Xhi.Bhi + (Xlo.Bhi + Xhi.Blo): the first term is a kind::tf32 MMA whose
+//     raw fp32 X operand the tensor core truncates to Xhi itself; the two correction terms need only
+//     ~8 bits each, so they are ONE kind::f16 (bf16) MMA with K=16 = 8 x (Xlo,Bhi) + 8 x (Xhi,Blo).
+//     A splitter warpgroup computes Xlo = x - trunc_tf32(x), packs bf16 [Xlo | Xhi] and writes it
+//     straight into TMEM (tcgen05.st), from where the MMA reads its A operand -- no second copy of X
+//     in shared memory; the matching bf16 [Bhi | Blo] operand is precomputed in HBM (op_cb);
 //   * K-chunked accumulation: the tensor core accumulates in fp32 with round-toward-zero, which
 //     biases a 512-step sum by ~1.5e-5 relative (measured); accumulators are therefore drained
 //     every 8 k-blocks into fp32 registers of the epilogue warps (round-to-nearest adds), with two
@@ -26,6 +29,8 @@
 #include "zb200_common.cuh"
 
 #include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace zb200 {
 
@@ -58,7 +63,11 @@ struct Params {
     int n_folds;
     int norm_kind;
     int chunk_kb;         // k-blocks per accumulation chunk (tf32x3 kernel)
-    int lo_bufs;          // Xlo staging buffers in TMEM     (tf32x3 kernel)
+    int lo_bufs;          // operand staging buffers in TMEM: 1, 2 or 4       (tf32x3 kernel)
+    int ts_hi;            // 1: the tf32 MMA also reads X from TMEM (raw copy)  (tf32x3 kernel)
+    int epi_solo;         // 1: epilogue warpgroup 1 owns all columns, warpgroup 2 idles
+    int cluster;          // CTAs per cluster sharing the B operand through TMA multicast (1, 2 or 4)
+    int dbg;              // ZB200_TC_DEBUG bitmask: experiments only (results are wrong when set)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -84,6 +93,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// experiment support: cycles spent blocked per wait site, summed over CTAs (ZB200_TC_DEBUG & 16)
+__device__ unsigned long long g_wait_cycles[16];
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+}
+// One elected lane of a fully converged warp; unlike `lane == 0` ptxas knows the region has exactly
+// one active thread and emits the uniform-datapath instructions (UTCHMMA, UTMALDG) without a
+// per-instruction election loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -96,6 +127,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
         "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
+}
+// same load, delivered to the same smem offset of every CTA in cta_mask; each destination CTA's
+// mbarrier (same offset) receives the complete_tx of the bytes written into that CTA
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
+        "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -115,6 +165,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
                  : "memory");
 }
 
@@ -139,6 +197,14 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                                 // [61,64) SWIZZLE_128B
     return d;
 }
+// The same descriptor split in two 32-bit halves: only the low word (address >> 4, LBO) changes
+// between tiles, so the single issuing thread keeps the high word in a register and does 32-bit
+// arithmetic on the low one.  (Issue-bound otherwise: a naive loop costs ~140 clk per MMA, the
+// tensor core needs 48-56 clk at N=96 -- scripts/microbench/umma_rate.cu.)
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
+
 // kind::tf32, fp32 accumulate, A and B K-major, M=128, N=n
 __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
     uint32_t d = 0;
@@ -249,7 +315,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], p.cluster);      // every CTA of the cluster releases the shared B slot
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -264,14 +330,20 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();        // peers' barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // all CTAs of a cluster run the same number of tiles (they consume B in lock-step); tiles past
+    // the end are all-zero (TMA out-of-bounds fill) and their rows are never stored
+    const uint32_t crank = p.cluster > 1 ? cluster_rank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int b_rows = p.n_pad / p.cluster;       // B rows this CTA fetches and multicasts
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
@@ -281,7 +353,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full[s], x_bytes + b_bytes);
                     tma_load_2d(stage_x(s), &map_x, &full[s], kb * kBlockK, row0, kEvictFirst);
-                    tma_load_2d(stage_b(s), &map_b, &full[s], kb * kBlockK, 0, kEvictLast);
+                    if (p.cluster == 1)
+                        tma_load_2d(stage_b(s), &map_b, &full[s], kb * kBlockK, 0, kEvictLast);
+                    else
+                        tma_load_2d_mc(stage_b(s) + (size_t)crank * b_rows * 128, &map_b, &full[s], kb * kBlockK,
+                                       (int)crank * b_rows, cmask, kEvictLast);
                     if (++s == p.n_stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -289,8 +365,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_tf32(p.n_pad);
+            const uint32_t x_lo0 = desc_lo_sw128(smem_u32(smem));
+            const uint32_t stage_step = stage_bytes >> 4;
             int s = 0;
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
@@ -298,21 +376,25 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 const uint32_t acc_ph = (uint32_t)(t / p.acc_bufs) & 1u;
                 mbar_wait(&acc_empty[buf], acc_ph ^ 1);
                 tc_fence_after();
+                const uint32_t d_tmem0 = tmem_base + (uint32_t)(buf * p.subtiles * p.n_pad);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t xa = smem_u32(stage_x(s));
-                    const uint64_t db = make_desc_sw128(smem_u32(stage_b(s)));
-                    for (int sub = 0; sub < p.subtiles; ++sub) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.subtiles + sub) * p.n_pad);
-                        const uint64_t dx = make_desc_sw128(xa + sub * kTileRows * 128);
+                    const uint32_t xl = x_lo0 + (uint32_t)s * stage_step;
+                    const uint32_t bl = xl + (x_bytes >> 4);
+                    const uint32_t acc0 = kb > 0 ? 1u : 0u;
 #pragma unroll
-                        for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-                            const uint64_t koff = (uint64_t)((k4 * kUmmaK * 4) >> 4);   // 32 B steps inside the atom
-                            umma_tf32(d_tmem, dx + koff, db + koff, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
-                        }
+                    for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {      // 32-byte steps inside the swizzle atom
+                        umma_tf32(d_tmem0, desc_from_lo(xl + 2 * k4), desc_from_lo(bl + 2 * k4), idesc, k4 ? 1u : acc0);
                     }
-                    umma_commit(&empty[s]);                       // stage reusable once these MMAs retire
+                    if (p.subtiles == 2) {
+#pragma unroll
+                        for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4)
+                            umma_tf32(d_tmem0 + p.n_pad, desc_from_lo(xl + 1024 + 2 * k4), desc_from_lo(bl + 2 * k4), idesc,
+                                      k4 ? 1u : acc0);
+                    }
+                    if (p.cluster == 1) umma_commit(&empty[s]);   // stage reusable once these MMAs retire
+                    else umma_commit_mc(&empty[s], cmask);
                     if (kb == p.k_blocks - 1) umma_commit(&acc_full[buf]);
                     if (++s == p.n_stages) { s = 0; ph ^= 1; }
                 }
@@ -350,6 +432,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();        // no CTA leaves while a peer may still write into it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
@@ -362,12 +445,21 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 //   warpgroup 1,2  epilogue: running fp32 sums of up to 128 accumulator columns per thread
 //   warpgroup 3  splitter: Xlo = x - trunc_tf32(x) for its 128 rows, tcgen05.st into TMEM
 // ================================================================================================
-constexpr int kRegsCtl = 40, kRegsEpi = 192, kRegsSplit = 88;      // (40 + 2*192 + 88) * 128 = 64 Ki
+constexpr int kRegsCtl = 48, kRegsEpi = 176, kRegsSplit = 112;     // (48 + 2*176 + 112) * 128 = 64 Ki
 
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// D[tmem] (+)= A[tmem] . B[smem]^T
+// D[tmem] (+)= A[tmem] . B[smem]^T with bf16 operands (K = 16 per instruction), fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                   // c_format = F32
+    d |= 1u << 7;                   // a_format = BF16
+    d |= 1u << 10;                  // b_format = BF16
+    d |= (uint32_t)(n >> 3) << 17;  // N / 8
+    d |= (uint32_t)(128 >> 4) << 24;  // M / 16
+    return d;
+}
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(
@@ -375,6 +467,16 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -407,72 +509,99 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
     uint64_t* full = bars;                        // TMA landed                               [stages]
     uint64_t* empty = bars + p.n_stages;          // MMAs reading the stage retired           [stages]
-    uint64_t* lo_full = bars + 2 * p.n_stages;    // Xlo of a k-block is in TMEM              [2]
-    uint64_t* lo_empty = lo_full + 2;             // MMAs reading that Xlo retired            [2]
-    uint64_t* acc_full = lo_empty + 2;            // accumulation chunk complete              [2]
+    uint64_t* lo_full = bars + 2 * p.n_stages;    // staged operands of a k-block are in TMEM [4]
+    uint64_t* lo_empty = lo_full + 4;             // MMAs reading them retired                [4]
+    uint64_t* acc_full = lo_empty + 4;            // accumulation chunk complete              [2]
     uint64_t* acc_empty = acc_full + 2;           // chunk drained by the epilogue            [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+    // Warp-role layout.  The SM's issue arbiter prefers the highest warp id of a sub-partition, and
+    // every sub-partition hosts one busy splitter warp, so the latency-critical single-thread roles
+    // (TMA producer, MMA issuer) take the LAST warpgroup and the splitter the first:
+    //   warps 0-3 splitter | warps 4-11 epilogue (two warpgroups) | warp 12 TMA, 13 MMA, 14 TMEM alloc
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wg = warp >> 2;
+    constexpr int kWarpTma = 12, kWarpMma = 13, kWarpAlloc = 14;
+    const bool prof = (p.dbg & 16) != 0;
+    unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;      // per-thread blocked-cycle counters (experiments)
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kWarpTma && lane == 0) {
         prefetch_tmap(&map_x);
         prefetch_tmap(&map_bhi);
         prefetch_tmap(&map_blo);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], p.cluster);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(&lo_full[b], 4);
             mbar_init(&lo_empty[b], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 8);
+            mbar_init(&acc_empty[b], p.epi_solo ? 4 : 8);
         }
         fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == kWarpAlloc) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t lo_base = tmem_base + (uint32_t)(2 * p.subtiles * p.n_pad);      // after the two accumulator sets
+    // TMEM columns: [2 accumulator sets][lo_bufs x subtiles x (Xraw? 32 | bf16 pack 32)]
+    const uint32_t lo_base = tmem_base + (uint32_t)(2 * p.subtiles * p.n_pad);
+    const uint32_t lo_mask = (uint32_t)p.lo_bufs - 1u;               // lo_bufs is a power of two
+    const uint32_t lo_shift = p.lo_bufs == 4 ? 2u : (p.lo_bufs == 2 ? 1u : 0u);
 
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t crank = p.cluster > 1 ? cluster_rank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;     // lock-step within the cluster
+    const int b_rows = p.n_pad / p.cluster;
     const int n_chunks = (p.k_blocks + p.chunk_kb - 1) / p.chunk_kb;
 
-    if (wg == 0) {
+    if (wg == 3) {
         reg_dec<kRegsCtl>();
-        if (warp == 0) {
+        if (warp == kWarpTma) {
             // ===================== TMA producer =====================
-            if (lane == 0) {
+            if (elect_one()) {
                 int s = 0;
                 uint32_t ph = 0;
                 for (int t = 0; t < my_tiles; ++t) {
                     const int tile = blockIdx.x + t * gridDim.x;
                     const int row0 = tile * p.subtiles * kTileRows;
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
-                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_wait_t(&empty[s], ph ^ 1, w0, prof);
                         mbar_arrive_expect_tx(&full[s], x_bytes + 2 * b_bytes);
                         tma_load_2d(stage_x(s), &map_x, &full[s], kb * kBlockK, row0, kEvictFirst);
-                        tma_load_2d(stage_bhi(s), &map_bhi, &full[s], kb * kBlockK, 0, kEvictLast);
-                        tma_load_2d(stage_blo(s), &map_blo, &full[s], kb * kBlockK, 0, kEvictLast);
+                        if (p.cluster == 1) {
+                            tma_load_2d(stage_bhi(s), &map_bhi, &full[s], kb * kBlockK, 0, kEvictLast);
+                            tma_load_2d(stage_blo(s), &map_blo, &full[s], kb * kBlockK, 0, kEvictLast);
+                        } else {
+                            const size_t off = (size_t)crank * b_rows * 128;
+                            tma_load_2d_mc(stage_bhi(s) + off, &map_bhi, &full[s], kb * kBlockK, (int)crank * b_rows, cmask,
+                                           kEvictLast);
+                            tma_load_2d_mc(stage_blo(s) + off, &map_blo, &full[s], kb * kBlockK, (int)crank * b_rows, cmask,
+                                           kEvictLast);
+                        }
                         if (++s == p.n_stages) { s = 0; ph ^= 1; }
                     }
                 }
             }
             __syncwarp();
-        } else if (warp == 1) {
+        } else if (warp == kWarpMma) {
             // ===================== MMA issuer =====================
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t idesc = make_idesc_tf32(p.n_pad);
+                const uint32_t idesc_c = make_idesc_bf16(p.n_pad);
+                const uint32_t x_lo0 = desc_lo_sw128(smem_u32(smem));
+                const uint32_t stage_step = stage_bytes >> 4;
                 int s = 0;
                 uint32_t ph = 0;
                 uint32_t it = 0;            // running k-block counter  -> Xlo buffer / phase
@@ -480,33 +609,47 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 for (int t = 0; t < my_tiles; ++t) {
                     for (int c = 0; c < n_chunks; ++c, ++ck) {
                         const int buf = ck & 1;
-                        mbar_wait(&acc_empty[buf], ((ck >> 1) & 1u) ^ 1u);
+                        mbar_wait_t(&acc_empty[buf], ((ck >> 1) & 1u) ^ 1u, w0, prof);
                         tc_fence_after();
                         const int kb_end = min(p.k_blocks, (c + 1) * p.chunk_kb);
-                        for (int kb = c * p.chunk_kb; kb < kb_end; ++kb, ++it) {
-                            const int lb = (p.lo_bufs == 2) ? (int)(it & 1u) : 0;
-                            const uint32_t lo_ph = (p.lo_bufs == 2) ? ((it >> 1) & 1u) : (it & 1u);
-                            mbar_wait(&lo_full[lb], lo_ph);                  // implies full[s]
+                        const uint32_t d0 = tmem_base + (uint32_t)(buf * p.subtiles * p.n_pad);
+                        const int kb_begin = c * p.chunk_kb;
+                        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                            const int lb = (int)(it & lo_mask);
+                            const uint32_t lo_ph = (it >> lo_shift) & 1u;
+                            mbar_wait_t(&lo_full[lb], lo_ph, w1, prof);       // implies full[s]
+                            const long long t_fence = prof ? clock64() : 0;
                             tc_fence_after();
-                            const uint32_t xa = smem_u32(stage_x(s));
-                            const uint64_t dbh = make_desc_sw128(smem_u32(stage_bhi(s)));
-                            const uint64_t dbl = make_desc_sw128(smem_u32(stage_blo(s)));
-                            for (int sub = 0; sub < p.subtiles; ++sub) {
-                                const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.subtiles + sub) * p.n_pad);
-                                const uint32_t a_lo = lo_base + (uint32_t)((lb * p.subtiles + sub) * kBlockK);
-                                const uint64_t dx = make_desc_sw128(xa + sub * kTileRows * 128);
+                            const long long t_issue = prof ? clock64() : 0;
+                            if (prof) w0 += (unsigned long long)(t_issue - t_fence);   // (reported as mma.acc_empty+fence)
+                            const uint32_t xl = x_lo0 + (uint32_t)s * stage_step;
+                            const uint32_t bhl = xl + (x_bytes >> 4);
+                            const uint32_t bcl = bhl + (b_bytes >> 4);
+                            const uint32_t a0 = lo_base + (uint32_t)(lb * p.subtiles) * kBlockK;
+                            const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
+                            // Xhi.Bhi (tf32; the tensor core truncates the raw X itself) and the bf16 correction
+                            // Xlo.Bhi + Xhi.Blo, for the 4 K-steps of the k-block and each sub-tile
+#pragma unroll
+                            for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+                                umma_tf32(d0, desc_from_lo(xl + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc, k4 ? 1u : acc0);
+                                if (!(p.dbg & 1)) umma_bf16_ts(d0, a0 + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
+                            }
+                            if (p.subtiles == 2) {
 #pragma unroll
                                 for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-                                    const uint64_t koff = (uint64_t)((k4 * kUmmaK * 4) >> 4);
-                                    const uint32_t first = (kb == c * p.chunk_kb && k4 == 0) ? 0u : 1u;
-                                    umma_tf32(d_tmem, dx + koff, dbh + koff, idesc, first);          // Xhi . Bhi
-                                    umma_tf32_ts(d_tmem, a_lo + k4 * kUmmaK, dbh + koff, idesc, 1u);  // Xlo . Bhi
-                                    umma_tf32(d_tmem, dx + koff, dbl + koff, idesc, 1u);             // Xhi . Blo
+                                    umma_tf32(d0 + p.n_pad, desc_from_lo(xl + 1024 + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc,
+                                              k4 ? 1u : acc0);
+                                    if (!(p.dbg & 1))
+                                        umma_bf16_ts(d0 + p.n_pad, a0 + kBlockK + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
                                 }
                             }
-                            umma_commit(&empty[s]);
+                            if (prof) w2 += (unsigned long long)(clock64() - t_issue);
+                            const long long t_commit = prof ? clock64() : 0;
+                            if (p.cluster == 1) umma_commit(&empty[s]);
+                            else umma_commit_mc(&empty[s], cmask);
                             umma_commit(&lo_empty[lb]);
                             if (kb == kb_end - 1) umma_commit(&acc_full[buf]);
+                            if (prof) w3 += (unsigned long long)(clock64() - t_commit);
                             if (++s == p.n_stages) { s = 0; ph ^= 1; }
                         }
                     }
@@ -514,35 +657,67 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
             __syncwarp();
         }
-    } else if (wg == 3) {
+    } else if (wg == 0) {
         // ===================== splitter =====================
+        // Xlo = x - trunc_tf32(x): exact in fp32, and exactly what the tensor core drops when it
+        // truncates the raw X operand.  Both sub-tiles' rows are loaded before the buffer wait so
+        // the shared-memory latency overlaps the previous k-block's MMAs.
         reg_dec<kRegsSplit>();
         const int q = warp & 3;
         const int r = q * 32 + lane;                              // row inside a 128-row sub-tile
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         int s = 0;
         uint32_t ph = 0;
         uint32_t it = 0;
+        // Eight k values (two 16-B chunks) -> 8 TMEM columns of bf16 pairs: columns 0..3 hold
+        // Xlo[0..7], columns 4..7 hold Xhi[0..7] (K slot 2c in the low half-word, 2c+1 in the high).
+        auto lo_of = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
+        auto pack2 = [](float even, float odd) {
+            const __nv_bfloat162 v = __floats2bfloat162_rn(even, odd);      // .x = low half-word
+            return *reinterpret_cast<const uint32_t*>(&v);
+        };
+        auto split8 = [&](const float4& a, const float4& b, uint32_t* w) {
+            w[0] = pack2(lo_of(a.x), lo_of(a.y));
+            w[1] = pack2(lo_of(a.z), lo_of(a.w));
+            w[2] = pack2(lo_of(b.x), lo_of(b.y));
+            w[3] = pack2(lo_of(b.z), lo_of(b.w));
+            w[4] = pack2(a.x, a.y);
+            w[5] = pack2(a.z, a.w);
+            w[6] = pack2(b.x, b.y);
+            w[7] = pack2(b.z, b.w);
+        };
         for (int t = 0; t < my_tiles; ++t) {
             for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-                const int lb = (p.lo_bufs == 2) ? (int)(it & 1u) : 0;
-                const uint32_t lo_ph = (p.lo_bufs == 2) ? ((it >> 1) & 1u) : (it & 1u);
-                mbar_wait(&full[s], ph);
-                mbar_wait(&lo_empty[lb], lo_ph ^ 1u);
+                const int lb = (int)(it & lo_mask);
+                const uint32_t lo_ph = (it >> lo_shift) & 1u;
+                mbar_wait_t(&full[s], ph, w0, prof);
+                const uint8_t* rowp = stage_x(s) + (size_t)r * 128;
+                float4 x0[8], x1[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)                       // logical 16-B chunk c sits at c ^ (r % 8)
+                    x0[c] = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+                if (p.subtiles == 2) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        x1[c] = *reinterpret_cast<const float4*>(rowp + kTileRows * 128 + ((c ^ (r & 7)) << 4));
+                }
+                mbar_wait_t(&lo_empty[lb], lo_ph ^ 1u, w1, prof);
                 tc_fence_after();
-                for (int sub = 0; sub < p.subtiles; ++sub) {
-                    const uint8_t* rowp = stage_x(s) + (size_t)sub * kTileRows * 128 + (size_t)r * 128;
+                if (!(p.dbg & 2)) {
                     uint32_t lo[32];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {                 // logical 16-B chunk c sits at c ^ (r % 8)
-                        const float4 x = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
-                        lo[4 * c + 0] = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-                        lo[4 * c + 1] = __float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-                        lo[4 * c + 2] = __float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-                        lo[4 * c + 3] = __float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-                    }
-                    tmem_st32(lo_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((lb * p.subtiles + sub) * kBlockK), lo);
+                    for (int c = 0; c < 4; ++c) split8(x0[2 * c], x0[2 * c + 1], lo + 8 * c);
+                    tmem_st32(lo_base + lane_addr + (uint32_t)(lb * p.subtiles + 0) * kBlockK, lo);
                 }
+                if (p.subtiles == 2 && !(p.dbg & 2)) {
+                    uint32_t lo[32];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) split8(x1[2 * c], x1[2 * c + 1], lo + 8 * c);
+                    tmem_st32(lo_base + lane_addr + (uint32_t)(lb * p.subtiles + 1) * kBlockK, lo);
+                }
+                const long long t_st = prof ? clock64() : 0;
                 tmem_st_wait();
+                if (prof) w2 += (unsigned long long)(clock64() - t_st);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&lo_full[lb]);
@@ -557,11 +732,12 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         // two accumulators: group g owns sub-tile g, all columns; one accumulator: group g owns a column half
         const int sub = (p.subtiles == 2) ? g : 0;
         const int half = ((p.n_pad / 16 + 1) / 2) * 16;
-        const int c_beg = (p.subtiles == 2) ? 0 : g * half;
-        const int c_end = (p.subtiles == 2) ? p.n_pad : min(p.n_pad, (g + 1) * half);
+        const int c_beg = (p.subtiles == 2 || p.epi_solo) ? 0 : g * half;
+        const int c_end = (p.subtiles == 2 || p.epi_solo) ? p.n_pad : min(p.n_pad, (g + 1) * half);
+        const bool idle = p.epi_solo && g == 1;                   // second warpgroup has nothing to own
         const int n_cc = (c_end - c_beg + 15) / 16;               // <= kMaxColChunks
         uint32_t ck = 0;
-        for (int t = 0; t < my_tiles; ++t) {
+        for (int t = 0; t < (idle ? 0 : my_tiles); ++t) {
             const int tile = blockIdx.x + t * gridDim.x;
             const long long row = (long long)tile * p.subtiles * kTileRows + sub * kTileRows + q * 32 + lane;
             float sum[kMaxColChunks][16];
@@ -571,7 +747,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 for (int i = 0; i < 16; ++i) sum[cc][i] = 0.f;
             for (int c = 0; c < n_chunks; ++c, ++ck) {
                 const int buf = ck & 1;
-                mbar_wait(&acc_full[buf], (ck >> 1) & 1u);
+                mbar_wait_t(&acc_full[buf], (ck >> 1) & 1u, w0, prof);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
                                        (uint32_t)((buf * p.subtiles + sub) * p.n_pad + c_beg);
@@ -606,9 +782,17 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
     }
 
+    if (prof && lane == 0 && (warp == kWarpTma || warp == kWarpMma || warp == 4 || warp == 0)) {
+        const int base = warp == kWarpTma ? 0 : (warp == kWarpMma ? 1 : (warp == 4 ? 5 : 8));
+        atomicAdd(&g_wait_cycles[base], w0);        // 0 producer.empty | 1 mma.acc_empty | 5 epi.acc_full | 8 split.full
+        atomicAdd(&g_wait_cycles[base + 1], w1);    // 2 mma.lo_full | 9 split.lo_empty
+        atomicAdd(&g_wait_cycles[base + 2], w2);    // 3 mma.issue   | 10 split.st_wait
+        if (warp == kWarpMma) atomicAdd(&g_wait_cycles[4], w3);   // 4 mma.commit
+    }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (p.cluster > 1) cluster_sync_all();        // no CTA leaves while a peer may still write into it
+    if (warp == kWarpAlloc) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
@@ -669,12 +853,18 @@ int init_tensor_maps(zb200_plan* p) {
     if (p->cc_major != 10 || p->kk % 4 != 0) return ZB200_OK;       // SIMT only; not an error
     for (Operand* op : {&p->real, &p->cplx}) {
         if (op->rows_pad > 256) continue;
-        int rc = tc::encode_2d(&op->tmap_hi, op->hi, (uint64_t)p->k_pad, (uint64_t)op->rows_pad,
-                               (uint64_t)p->k_pad * 4, (uint32_t)op->rows_pad);
-        if (rc) return rc;
-        rc = tc::encode_2d(&op->tmap_lo, op->lo, (uint64_t)p->k_pad, (uint64_t)op->rows_pad, (uint64_t)p->k_pad * 4,
-                           (uint32_t)op->rows_pad);
-        if (rc) return rc;
+        op->max_cluster = 1;
+        for (int lg = 0; lg < 3; ++lg) {
+            const int c = 1 << lg;
+            if (op->rows_pad % (8 * c) != 0) break;                  // B slices must start on a swizzle atom
+            int rc = tc::encode_2d(&op->tmap_hi[lg], op->hi, (uint64_t)p->k_pad, (uint64_t)op->rows_pad,
+                                   (uint64_t)p->k_pad * 4, (uint32_t)(op->rows_pad / c));
+            if (rc) return rc;
+            rc = tc::encode_2d(&op->tmap_cb[lg], op->cb, (uint64_t)p->k_pad, (uint64_t)op->rows_pad,
+                               (uint64_t)p->k_pad * 4, (uint32_t)(op->rows_pad / c));
+            if (rc) return rc;
+            op->max_cluster = c;
+        }
         op->has_tmap = true;
     }
     return ZB200_OK;
@@ -712,44 +902,76 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                          : (out_kind == ZB200_OUT_REAL ? p->n_modes
                                                        : (out_kind == ZB200_OUT_COMPLEX ? 2 * p->n_complex : p->n_complex));
     prm.chunk_kb = 8;
+    if (const char* e = getenv("ZB200_TC_DEBUG")) prm.dbg = atoi(e);
+    if (prm.dbg & 4) prm.chunk_kb = prm.k_blocks;
 
     // tile shape: two 128-patch accumulators per tile when TMEM/smem allow and there is enough work
     // to keep every SM busy with 256-patch tiles
-    const int bar_bytes = 1024 + 8 * (2 * 8 + 8) + 16;
+    const int bar_bytes = 1024 + 8 * (2 * 8 + 12) + 16;
     auto stage_bytes = [&](int sub) { return sub * kTileRows * 128 + (x3 ? 2 : 1) * prm.n_pad * 128; };
     int sub = 2;
-    if (x3) {
-        if (prm.n_pad > 96) sub = 1;                                  // 2 acc sets * 2 * n_pad + 2*64 Xlo <= 512
-        if (scores && n_folds > kFusedFolds) {
-            set_error("fused n-fold scores support at most %d folds (got %d)", kFusedFolds, n_folds);
-            return ZB200_EUNSUP;
-        }
-        if (scores && sub == 1) {
-            set_error("fused n-fold scores in tf32x3 need <= 96 operand rows (have %d); use the unfused path", prm.n_pad);
-            return ZB200_EUNSUP;
-        }
-    } else if (sub * prm.n_pad > (int)kTmemCols) {
-        sub = 1;
+    if (scores && n_folds > kFusedFolds) {
+        set_error("fused n-fold scores support at most %d folds (got %d)", kFusedFolds, n_folds);
+        return ZB200_EUNSUP;
     }
-    if (sub == 2 && !(x3 && scores) && ceil_div(n, 256) < p->sm_count) sub = 1;
-    if ((kSmemLimit - bar_bytes) / stage_bytes(sub) < 2 && sub == 2 && !(x3 && scores)) sub = 1;
+    if (x3) {
+        sub = prm.n_pad <= 96 ? 2 : 1;                    // 2 accumulator sets x sub x n_pad + staging <= 512 columns
+        if (ceil_div(n, 256) < p->sm_count || (prm.dbg & 8)) sub = 1;
+        prm.ts_hi = 0;
+        prm.epi_solo = (sub == 1 && prm.n_pad <= 16 * kMaxColChunks) ? 1 : 0;
+        if (scores && sub == 1 && !prm.epi_solo) {
+            set_error("fused n-fold scores in tf32x3 need <= 128 operand rows (have %d); use the unfused path", prm.n_pad);
+            return ZB200_EUNSUP;
+        }
+    } else {
+        if (sub * prm.n_pad > (int)kTmemCols) sub = 1;
+        if (sub == 2 && ceil_div(n, 256) < p->sm_count) sub = 1;
+        if (prm.dbg & 8) sub = 1;
+        if ((kSmemLimit - bar_bytes) / stage_bytes(sub) < 2 && sub == 2) sub = 1;
+    }
     prm.subtiles = sub;
     prm.n_stages = (kSmemLimit - bar_bytes) / stage_bytes(sub);
     if (prm.n_stages > 8) prm.n_stages = 8;
+    if (const char* e = getenv("ZB200_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < prm.n_stages) prm.n_stages = v; }
     if (prm.n_stages < 1) {
         set_error("project_tc: operand of %d rows does not fit shared memory", prm.n_pad);
         return ZB200_EUNSUP;
     }
     prm.acc_bufs = (2 * sub * prm.n_pad <= (int)kTmemCols) ? 2 : 1;
-    prm.lo_bufs = (2 * sub * prm.n_pad + 2 * sub * kBlockK <= (int)kTmemCols) ? 2 : 1;
+    {
+        const int per_buf = sub * kBlockK;
+        const int room = ((int)kTmemCols - 2 * sub * prm.n_pad) / per_buf;
+        prm.lo_bufs = room >= 4 ? 4 : (room >= 2 ? 2 : 1);
+    }
     prm.n_tiles = (int)ceil_div(n, (int64_t)sub * kTileRows);
 
     CUtensorMap map_x;
     int rc = encode_2d(&map_x, d_patches, (uint64_t)p->kk, (uint64_t)n, (uint64_t)p->kk * 4, (uint32_t)(sub * kTileRows));
     if (rc) return rc;
 
+    // cluster of C CTAs shares each B k-block through TMA multicast (L2 -> SM traffic of B / C)
+    int cluster = 2;
+    if (const char* e = getenv("ZB200_TC_CLUSTER")) cluster = atoi(e);
+    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
+    while (cluster > 1 && (cluster > op.max_cluster || prm.n_tiles < 2 * cluster)) cluster >>= 1;
+    prm.cluster = cluster;
+    const int lg = cluster == 4 ? 2 : (cluster == 2 ? 1 : 0);
+
     const size_t smem = (size_t)prm.n_stages * stage_bytes(sub) + bar_bytes;
-    const int grid = prm.n_tiles < p->sm_count ? prm.n_tiles : p->sm_count;
+    int grid = prm.n_tiles < p->sm_count ? prm.n_tiles : p->sm_count;
+    grid = (grid / cluster) * cluster;                               // whole clusters only (148 = 2*74 = 4*37)
+    if (grid < cluster) grid = cluster;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     const int kout = scores ? kOutScores
                             : (out_kind == ZB200_OUT_ABS ? kOutAbs : (out_kind == ZB200_OUT_ABS_PHASE ? kOutAbsPhase : kOutPlain));
 #define ZB_TC_LAUNCH(KOUT)                                                                                            \
@@ -757,11 +979,13 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
         if (x3) {                                                                                                     \
             ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                          (int)smem));                                                                 \
-            project_tc3_kernel<KOUT><<<grid, 512, smem, s>>>(map_x, op.tmap_hi, op.tmap_lo, prm);                      \
+            cfg.blockDim = dim3(512);                                                                                 \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm));  \
         } else {                                                                                                      \
             ZB_CUDA(cudaFuncSetAttribute(project_tc_kernel<KOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                          (int)smem));                                                                 \
-            project_tc_kernel<KOUT><<<grid, 256, smem, s>>>(map_x, op.tmap_hi, prm);                                   \
+            cfg.blockDim = dim3(256);                                                                                 \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc_kernel<KOUT>, map_x, op.tmap_hi[lg], prm));                   \
         }                                                                                                             \
     }
     ZB_TC_LAUNCH(kOutPlain)
@@ -770,6 +994,17 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     ZB_TC_LAUNCH(kOutScores)
 #undef ZB_TC_LAUNCH
     ZB_LAUNCHED();
+    if (prm.dbg & 16) {
+        unsigned long long h[16];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_wait_cycles, sizeof(h));
+        fprintf(stderr, "[zb200 wait cycles / CTA] producer.empty=%llu mma.acc_empty=%llu mma.lo_full=%llu mma.issue=%llu "
+                "mma.commit=%llu split.full=%llu split.lo_empty=%llu split.st_wait=%llu epi.acc_full=%llu (grid %d, tiles %d, k_blocks %d, stages %d)\n",
+                h[0] / grid, h[1] / grid, h[2] / grid, h[3] / grid, h[4] / grid, h[8] / grid, h[9] / grid, h[10] / grid, h[5] / grid, grid, prm.n_tiles, prm.k_blocks,
+                prm.n_stages);
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_wait_cycles, z, sizeof(z));
+    }
     return ZB200_OK;
 }
 

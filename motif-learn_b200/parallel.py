@@ -1,0 +1,90 @@
+"""Multi-GPU sharding of the Zernike path: one process per GPU, torch.distributed plumbing.
+
+The path has no mid-computation exchange: patch stacks shard by contiguous
+patch ranges, frame batches by frames, a single large frame by row bands whose halo rows are
+read from the (replicated, <= 67 MB) frame itself -- no halo exchange.  The only collective is
+the optional final gather of the feature / score shards (NCCL over NVLink on GPUs, gloo in the
+CPU tests).  The reference is single-process; nothing here mirrors reference code.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) of ``n_items`` for ``rank``: sizes differ by at most one,
+    the first ``n_items % world`` ranks get the extra item, every item is owned exactly once."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(int(n_items), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_items: int, world: int) -> List[int]:
+    return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
+
+
+def row_band(height: int, rank: int, world: int) -> Tuple[int, int]:
+    """(row0, rows) of the output row band owned by ``rank`` for image-tile sharding.  The band's
+    windows reach size//2 rows above and size-1-size//2 below; those halo rows are read from the
+    full frame every rank holds (zero beyond the image), so bands need no exchange."""
+    lo, hi = shard_range(height, rank, world)
+    return lo, hi - lo
+
+
+def dist_info():
+    """(rank, world) of the default process group, (0, 1) when torch.distributed is not initialised."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def gather_ragged(local, dim: int = 0, sizes: Sequence[int] | None = None, group=None):
+    """All-gather tensors whose extent along ``dim`` differs per rank; returns the concatenation
+    in rank order on every rank.  Sizes are exchanged first unless given; shards are padded to
+    the largest one so a single fixed-size all_gather moves the payload."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist_info()
+    if world == 1:
+        return local
+    if sizes is None:
+        mine = torch.tensor([local.shape[dim]], dtype=torch.int64, device=local.device)
+        all_sizes = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(all_sizes, mine, group=group)
+        sizes = [int(s.item()) for s in all_sizes]
+    biggest = max(sizes)
+    moved = local.movedim(dim, 0).contiguous()
+    if moved.shape[0] < biggest:
+        pad = torch.zeros((biggest - moved.shape[0],) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
+        moved = torch.cat([moved, pad], dim=0)
+    parts = [torch.empty_like(moved) for _ in range(world)]
+    dist.all_gather(parts, moved, group=group)
+    out = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+    return out.movedim(0, dim)
+
+
+def transform_patches_sharded(transform: Callable, patches, gather: bool = True):
+    """Project this rank's contiguous shard of a replicated patch stack and (optionally) gather the
+    feature rows of all ranks.  ``transform`` maps a patch tensor (n, k, k) to a tensor (n, F) --
+    e.g. ``lambda x: zps.transform(x).data``."""
+    rank, world = dist_info()
+    lo, hi = shard_range(int(patches.shape[0]), rank, world)
+    local = transform(patches[lo:hi])
+    if not gather or world == 1:
+        return local
+    return gather_ragged(local, dim=0, sizes=shard_sizes(int(patches.shape[0]), world))
+
+
+def symmetry_map_sharded(band_fn: Callable, height: int, gather: bool = True):
+    """Image-tile sharding of one frame: ``band_fn(row0, rows)`` returns this rank's (F, rows, W)
+    score band (e.g. ``lambda r0, r: zps.symmetry_map(img, folds, row0=r0, rows=r)``); bands are
+    concatenated along the row axis in rank order."""
+    rank, world = dist_info()
+    row0, rows = row_band(height, rank, world)
+    band = band_fn(row0, rows)
+    if not gather or world == 1:
+        return band
+    return gather_ragged(band, dim=1, sizes=shard_sizes(height, world))
