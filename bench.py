@@ -31,6 +31,9 @@ PATCH = 64
 MAP_SIZE = 2048
 MAP_WINDOW = 48
 FOLDS = [2, 3, 4, 6]
+# DRAM bytes per launch of the projection kernel at the default batch, from the committed ncu
+# captures (profiles/r01_prof_tc3_raw.csv, r01_prof_tc1_raw.csv): read + write
+NCU_TRAFFIC = {"tf32x3": 4.351198e9 + 42.209e6, "tf32": 4.311022e9 + 53.497e6}
 
 
 def peaks():
@@ -47,7 +50,7 @@ def peaks():
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.01):
+    def __init__(self, index: int, period_s: float = 0.002):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -255,8 +258,11 @@ def bench_patches(torch, dist, rank, world, args, pk):
     achieved = alg_bytes * args.steps / (ms / 1e3) / 1e9
     flops = 2.0 * batch * PATCH * PATCH * n_modes
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-            "kernel": "project_tc_kernel" if prec != "fp32" else "project_simt_kernel",
+            "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get(prec) if batch == 262144 else None,
+            "traffic_source": "profiles/r01 ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch",
+            "peak_source": pk["source"],
+            "kernel": {"fp32": "project_simt_kernel", "tf32": "project_tc_kernel<plain>",
+                       "tf32x3": "project_tc3_kernel<plain>"}[prec],
             "algorithmic_bytes_per_launch": alg_bytes,
             "tflops": flops * args.steps / (ms / 1e3) / 1e12}
 
@@ -315,7 +321,7 @@ def bench_map(torch, dist, rank, world, args, pk):
     ach = flops * steps / (ms / 1e3) / 1e12
     tf32_peak = pk["bf16_tflops"] / 2.0
     roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-            "traffic": None, "peak_source": pk["source"] + " bf16 / 2 (tf32 dense rate)",
+            "traffic": 18.80e6 + 17.24e6, "peak_source": pk["source"] + " bf16 / 2 (tf32 dense rate)",
             "kernel": "map_simt_kernel<scores>", "algorithmic_flops_per_launch": flops}
     # end to end: numpy frame in, numpy scores out
     zp_host = ZPs(N_MAX, MAP_WINDOW, precision=zp.precision, output="numpy")
@@ -339,7 +345,7 @@ def bench_map(torch, dist, rank, world, args, pk):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="patches", choices=["patches", "map"])
