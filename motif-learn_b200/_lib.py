@@ -39,6 +39,7 @@ SIGNATURES = {
     "zb200_launch_count": (_i64, []),
     "zb200_reset_launch_count": (None, []),
     "zb200_plan_supports": (_int, [_vp, _int, _int]),
+    "zb200_plan_supports_map": (_int, [_vp, _int]),
     "zb200_num_modes": (_int, [_int]),
     "zb200_num_complex_modes": (_int, [_int]),
     "zb200_mode_table": (_int, [_int, _i32p, _i32p]),

@@ -183,6 +183,12 @@ extern "C" int zb200_plan_supports(const zb200_plan* p, int precision, int out_k
     return 0;
 }
 
+extern "C" int zb200_plan_supports_map(const zb200_plan* p, int precision) {
+    if (!p) return 0;
+    if (precision == ZB200_PREC_FP32) return 1;
+    return map_tc_supported(p, precision) ? 1 : 0;
+}
+
 // ---- K3 ---------------------------------------------------------------------------------------
 static int project_any(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind,
                        void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds,
@@ -320,10 +326,8 @@ extern "C" int zb200_moment_map_f32(const zb200_plan* p, const float* d_img, int
     int rc = check_map_args(p, d_img, H, W, row0, rows);
     if (rc) return rc;
     ZB_CHECK_ARG(d_out || rows == 0, "map: null output");
-    if (precision != ZB200_PREC_FP32) {
-        set_error("dense map: only ZB200_PREC_FP32 is implemented in this build");
-        return ZB200_EUNSUP;
-    }
+    if (precision != ZB200_PREC_FP32)
+        return map_tc(p, d_img, H, W, row0, rows, precision, d_out, nullptr, nullptr, nullptr, 0, 0, as_stream(stream));
     return map_simt(p, d_img, H, W, row0, rows, d_out, nullptr, nullptr, nullptr, 0, 0, as_stream(stream));
 }
 
@@ -334,12 +338,11 @@ extern "C" int zb200_symmetry_map_f32(const zb200_plan* p, const float* d_img, i
     if (rc) return rc;
     ZB_CHECK_ARG(d_scores || rows == 0, "symmetry map: null output");
     ZB_CHECK_ARG(norm_kind >= ZB200_NORM_NONE && norm_kind <= ZB200_NORM_INF, "symmetry map: bad norm kind");
-    if (precision != ZB200_PREC_FP32) {
-        set_error("dense map: only ZB200_PREC_FP32 is implemented in this build");
-        return ZB200_EUNSUP;
-    }
     cudaStream_t s = as_stream(stream);
     rc = upload_weights(p, h_weights, h_select, n_folds, p->n_modes, p->real.rows_pad, s);
     if (rc) return rc;
+    if (precision != ZB200_PREC_FP32)
+        return map_tc(p, d_img, H, W, row0, rows, precision, nullptr, d_scores, p->d_weights, p->d_select, n_folds,
+                      norm_kind, s);
     return map_simt(p, d_img, H, W, row0, rows, nullptr, d_scores, p->d_weights, p->d_select, n_folds, norm_kind, s);
 }

@@ -68,6 +68,7 @@ struct Operand {
     // sizes C = 1, 2, 4 (index log2 C): each CTA of a cluster fetches 1/C of the rows and multicasts
     CUtensorMap tmap_hi[3];
     CUtensorMap tmap_cb[3];
+    CUtensorMap tmap_lo_f32[3];   // over the fp32 `lo` operand (dense-map 3xTF32 path)
     int max_cluster = 1;     // largest C with rows_pad % (8 C) == 0
     bool has_tmap = false;
 };
@@ -121,6 +122,11 @@ bool tc_supported(const zb200_plan* plan, int precision, bool complex_order);
 int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,
              float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds,
              int norm_kind, cudaStream_t s);
+
+bool map_tc_supported(const zb200_plan* plan, int precision);
+int map_tc(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows, int precision,
+           float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
+           cudaStream_t s);
 
 int upload_weights(const zb200_plan* plan, const float* h_weights, const uint8_t* h_select, int n_folds,
                    int n_cols, int cols_pad, cudaStream_t s);

@@ -173,9 +173,9 @@ class ZPs(BaseEstimator, TransformerMixin):
     def _precision_code(self, for_map: bool = False) -> int:
         lib = _lib.load()
         if self.precision == "auto":
-            if not for_map and lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3, _lib.OUT_REAL):
-                return _lib.PREC_TF32X3
-            return _lib.PREC_FP32
+            ok = (lib.zb200_plan_supports_map(self._plan, _lib.PREC_TF32X3) if for_map
+                  else lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3, _lib.OUT_REAL))
+            return _lib.PREC_TF32X3 if ok else _lib.PREC_FP32
         return _lib.PRECISIONS[self.precision]
 
     def _want_host(self, given) -> bool:

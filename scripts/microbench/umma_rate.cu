@@ -118,7 +118,13 @@ __global__ void __launch_bounds__(128, 1) bench_lean(int n, int iters, unsigned 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
     if (warp == 1 && lane == 0) {
-        const uint64_t da = make_desc_sw128(smem_u32(smem));
+        uint64_t da = make_desc_sw128(smem_u32(smem));
+        if (kMode == 4) {   // un-swizzled K-major, rows 16 B apart (overlapping): LBO 16 B, SBO 128 B
+            da = (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)8 << 32) | ((uint64_t)1 << 46);
+        }
+        if (kMode == 5) {   // un-swizzled K-major canonical: LBO 128 B, SBO 256 B
+            da = (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4) | ((uint64_t)8 << 16) | ((uint64_t)16 << 32) | ((uint64_t)1 << 46);
+        }
         const uint64_t db = make_desc_sw128(smem_u32(smem + 16384));
         const uint32_t a_t = tmem + 448;
         const uint32_t id = idesc(n, 2);
@@ -168,6 +174,8 @@ int main() {
         run_lean<0>("SS same D", n, d);
         run_lean<1>("TS same D", n, d);
     }
+    run_lean<5>("SS A un-swizzled canonical", 96, d);
+    run_lean<4>("SS A Toeplitz (rows 16 B apart)", 96, d);
     for (int n : {96, 192}) {
         run_lean<2>("SS 2 D alternating", n, d);
         run_lean<3>("SS 4 on D0 then 4 on D1", n, d);
