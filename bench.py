@@ -50,7 +50,7 @@ def peaks():
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.002):
+    def __init__(self, index: int, period_s: float = 0.02):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -303,7 +303,8 @@ def bench_map(torch, dist, rank, world, args, pk):
     from motif_learn_b200.datasets import honeycomb_image
     from motif_learn_b200.features import ZPs
     dev = torch.cuda.current_device()
-    zp = ZPs(N_MAX, MAP_WINDOW, precision="fp32" if args.precision == "auto" else args.precision)
+    zp = ZPs(N_MAX, MAP_WINDOW, precision=args.precision)
+    prec = {0: "fp32", 1: "tf32", 2: "tf32x3"}[zp._precision_code(for_map=True)]
     img, _ = honeycomb_image(MAP_SIZE, bond=12.0, seed=rank)
     dimg = torch.from_numpy(img).cuda()
     scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -321,10 +322,12 @@ def bench_map(torch, dist, rank, world, args, pk):
     ach = flops * steps / (ms / 1e3) / 1e12
     tf32_peak = pk["bf16_tflops"] / 2.0
     roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-            "traffic": 18.80e6 + 17.24e6, "peak_source": pk["source"] + " bf16 / 2 (tf32 dense rate)",
-            "kernel": "map_simt_kernel<scores>", "algorithmic_flops_per_launch": flops}
+            "traffic": None, "peak_source": pk["source"] + " bf16 / 2 (tf32 dense rate)",
+            "kernel": "map_simt_kernel<scores>" if prec == "fp32" else "map_tc_kernel<scores>",
+            "algorithmic_flops_per_launch": flops,
+            "executed_tflops": ach * {"fp32": 1, "tf32": 1, "tf32x3": 3}[prec] * (96.0 / len(zp.n) if prec != "fp32" else 1.0)}
     # end to end: numpy frame in, numpy scores out
-    zp_host = ZPs(N_MAX, MAP_WINDOW, precision=zp.precision, output="numpy")
+    zp_host = ZPs(N_MAX, MAP_WINDOW, precision=args.precision, output="numpy")
     host = torch.empty((MAP_SIZE, MAP_SIZE), dtype=torch.float32, pin_memory=True)
     host.copy_(dimg)
     t0 = time.perf_counter()
@@ -335,9 +338,10 @@ def bench_map(torch, dist, rank, world, args, pk):
     e2e = {"value": mpix * world * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": MAP_SIZE * MAP_SIZE * 4,
            "d2h_bytes_per_step": int(res.size * 8), "steps": e2e_steps, "api": "ZPs.symmetry_map(numpy) -> numpy"}
     return {"metric": "symmetry_map_mpix_per_sec", "value": value, "unit": "Mpix/s", "ms_per_step": ms / steps,
-            "steps": steps, "dtype": "f32",
+            "steps": steps, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)"}[prec],
             "config": {"workload": f"symmetry map {MAP_SIZE}x{MAP_SIZE} n_max={N_MAX} window={MAP_WINDOW} "
-                                   f"folds={FOLDS} (BASELINE configs[1])", "l2": "256 MiB scratch write between steps",
+                                   f"folds={FOLDS} (BASELINE configs[1])", "precision": prec,
+                       "l2": "256 MiB scratch write between steps",
                        "parallelism": f"one frame per GPU x{world}, no collective"},
             "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
 
@@ -352,7 +356,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
     ap.add_argument("--batch", type=int, default=262144, help="patches per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=65536)
-    ap.add_argument("--map-steps", type=int, default=5)
+    ap.add_argument("--map-steps", type=int, default=20)
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

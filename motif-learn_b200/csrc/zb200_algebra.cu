@@ -175,19 +175,25 @@ __global__ void cast_kernel(const S* __restrict__ in, D* __restrict__ out, long 
     if (i < n) out[i] = (D)in[i];
 }
 
-int upload_weights(const zb200_plan* p, const float* h_weights, const uint8_t* h_select, int n_folds,
-                   int n_cols, int cols_pad, cudaStream_t s) {
+// Score tables for the fused kernels: weights [n_folds][cols_pad] (zero padded) followed by the
+// select mask [cols_pad], in one stream-ordered allocation (no host/device synchronisation: the
+// copy from pageable memory is staged by the runtime before it returns).  Free with cudaFreeAsync
+// on the same stream after the consuming kernel has been enqueued.
+int upload_weights(const float* h_weights, const uint8_t* h_select, int n_folds, int n_cols, int cols_pad,
+                   cudaStream_t s, float** d_w, uint8_t** d_sel) {
     ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
     ZB_CHECK_ARG(h_weights && h_select, "weights/select must not be null");
-    // stage through the plan's pinned buffer so the async copy is truly asynchronous
-    ZB_CUDA(cudaStreamSynchronize(s));   // previous use of the staging buffer has drained
-    float* hw = p->h_pin_w;
-    uint8_t* hs = reinterpret_cast<uint8_t*>(hw + (size_t)kMaxFolds * cols_pad);
+    const size_t wbytes = sizeof(float) * (size_t)n_folds * cols_pad;
+    std::vector<unsigned char> host(wbytes + cols_pad, 0);
+    float* hw = reinterpret_cast<float*>(host.data());
     for (int f = 0; f < n_folds; ++f)
-        for (int c = 0; c < cols_pad; ++c) hw[(size_t)f * cols_pad + c] = c < n_cols ? h_weights[(size_t)f * n_cols + c] : 0.f;
-    for (int c = 0; c < cols_pad; ++c) hs[c] = c < n_cols ? (h_select[c] ? 1 : 0) : 0;
-    ZB_CUDA(cudaMemcpyAsync(p->d_weights, hw, sizeof(float) * n_folds * cols_pad, cudaMemcpyHostToDevice, s));
-    ZB_CUDA(cudaMemcpyAsync(p->d_select, hs, cols_pad, cudaMemcpyHostToDevice, s));
+        for (int c = 0; c < n_cols; ++c) hw[(size_t)f * cols_pad + c] = h_weights[(size_t)f * n_cols + c];
+    for (int c = 0; c < n_cols; ++c) host[wbytes + c] = h_select[c] ? 1 : 0;
+    void* dev = nullptr;
+    ZB_CUDA(cudaMallocAsync(&dev, host.size(), s));
+    ZB_CUDA(cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, s));
+    *d_w = static_cast<float*>(dev);
+    *d_sel = static_cast<uint8_t*>(dev) + wbytes;
     return ZB200_OK;
 }
 

@@ -96,9 +96,6 @@ extern "C" void zb200_plan_destroy(zb200_plan* p) {
     cudaFree(p->d_m);
     free_operand(p->real);
     free_operand(p->cplx);
-    cudaFree(p->d_weights);
-    cudaFree(p->d_select);
-    if (p->h_pin_w) cudaFreeHost(p->h_pin_w);
     for (int i = 0; i < 2; ++i) {
         if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
         if (p->pin_out[i]) cudaFreeHost(p->pin_out[i]);
@@ -148,6 +145,16 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
         }                                                                              \
     } while (0)
 
+    {
+        // keep stream-ordered scratch (score tables, operand planes of the dense map) cached in the
+        // default pool across synchronisation points instead of returning it to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     ZB_PLAN_CUDA(cudaMalloc(&p->basis64, sizeof(double) * (size_t)p->n_modes * p->kk));
     ZB_PLAN_CUDA(cudaMalloc(&p->d_n, sizeof(int32_t) * p->n_modes));
     ZB_PLAN_CUDA(cudaMalloc(&p->d_m, sizeof(int32_t) * p->n_modes));
@@ -155,10 +162,6 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
     ZB_PLAN_CUDA(cudaMemcpy(p->d_m, p->h_m, sizeof(int32_t) * p->n_modes, cudaMemcpyHostToDevice));
     ZB_PLAN_TRY(alloc_operand(p->real, p->n_modes, p->k_pad));
     ZB_PLAN_TRY(alloc_operand(p->cplx, 2 * p->n_complex, p->k_pad));
-    const int wcols = p->cplx.rows_pad > p->real.rows_pad ? p->cplx.rows_pad : p->real.rows_pad;
-    ZB_PLAN_CUDA(cudaMalloc(&p->d_weights, sizeof(float) * kMaxFolds * wcols));
-    ZB_PLAN_CUDA(cudaMalloc(&p->d_select, wcols));
-    ZB_PLAN_CUDA(cudaMallocHost(&p->h_pin_w, sizeof(float) * kMaxFolds * wcols + wcols));
     ZB_PLAN_TRY(launch_basis(p, nullptr));
     ZB_PLAN_TRY(launch_pack(p, nullptr));
     ZB_PLAN_CUDA(cudaDeviceSynchronize());
@@ -227,13 +230,11 @@ extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG(d_patches && d_scores, "project_scores: null device pointer");
     cudaStream_t s = as_stream(stream);
-    int rc = upload_weights(p, h_weights, h_select, n_folds, p->n_modes, p->real.rows_pad, s);
-    if (rc) return rc;
     if (precision == ZB200_PREC_FP32) {
         // SIMT contraction into a temporary, then the score kernel (two launches, no fusion)
         float* tmp = nullptr;
         ZB_CUDA(cudaMallocAsync(&tmp, sizeof(float) * (size_t)n * p->n_modes, s));
-        rc = project_simt(p, d_patches, n, tmp, s);
+        int rc = project_simt(p, d_patches, n, tmp, s);
         if (!rc) {
             std::vector<double> wd((size_t)n_folds * p->n_modes);
             for (size_t i = 0; i < wd.size(); ++i) wd[i] = h_weights[i];
@@ -243,8 +244,13 @@ extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float
         cudaFreeAsync(tmp, s);
         return rc;
     }
-    return project_any(p, d_patches, n, precision, ZB200_OUT_REAL, d_scores, nullptr, p->d_weights, p->d_select,
-                       n_folds, norm_kind, s);
+    float* d_w = nullptr;
+    uint8_t* d_sel = nullptr;
+    int rc = upload_weights(h_weights, h_select, n_folds, p->n_modes, p->real.rows_pad, s, &d_w, &d_sel);
+    if (rc) return rc;
+    rc = project_any(p, d_patches, n, precision, ZB200_OUT_REAL, d_scores, nullptr, d_w, d_sel, n_folds, norm_kind, s);
+    cudaFreeAsync(d_w, s);
+    return rc;
 }
 
 // Host-buffer pipeline: chunks of patches flow  host -> (pinned) -> HBM -> kernel -> pinned -> host.
@@ -339,10 +345,14 @@ extern "C" int zb200_symmetry_map_f32(const zb200_plan* p, const float* d_img, i
     ZB_CHECK_ARG(d_scores || rows == 0, "symmetry map: null output");
     ZB_CHECK_ARG(norm_kind >= ZB200_NORM_NONE && norm_kind <= ZB200_NORM_INF, "symmetry map: bad norm kind");
     cudaStream_t s = as_stream(stream);
-    rc = upload_weights(p, h_weights, h_select, n_folds, p->n_modes, p->real.rows_pad, s);
+    float* d_w = nullptr;
+    uint8_t* d_sel = nullptr;
+    rc = upload_weights(h_weights, h_select, n_folds, p->n_modes, p->real.rows_pad, s, &d_w, &d_sel);
     if (rc) return rc;
     if (precision != ZB200_PREC_FP32)
-        return map_tc(p, d_img, H, W, row0, rows, precision, nullptr, d_scores, p->d_weights, p->d_select, n_folds,
-                      norm_kind, s);
-    return map_simt(p, d_img, H, W, row0, rows, nullptr, d_scores, p->d_weights, p->d_select, n_folds, norm_kind, s);
+        rc = map_tc(p, d_img, H, W, row0, rows, precision, nullptr, d_scores, d_w, d_sel, n_folds, norm_kind, s);
+    else
+        rc = map_simt(p, d_img, H, W, row0, rows, nullptr, d_scores, d_w, d_sel, n_folds, norm_kind, s);
+    cudaFreeAsync(d_w, s);
+    return rc;
 }

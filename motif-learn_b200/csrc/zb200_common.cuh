@@ -93,9 +93,6 @@ struct zb200_plan {
     int32_t h_m[1024];
     zb200::Operand real;          // real row order
     zb200::Operand cplx;          // complex-interleaved row order
-    float* d_weights = nullptr;   // scratch for score weights  [ZB200_MAX_FOLDS][rows_pad]
-    uint8_t* d_select = nullptr;
-    float* h_pin_w = nullptr;     // pinned staging for the two above
     void* pin_in[2] = {nullptr, nullptr};   // pinned staging for the host entry point
     void* pin_out[2] = {nullptr, nullptr};
     void* dev_in[2] = {nullptr, nullptr};
@@ -128,6 +125,6 @@ int map_tc(const zb200_plan* plan, const float* d_img, int H, int W, int row0, i
            float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
            cudaStream_t s);
 
-int upload_weights(const zb200_plan* plan, const float* h_weights, const uint8_t* h_select, int n_folds,
-                   int n_cols, int cols_pad, cudaStream_t s);
+int upload_weights(const float* h_weights, const uint8_t* h_select, int n_folds, int n_cols, int cols_pad,
+                   cudaStream_t s, float** d_w, uint8_t** d_sel);
 }  // namespace zb200
