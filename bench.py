@@ -98,12 +98,15 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- reference arm
 def cpu_threads():
+    """Give the BLAS behind numpy.dot every host core (torchrun exports OMP_NUM_THREADS=1) and
+    return the thread count actually in use."""
     try:
-        import numpy  # noqa: F401  (loads the BLAS whose pool is queried)
-        from threadpoolctl import threadpool_info
+        import numpy  # noqa: F401  (loads the BLAS whose pool is configured)
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
         return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
-        return os.cpu_count() or 1
+        return 1
 
 
 def cpu_patches(n_sample: int, repeats: int):
@@ -128,7 +131,7 @@ def cpu_patches(n_sample: int, repeats: int):
     return n_sample / min(times), times
 
 
-def cpu_map(size: int, repeats: int = 1):
+def cpu_map(size: int, repeats: int = 1, window: int = MAP_WINDOW):
     """The reference's CPU algorithm for the map path (scipy fftconvolve per mode + rot_maps,
     _zps.py:159-193, _zmoments.py:420-462) through the oracle port on a size x size crop."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -136,7 +139,7 @@ def cpu_map(size: int, repeats: int = 1):
     import zernike_oracle as zo
     from motif_learn_b200.datasets import honeycomb_image
     img, _ = honeycomb_image(size, bond=12.0, seed=0)
-    n, m, basis = zo.zernike_basis(N_MAX, MAP_WINDOW)
+    n, m, basis = zo.zernike_basis(N_MAX, window)
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -166,16 +169,17 @@ def run_reference(args, rank, world):
                 "sample": f"{n_sample} float32 64x64 lattice patches per step, numpy.dot float64 (reference algorithm)"}
     else:
         size = 512
+        window = 64 if args.workload == "map4k" else MAP_WINDOW
         per_step = []
         for _ in range(min(args.warmup, 1)):
-            cpu_map(256)
+            cpu_map(256, window=window)
         for _ in range(args.steps):
-            _, dt = cpu_map(size)
+            _, dt = cpu_map(size, window=window)
             per_step.append(dt)
         total = sum(per_step)
         value = size * size * args.steps / 1e6 / total
         line = {"metric": "symmetry_map_mpix_per_sec", "unit": "Mpix/s",
-                "config": {"workload": f"symmetry map n_max={N_MAX} window={MAP_WINDOW} folds={FOLDS}",
+                "config": {"workload": f"symmetry map n_max={N_MAX} window={window} folds={FOLDS}",
                            "image": f"{size}x{size} crop of the {MAP_SIZE}x{MAP_SIZE} frame"},
                 "sample": f"{size}x{size} crop per step: 91 scipy.fftconvolve (1 thread) + rot_maps"}
     line.update({"impl": "reference", "value": value, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -298,27 +302,37 @@ def bench_patches(torch, dist, rank, world, args, pk):
     return line
 
 
-def bench_map(torch, dist, rank, world, args, pk):
+def bench_map(torch, dist, rank, world, args, pk, tiled=False):
+    """tiled=False: BASELINE configs[1], one 2048^2 frame per GPU (weak scaling over frames).
+    tiled=True: BASELINE configs[3], ONE 4096^2 frame with defects, 64-px window, output row bands
+    spread over the GPUs (strong scaling; halo rows come from the replicated frame, no exchange)."""
     import numpy as np
     from motif_learn_b200.datasets import honeycomb_image
     from motif_learn_b200.features import ZPs
+    from motif_learn_b200.parallel import row_band
+    MAP_SIZE, MAP_WINDOW = (4096, 64) if tiled else (2048, 48)
     dev = torch.cuda.current_device()
     zp = ZPs(N_MAX, MAP_WINDOW, precision=args.precision)
     prec = {0: "fp32", 1: "tf32", 2: "tf32x3"}[zp._precision_code(for_map=True)]
-    img, _ = honeycomb_image(MAP_SIZE, bond=12.0, seed=rank)
+    if tiled:
+        img, _ = honeycomb_image(MAP_SIZE, bond=12.0, seed=0, vacancy_frac=0.01, dopant_frac=0.005)
+        row0, rows = row_band(MAP_SIZE, rank, world)
+    else:
+        img, _ = honeycomb_image(MAP_SIZE, bond=12.0, seed=rank)
+        row0, rows = 0, MAP_SIZE
     dimg = torch.from_numpy(img).cuda()
     scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     holder = {}
 
     def step():
-        holder["s"] = zp.symmetry_map(dimg, FOLDS)
+        holder["s"] = zp.symmetry_map(dimg, FOLDS, row0=row0, rows=rows)
 
     steps = max(2, min(args.steps, args.map_steps))
     ms, clocks, launches = timed(torch, dist, world, step, steps, min(args.warmup, 3) if args.warmup >= 3 else 3, dev,
                                  between=lambda: flush_l2(torch, scratch))
     mpix = MAP_SIZE * MAP_SIZE / 1e6
-    value = mpix * world * steps / (ms / 1e3)
-    flops = 2.0 * MAP_SIZE * MAP_SIZE * MAP_WINDOW * MAP_WINDOW * len(zp.n)
+    value = mpix * (1 if tiled else world) * steps / (ms / 1e3)
+    flops = 2.0 * rows * MAP_SIZE * MAP_WINDOW * MAP_WINDOW * len(zp.n)
     ach = flops * steps / (ms / 1e3) / 1e12
     tf32_peak = pk["bf16_tflops"] / 2.0
     roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
@@ -333,16 +347,22 @@ def bench_map(torch, dist, rank, world, args, pk):
     t0 = time.perf_counter()
     e2e_steps = 2
     for _ in range(e2e_steps):
-        res = zp_host.symmetry_map(host.numpy(), FOLDS)
+        res = zp_host.symmetry_map(host.numpy(), FOLDS, row0=row0, rows=rows)
     dt = time.perf_counter() - t0
-    e2e = {"value": mpix * world * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": MAP_SIZE * MAP_SIZE * 4,
+    if world > 1:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    e2e = {"value": mpix * (1 if tiled else world) * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": MAP_SIZE * MAP_SIZE * 4,
            "d2h_bytes_per_step": int(res.size * 8), "steps": e2e_steps, "api": "ZPs.symmetry_map(numpy) -> numpy"}
     return {"metric": "symmetry_map_mpix_per_sec", "value": value, "unit": "Mpix/s", "ms_per_step": ms / steps,
             "steps": steps, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)"}[prec],
+            "scaling": "strong" if tiled else "weak",
             "config": {"workload": f"symmetry map {MAP_SIZE}x{MAP_SIZE} n_max={N_MAX} window={MAP_WINDOW} "
-                                   f"folds={FOLDS} (BASELINE configs[1])", "precision": prec,
+                                   f"folds={FOLDS} (BASELINE configs[{3 if tiled else 1}])", "precision": prec,
                        "l2": "256 MiB scratch write between steps",
-                       "parallelism": f"one frame per GPU x{world}, no collective"},
+                       "parallelism": (f"one frame, {world} row bands with halo rows from the replicated frame, no collective"
+                                       if tiled else f"one frame per GPU x{world}, no collective")},
             "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
 
 
@@ -352,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="patches", choices=["patches", "map"])
+    ap.add_argument("--workload", default="patches", choices=["patches", "map", "map4k"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
     ap.add_argument("--batch", type=int, default=262144, help="patches per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=65536)
@@ -377,11 +397,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pk = peaks()
-    primary = bench_patches if args.workload == "patches" else bench_map
-    secondary = bench_map if args.workload == "patches" else bench_patches
+    if args.workload == "map4k":
+        primary = lambda *a: bench_map(*a, tiled=True)          # noqa: E731
+        secondary = bench_patches
+    else:
+        primary = bench_patches if args.workload == "patches" else bench_map
+        secondary = bench_map if args.workload == "patches" else bench_patches
     line = primary(torch, dist, rank, world, args, pk)
     line.setdefault("steps", args.steps)
-    line.update({"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+    line.setdefault("scaling", "weak")
+    line.update({"n_gpus": world, "warmup": args.warmup, "higher_is_better": True,
                  "vs_baseline": None, "data": "synthetic"})
     if not args.no_also:
         try:
@@ -402,7 +427,7 @@ def main():
                 line["also"]["cpu_baseline"] = {"value": mv, "unit": "Mpix/s", "cores": 1, "kind": "port",
                                                 "sample": f"384x384 crop, 91 scipy.fftconvolve + rot_maps, {dt:.1f} s"}
         else:
-            mv, dt = cpu_map(512)
+            mv, dt = cpu_map(512, window=64 if args.workload == "map4k" else MAP_WINDOW)
             line["cpu_baseline"] = {"value": mv, "unit": "Mpix/s", "cores": 1, "kind": "port",
                                     "sample": f"512x512 crop, 91 scipy.fftconvolve (1 thread, reference algorithm "
                                               f"_zps.py:159-193 via oracle port) + rot_maps, {dt:.1f} s"}

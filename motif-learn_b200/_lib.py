@@ -62,6 +62,7 @@ SIGNATURES = {
     "zb200_rotate": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, C.c_double, _vp, _vp]),
     "zb200_rot_scores": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, _vp, _int, _int, _vp, _i64, _i64, _vp]),
     "zb200_mirror_scores": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, _vp, _int, _vp, _vp]),
+    "zb200_complex_abs_phase": (_int, [_int, _vp, _i64, _vp, _vp, _vp]),
     "zb200_cast": (_int, [_int, _vp, _int, _vp, _i64, _vp]),
 }
 

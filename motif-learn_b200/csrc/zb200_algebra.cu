@@ -169,6 +169,15 @@ __global__ void mirror_kernel(const Cx<T>* __restrict__ in, long long n_items, i
     out[it] = best;
 }
 
+template <typename T>
+__global__ void abs_phase_kernel(const Cx<T>* __restrict__ in, long long n, T* __restrict__ mag_out, T* __restrict__ ph_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Cx<T> v = in[i];
+    mag_out[i] = hypot(v.re, v.im);
+    if (ph_out) ph_out[i] = atan2(v.im, v.re);
+}
+
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ in, D* __restrict__ out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,6 +364,19 @@ extern "C" int zb200_mirror_scores(int dtype, const void* d_in, int64_t n_items,
         mirror_kernel<T><<<grid_for(n_items, 128), 128, 0, s>>>(static_cast<const Cx<T>*>(d_in), n_items, n_c, is, ms,
                                                               static_cast<const float2*>(sc.ptr), n_theta,
                                                               static_cast<T*>(d_out));
+    })
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+extern "C" int zb200_complex_abs_phase(int dtype, const void* d_in, int64_t n, void* d_abs, void* d_phase, void* stream) {
+    ZB_CHECK_ARG(n >= 0, "complex_abs_phase: negative count");
+    if (n == 0) return ZB200_OK;
+    ZB_CHECK_ARG(d_in && d_abs, "complex_abs_phase: null pointer");
+    cudaStream_t s = as_stream(stream);
+    ZB_DISPATCH_DTYPE(dtype, {
+        abs_phase_kernel<T><<<grid_for(n, 256), 256, 0, s>>>(static_cast<const Cx<T>*>(d_in), n, static_cast<T*>(d_abs),
+                                                           static_cast<T*>(d_phase));
     })
     ZB_LAUNCHED();
     return ZB200_OK;

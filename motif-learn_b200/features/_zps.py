@@ -225,11 +225,18 @@ class ZPs(BaseEstimator, TransformerMixin):
         if not lib.zb200_plan_supports(self._plan, prec, code):
             # the fused epilogue is not available for this shape/precision: real moments from the
             # projection kernel, then the packing kernel (two launches, still all on the GPU)
-            zc = self._transform_patches(images).to_complex()
+            dev_in = images if is_torch(images) else torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
+            zc = self._transform_patches(dev_in.to(device="cuda")).to_complex().data.contiguous()
             if kind == "complex":
-                return zc.data
-            data = zc.data if is_torch(zc.data) else torch.from_numpy(zc.data)
-            return data.abs() if kind == "abs" else (data.abs(), data.angle())
+                return zc
+            real_t = torch.float32 if zc.dtype == torch.complex64 else torch.float64
+            mag = torch.empty(zc.shape, dtype=real_t, device=zc.device)
+            ph = torch.empty_like(mag) if kind == "abs_phase" else None
+            _lib.check(lib.zb200_complex_abs_phase(_lib.F32 if real_t == torch.float32 else _lib.F64, int(zc.data_ptr()),
+                                                   zc.numel(), int(mag.data_ptr()),
+                                                   None if ph is None else int(ph.data_ptr()), self._stream()),
+                       "complex_abs_phase")
+            return mag if ph is None else (mag, ph)
         dev = images if is_torch(images) else torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
         dev = dev.to(device="cuda", dtype=torch.float32).contiguous()
         n_img, n_c = int(dev.shape[0]), lib.zb200_num_complex_modes(self.n_max)
