@@ -33,7 +33,8 @@ MAP_WINDOW = 48
 FOLDS = [2, 3, 4, 6]
 # DRAM bytes per launch of the projection kernel at the default batch, from the committed ncu
 # captures (profiles/r01_prof_tc3_raw.csv, r01_prof_tc1_raw.csv): read + write
-NCU_TRAFFIC = {"tf32x3": 4.351198e9 + 42.209e6, "tf32": 4.311022e9 + 53.497e6}
+NCU_TRAFFIC = {"tf32x3": 4.330278e9 + 45.745e6, "tf32": 4.317721e9 + 53.717e6}
+NCU_TRAFFIC_MAP = 136.456e6 + 48.684e6      # map_tc_kernel<scores>, 2048^2, profiles/r01_prof_map_raw.csv
 
 
 def peaks():
@@ -336,7 +337,8 @@ def bench_map(torch, dist, rank, world, args, pk, tiled=False):
     ach = flops * steps / (ms / 1e3) / 1e12
     tf32_peak = pk["bf16_tflops"] / 2.0
     roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-            "traffic": None, "peak_source": pk["source"] + " bf16 / 2 (tf32 dense rate)",
+            "traffic": NCU_TRAFFIC_MAP if (prec == "tf32x3" and not tiled) else None,
+            "peak_source": pk["source"] + " bf16 / 2 (tf32 dense rate)",
             "kernel": "map_simt_kernel<scores>" if prec == "fp32" else "map_tc_kernel<scores>",
             "algorithmic_flops_per_launch": flops,
             "executed_tflops": ach * {"fp32": 1, "tf32": 1, "tf32x3": 3}[prec] * (96.0 / len(zp.n) if prec != "fp32" else 1.0)}

@@ -355,3 +355,77 @@ def test_map_equals_gather_plus_projection_at_config2_size(api, torch):
         if sel.any():
             gotm = band[:, torch.from_numpy(ys[sel] - 1000).cuda(), torch.from_numpy(xs[sel]).cuda()].cpu().numpy().T
             fp32_close(gotm, zref[sel])
+
+
+# ---- remaining BASELINE configurations -------------------------------------------------------------
+def test_config3_complex_n20_on_peak_patches(api, torch):
+    """BASELINE config 3 family: complex ZPs n_max=20 on 64x64 patches extracted at atom peaks.
+    Parity on a 4096-patch subset against the oracle (the full 1M stack is a throughput case)."""
+    from motif_learn_b200.datasets import honeycomb_image
+    img, pts = honeycomb_image(1024, bond=12.0, seed=5, angle=17.0, jitter=0.3, noise=0.01)
+    dimg = torch.from_numpy(img).cuda()
+    kp = api.KeyPoints(pts, dimg, 64)
+    patches = kp.extract_patches()
+    assert patches.is_cuda and patches.shape[0] >= 4096
+    patches = patches[:4096].contiguous()
+    host = patches.cpu().numpy()
+    np.testing.assert_array_equal(host, zo.extract_patches(img, kp.pts[:4096], 64))
+    n, m, v = zo.zernike_basis(20, 64)
+    ref = zo.project_patches(host.astype(np.float64), v)
+    refc, n_c, m_c = zo.to_complex(ref, n, m)
+    z = api.ZPs(20, 64)
+    zm = z.transform(patches)
+    fp32_close(zm.data.cpu().numpy(), ref)
+    zc = zm.to_complex()
+    np.testing.assert_array_equal(zc.m, m_c)
+    assert np.abs(zc.data.cpu().numpy() - refc).max() <= 3e-6 * np.abs(refc).max()
+    feats = z.transform_features(patches, "abs")          # falls back to real + packing kernels at n_max=20
+    assert feats.shape == (4096, 121)
+    assert np.abs(feats.cpu().numpy() - np.abs(refc)).max() <= 3e-6 * np.abs(refc).max()
+    mag, ph = z.transform_features(patches, "abs_phase")
+    big = np.abs(refc) > 1e-3 * np.abs(refc).max()
+    dphi = np.angle(np.exp(1j * (ph.cpu().numpy() - np.angle(refc))))
+    assert np.abs(dphi[big]).max() < 1e-3
+
+
+def test_config4_tiled_map_with_defects(api, torch):
+    """BASELINE config 4 geometry (64-px window, frame with vacancies/dopants) on a 1024x1536 frame:
+    row bands computed independently (as the GPUs of one box would) equal the oracle on three bands
+    including the seams, and equal the single-call result bit-exactly."""
+    from motif_learn_b200.datasets import honeycomb_image
+    from motif_learn_b200.parallel import row_band
+    H, W = 1024, 1536
+    img, _ = honeycomb_image((H, W), bond=12.0, seed=11, vacancy_frac=0.01, dopant_frac=0.005)
+    dimg = torch.from_numpy(img).cuda()
+    z = api.ZPs(12, 64)
+    full = z.symmetry_map(dimg, [2, 3, 4, 6])
+    bands = [z.symmetry_map(dimg, [2, 3, 4, 6], row0=r0, rows=r) for r0, r in (row_band(H, k, 4) for k in range(4))]
+    assert torch.equal(torch.cat(bands, dim=1), full)
+    n, m, v = zo.zernike_basis(12, 64)
+    got = full.cpu().numpy()
+    for r0 in (0, 224, 960):                               # top border, a band seam (256 +- 32), bottom border
+        lo, hi = max(0, r0 - 32), min(H, r0 + 64 + 32)
+        sub = img[lo:hi].astype(np.float64)
+        ref = zo.rot_maps(zo.moment_map_fft(sub, v, n, chunk=16), n, m, [2, 3, 4, 6])
+        # rows whose 64-px window lies inside the cropped strip (or touches the true frame border)
+        a = 0 if lo == 0 else 32
+        b = (hi - lo) if hi == H else (hi - lo) - 32
+        assert np.nanmax(np.abs(got[:, lo + a:lo + b] - ref[:, a:b])) < 1e-5
+
+
+def test_config5_frame_batch_gather_then_features(api, torch):
+    """BASELINE config 5 family on 3 frames: peaks -> clear_border -> gather -> ZPs(12,64) -> |Zc|,
+    frame-sharded exactly like the 8-GPU run would (each frame independent)."""
+    from motif_learn_b200.datasets import honeycomb_image
+    z = api.ZPs(12, 64)
+    n, m, v = zo.zernike_basis(12, 64)
+    for seed in (0, 1, 2):
+        img, pts = honeycomb_image(512, bond=12.0, seed=seed, angle=10.0 * seed, jitter=0.3)
+        kp = api.KeyPoints(pts, torch.from_numpy(img).cuda(), 64)
+        np.testing.assert_array_equal(kp.pts, zo.clear_border(pts, img.shape, 64))
+        patches = kp.extract_patches()
+        ref = zo.project_patches(zo.extract_patches(img, kp.pts, 64).astype(np.float64), v)
+        fp32_close(z.transform(patches).data.cpu().numpy(), ref)
+        refabs = np.abs(zo.to_complex(ref, n, m)[0])
+        got = z.transform_features(patches, "abs").cpu().numpy()
+        assert np.abs(got - refabs).max() <= 3e-6 * refabs.max()
