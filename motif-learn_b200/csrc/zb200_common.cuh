@@ -111,9 +111,15 @@ int launch_pack(zb200_plan* plan, cudaStream_t s);
 int init_tensor_maps(zb200_plan* plan);
 
 int project_simt(const zb200_plan* plan, const float* d_patches, int64_t n, float* d_out_real, cudaStream_t s);
+// frame + window corners for the fused gather -> projection path (K2 inside K3)
+struct GatherSource {
+    const float* img;
+    int H, W;
+    const int2* xy0;      // top-left corner (x0, y0) of each window
+};
 int project_tc(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind,
                void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
-               cudaStream_t s);
+               cudaStream_t s, const GatherSource* gather = nullptr);
 bool tc_supported(const zb200_plan* plan, int precision, bool complex_order);
 
 int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,

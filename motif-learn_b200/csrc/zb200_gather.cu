@@ -8,15 +8,19 @@
 
 namespace zb200 {
 
-// One CTA streams whole patches: consecutive lanes read consecutive pixels of a window
-// row (coalesced, arbitrary 4-B alignment) and write consecutive output floats (fully
-// coalesced 128-B lines).  Grid is a multiple of the SM count; CTAs stride over patches.
+// One CTA streams whole patches.  Windows start at arbitrary columns, so reads are 4-byte loads
+// (consecutive lanes -> consecutive pixels of a window row, served by L2: the frame is <= 67 MB),
+// while every thread assembles four consecutive output floats and writes them with one 128-bit
+// store (fully coalesced 512-B warp stores; the output stream is the HBM traffic of this kernel).
+// Grid is a multiple of the SM count; CTAs stride over patches.
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads)
 gather_kernel(const float* __restrict__ img, int H, int W, const double* __restrict__ pts,
               long long n_pts, int k, float* __restrict__ out) {
     const int kk = k * k;
     const int half = k / 2;
+    const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int k4 = k >> 2;
     for (long long p = blockIdx.x; p < n_pts; p += gridDim.x) {
         // np.rint == round-half-to-even == rint() in the default rounding mode
         const int cx = (int)rint(pts[2 * p]);
@@ -24,11 +28,13 @@ gather_kernel(const float* __restrict__ img, int H, int W, const double* __restr
         const int x0 = cx - half, y0 = cy - half;
         float* dst = out + p * (long long)kk;
         const bool interior = x0 >= 0 && y0 >= 0 && x0 + k <= W && y0 + k <= H;
-        if (interior) {
+        if (interior && vec) {
             const float* src = img + (long long)y0 * W + x0;
-            for (int e = threadIdx.x; e < kk; e += kThreads) {
-                const int r = e / k, c = e - r * k;
-                dst[e] = __ldg(src + (long long)r * W + c);
+            for (int v = threadIdx.x; v < (kk >> 2); v += kThreads) {
+                const int r = v / k4, c = (v - r * k4) << 2;
+                const float* s4 = src + (long long)r * W + c;
+                const float4 val = make_float4(__ldg(s4), __ldg(s4 + 1), __ldg(s4 + 2), __ldg(s4 + 3));
+                __stcs(reinterpret_cast<float4*>(dst) + v, val);          // streaming: written once
             }
         } else {
             for (int e = threadIdx.x; e < kk; e += kThreads) {
@@ -40,7 +46,34 @@ gather_kernel(const float* __restrict__ img, int H, int W, const double* __restr
     }
 }
 
+// window corners for the fused path: (x0, y0) = rint(pts) - k/2
+__global__ void corners_kernel(const double* __restrict__ pts, long long n, int k, int2* __restrict__ xy0) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xy0[i] = make_int2((int)rint(pts[2 * i]) - k / 2, (int)rint(pts[2 * i + 1]) - k / 2);
+}
+
 }  // namespace zb200
+
+extern "C" int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_img, int H, int W, const double* d_pts_xy,
+                                       int64_t n_pts, int precision, int out_kind, void* d_out, void* d_out2,
+                                       void* stream) {
+    using namespace zb200;
+    ZB_CHECK_ARG(plan, "project_peaks: plan is null");
+    ZB_CHECK_ARG(H > 0 && W > 0 && n_pts >= 0, "project_peaks: bad shape");
+    ZB_CHECK_ARG(out_kind >= ZB200_OUT_REAL && out_kind <= ZB200_OUT_ABS_PHASE, "project_peaks: bad out_kind %d", out_kind);
+    if (n_pts == 0) return ZB200_OK;
+    ZB_CHECK_ARG(d_img && d_pts_xy && d_out, "project_peaks: null pointer");
+    cudaStream_t s = as_stream(stream);
+    int2* xy0 = nullptr;
+    ZB_CUDA(cudaMallocAsync(&xy0, sizeof(int2) * (size_t)n_pts, s));
+    corners_kernel<<<(unsigned)ceil_div(n_pts, 256), 256, 0, s>>>(d_pts_xy, (long long)n_pts, plan->size, xy0);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    GatherSource src{d_img, H, W, xy0};
+    int rc = project_tc(plan, nullptr, n_pts, precision, out_kind, d_out, d_out2, nullptr, nullptr, 0, 0, s, &src);
+    cudaFreeAsync(xy0, s);
+    return rc;
+}
 
 extern "C" int zb200_gather_patches_f32(const float* d_img, int H, int W, const double* d_pts_xy,
                                         int64_t n_pts, int k, float* d_out, void* stream) {

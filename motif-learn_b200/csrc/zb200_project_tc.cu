@@ -70,6 +70,10 @@ struct Params {
     int ts_hi;            // 1: the tf32 MMA also reads X from TMEM (raw copy)  (tf32x3 kernel)
     int epi_solo;         // 1: epilogue warpgroup 1 owns all columns, warpgroup 2 idles
     int cluster;          // CTAs per cluster sharing the B operand through TMA multicast (1, 2 or 4)
+    int gather;           // 1: X tiles are gathered from a frame at peak windows instead of TMA-loaded (tf32x3)
+    const float* g_img;   // frame [g_H][g_W]
+    int g_H, g_W, g_k;
+    const int2* g_xy;     // top-left corner (x0, y0) of every patch window
     int dbg;              // ZB200_TC_DEBUG bitmask: experiments only (results are wrong when set)
 };
 
@@ -382,8 +386,8 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const int row0 = tile * p.subtiles * kTileRows;
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait_t(&empty[s], ph ^ 1, w0, prof);
-                        mbar_arrive_expect_tx(&full[s], x_bytes + 2 * b_bytes);
-                        tma_load_2d(stage_x(s), &map_x, &full[s], kb * kBlockK, row0, kEvictFirst);
+                        mbar_arrive_expect_tx(&full[s], (p.gather ? 0u : x_bytes) + 2 * b_bytes);
+                        if (!p.gather) tma_load_2d(stage_x(s), &map_x, &full[s], kb * kBlockK, row0, kEvictFirst);
                         if (p.cluster == 1) {
                             tma_load_2d(stage_bhi(s), &map_bhi, &full[s], kb * kBlockK, 0, kEvictLast);
                             tma_load_2d(stage_blo(s), &map_blo, &full[s], kb * kBlockK, 0, kEvictLast);
@@ -421,7 +425,8 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                             const int lb = (int)(it & lo_mask);
                             const uint32_t lo_ph = (it >> lo_shift) & 1u;
-                            mbar_wait_t(&lo_full[lb], lo_ph, w1, prof);       // implies full[s]
+                            mbar_wait_t(&lo_full[lb], lo_ph, w1, prof);       // implies full[s] unless X is gathered
+                            if (p.gather) mbar_wait(&full[s], ph);
                             const long long t_fence = prof ? clock64() : 0;
                             tc_fence_after();
                             const long long t_issue = prof ? clock64() : 0;
@@ -490,11 +495,56 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             w[6] = pack2(b.x, b.y);
             w[7] = pack2(b.z, b.w);
         };
+        const int g_rows = 32 * p.subtiles;                       // tile rows this warp gathers: [q*g_rows, +g_rows)
         for (int t = 0; t < my_tiles; ++t) {
+            int2 ca = make_int2(-(1 << 28), -(1 << 28)), cb = ca;  // windows of the rows q*g_rows+lane (and +32)
+            if (p.gather) {
+                const long long base = ((long long)blockIdx.x + (long long)t * gridDim.x) * p.subtiles * kTileRows + q * g_rows;
+                if (base + lane < p.n_patches) ca = __ldg(p.g_xy + base + lane);
+                if (p.subtiles == 2 && base + 32 + lane < p.n_patches) cb = __ldg(p.g_xy + base + 32 + lane);
+            }
+            auto gather_issue = [&](int kbi, int sg, uint32_t phg) {
+                mbar_wait(&empty[sg], phg ^ 1u);                   // the stage's previous MMAs have retired
+                const int e0 = kbi * kBlockK;
+                int wr = e0 / p.g_k, wc = e0 - wr * p.g_k + lane;   // window row / column of this lane
+                if (wc >= p.g_k) { wc -= p.g_k; ++wr; }
+                const uint32_t xs = smem_u32(stage_x(sg)) + (uint32_t)(q * g_rows) * 128u;
+                for (int j = 0; j < g_rows; ++j) {
+                    const int2 src = (j & 32) ? cb : ca;
+                    const int x0 = __shfl_sync(0xffffffffu, src.x, j & 31);
+                    const int y0 = __shfl_sync(0xffffffffu, src.y, j & 31);
+                    const int yy = y0 + wr, xx = x0 + wc;
+                    const bool inb = yy >= 0 && yy < p.g_H && xx >= 0 && xx < p.g_W;
+                    const float* gp = p.g_img + (inb ? (size_t)yy * p.g_W + xx : 0);
+                    const int row = q * g_rows + j;                 // tile row (swizzle phase = row % 8)
+                    const uint32_t dst = xs + (uint32_t)j * 128u + ((((uint32_t)lane >> 2) ^ (uint32_t)(row & 7)) << 4) +
+                                         ((uint32_t)lane & 3u) * 4u;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(gp), "r"(inb ? 4 : 0)
+                                 : "memory");                       // src-size 0 -> zero fill outside the frame
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
             for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
                 const int lb = (int)(it & lo_mask);
                 const uint32_t lo_ph = (it >> lo_shift) & 1u;
-                mbar_wait_t(&full[s], ph, w0, prof);
+                if (!p.gather) {
+                    mbar_wait_t(&full[s], ph, w0, prof);
+                } else {
+                    // K2 fused: the four warps copy 32-float window segments (one per tile row, coalesced
+                    // 128-B reads of the L2-resident frame) into the 128-B-swizzled K-major X stage with
+                    // 4-byte cp.async (no register staging, every copy of a k-block in flight at once),
+                    // one k-block ahead of the split so the L2 latency hides behind it.
+                    if (kb == 0) gather_issue(0, s, ph);
+                    if (kb + 1 < p.k_blocks) {
+                        const int sn = (s + 1 == p.n_stages) ? 0 : s + 1;
+                        gather_issue(kb + 1, sn, sn == 0 ? ph ^ 1u : ph);
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    }
+                    fence_proxy_async();                           // the MMA (async proxy) reads these rows
+                    asm volatile("bar.sync 1, 128;" ::: "memory");  // all four gather warps done with this stage
+                }
                 const uint8_t* rowp = stage_x(s) + (size_t)r * 128;
                 float4 x0[8], x1[8];
 #pragma unroll
@@ -678,10 +728,16 @@ int init_tensor_maps(zb200_plan* p) {
 }
 
 int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind, void* d_out,
-               void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind, cudaStream_t s) {
+               void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind, cudaStream_t s,
+               const GatherSource* gsrc) {
     using namespace tc;
     if (n == 0) return ZB200_OK;
-    ZB_CHECK_ARG((reinterpret_cast<uintptr_t>(d_patches) & 15) == 0, "project: patch pointer must be 16-byte aligned");
+    ZB_CHECK_ARG(gsrc || (reinterpret_cast<uintptr_t>(d_patches) & 15) == 0,
+                 "project: patch pointer must be 16-byte aligned");
+    if (gsrc && (precision != ZB200_PREC_TF32X3 || p->size < 32)) {
+        set_error("fused gather+projection needs precision tf32x3 and a window of at least 32 pixels");
+        return ZB200_EUNSUP;
+    }
     const bool x3 = precision == ZB200_PREC_TF32X3;
     const bool scores = d_w != nullptr;
     const bool cplx = !scores && out_kind != ZB200_OUT_REAL;
@@ -709,6 +765,14 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                          : (out_kind == ZB200_OUT_REAL ? p->n_modes
                                                        : (out_kind == ZB200_OUT_COMPLEX ? 2 * p->n_complex : p->n_complex));
     prm.chunk_kb = 8;
+    if (gsrc) {
+        prm.gather = 1;
+        prm.g_img = gsrc->img;
+        prm.g_H = gsrc->H;
+        prm.g_W = gsrc->W;
+        prm.g_k = p->size;
+        prm.g_xy = gsrc->xy0;
+    }
     if (const char* e = getenv("ZB200_TC_DEBUG")) prm.dbg = atoi(e);
     if (prm.dbg & 4) prm.chunk_kb = prm.k_blocks;
 
@@ -753,7 +817,8 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.n_tiles = (int)ceil_div(n, (int64_t)sub * kTileRows);
 
     CUtensorMap map_x;
-    int rc = encode_2d(&map_x, d_patches, (uint64_t)p->kk, (uint64_t)n, (uint64_t)p->kk * 4, (uint32_t)(sub * kTileRows));
+    int rc = gsrc ? encode_2d(&map_x, op.hi, (uint64_t)p->k_pad, (uint64_t)op.rows_pad, (uint64_t)p->k_pad * 4, 8)   // unused
+                  : encode_2d(&map_x, d_patches, (uint64_t)p->kk, (uint64_t)n, (uint64_t)p->kk * 4, (uint32_t)(sub * kTileRows));
     if (rc) return rc;
 
     // cluster of C CTAs shares each B k-block through TMA multicast (L2 -> SM traffic of B / C)

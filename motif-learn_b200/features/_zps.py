@@ -252,6 +252,57 @@ class ZPs(BaseEstimator, TransformerMixin):
                                                  self._stream()), "project_patches")
         return out if out2 is None else (out, out2)
 
+    def transform_peaks(self, image, pts, kind: str = "real", fused=None):
+        """Moments of the ``size x size`` windows centred at ``pts`` (rows of (x, y), as kept by
+        ``clear_border``) of one frame -- ``KeyPoints(pts, image, size).extract_patches()`` followed by
+        ``transform`` in ONE kernel: windows are gathered from the L2-resident frame straight into the
+        tensor-core operand, the patch stack never exists in HBM (BASELINE config 5).
+
+        kind='real' -> ``zmoments`` (N, M); 'complex' | 'abs' | 'abs_phase' as ``transform_features``.
+        ``fused=None`` picks the fused kernel when the intermediate patch stack would exceed 8 GiB
+        (it is the memory-lean path; at round 1 the two-kernel path is the faster one), ``True``/``False`` force it."""
+        if image.ndim != 2:
+            raise ValueError("Images must be 2D or 3D array.")
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        codes = {"real": _lib.OUT_REAL, "complex": _lib.OUT_COMPLEX, "abs": _lib.OUT_ABS, "abs_phase": _lib.OUT_ABS_PHASE}
+        code = codes[kind]
+        prec = self._precision_code()
+        dev = self._image_on_device(image)
+        pts_np = np.ascontiguousarray(np.asarray(pts, dtype=np.float64).reshape(-1, 2))
+        can_fuse = (prec == _lib.PREC_TF32X3 and self.size >= 32 and lib.zb200_plan_supports(self._plan, prec, code))
+        if fused is None:
+            fused = can_fuse and pts_np.shape[0] * self.size * self.size * 4 > (8 << 30)
+        if fused and not can_fuse:
+            raise ValueError("fused gather+projection needs precision 'tf32x3' (or 'auto' on a supported shape) and size >= 32")
+        if not fused:
+            # two kernels: gather to HBM, then the projection at the requested precision
+            from ._keypoint import KeyPoints
+            kp = KeyPoints.__new__(KeyPoints)
+            kp.shape, kp.size, kp.img, kp.pts, kp.patches = tuple(dev.shape), self.size, dev, pts_np, None
+            patches = kp.extract_patches()
+            return self._transform_patches(patches) if kind == "real" else self.transform_features(patches, kind)
+        dpts = torch.from_numpy(pts_np).to(dev.device)
+        count = int(dpts.shape[0])
+        n_c = lib.zb200_num_complex_modes(self.n_max)
+        out2 = None
+        if kind == "real":
+            out = torch.empty((count, len(self.n)), dtype=torch.float32, device=dev.device)
+        elif kind == "complex":
+            out = torch.empty((count, n_c), dtype=torch.complex64, device=dev.device)
+        else:
+            out = torch.empty((count, n_c), dtype=torch.float32, device=dev.device)
+            if kind == "abs_phase":
+                out2 = torch.empty_like(out)
+        _lib.check(lib.zb200_project_peaks_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]), int(dev.shape[1]),
+                                               int(dpts.data_ptr()), count, prec, code, int(out.data_ptr()),
+                                               None if out2 is None else int(out2.data_ptr()), self._stream()),
+                   "project_peaks")
+        if kind == "real":
+            data = _host_f64(out) if self._want_host(image) else out
+            return zmoments(data=data, n=self.n, m=self.m, patch_size=self.size)
+        return out if out2 is None else (out, out2)
+
     # ------------------------------------------------------------ K4: dense map
     def _image_on_device(self, image):
         torch = _lib.require_cuda()

@@ -429,3 +429,37 @@ def test_config5_frame_batch_gather_then_features(api, torch):
         refabs = np.abs(zo.to_complex(ref, n, m)[0])
         got = z.transform_features(patches, "abs").cpu().numpy()
         assert np.abs(got - refabs).max() <= 3e-6 * refabs.max()
+
+
+def test_fused_gather_projection(api, torch):
+    """K2 fused into K3 (zb200_project_peaks_f32): same numbers as gather + projection, bit-for-bit
+    against the unfused tensor-core path, and fp32-grade against the oracle; border windows read zeros."""
+    from motif_learn_b200.datasets import honeycomb_image
+    img, pts = honeycomb_image((600, 777), bond=12.0, seed=9, angle=23.0, jitter=0.4, noise=0.01)
+    dimg = torch.from_numpy(img).cuda()
+    for n_max, k in ((12, 64), (10, 32), (12, 48)):
+        kept = zo.clear_border(pts, img.shape, k)
+        z = api.ZPs(n_max, k)
+        n, m, v = zo.zernike_basis(n_max, k)
+        patches = zo.extract_patches(img, kept, k)
+        ref = zo.project_patches(patches.astype(np.float64), v)
+        fused = z.transform_peaks(dimg, kept, fused=True)
+        assert fused.data.is_cuda and fused.data.shape == ref.shape
+        fp32_close(fused.data.cpu().numpy(), ref)
+        unfused = z.transform(torch.from_numpy(patches).cuda()).data
+        assert torch.equal(fused.data, unfused)
+        refabs = np.abs(zo.to_complex(ref, n, m)[0])
+        assert np.abs(z.transform_peaks(dimg, kept, "abs", fused=True).cpu().numpy() - refabs).max() <= 3e-6 * refabs.max()
+        assert torch.equal(z.transform_peaks(dimg, kept).data, unfused)     # default: gather kernel + projection
+        host = z.transform_peaks(img, kept, fused=True)           # numpy frame in -> float64 numpy out
+        assert isinstance(host.data, np.ndarray) and host.data.dtype == np.float64
+        fp32_close(host.data, ref)
+    # windows hanging over the frame edge: zero extension, like the dense map
+    z = api.ZPs(12, 64)
+    edge = np.array([[3.0, 5.0], [770.0, 590.0], [400.2, 10.7]])
+    got = z.transform_peaks(dimg, edge, fused=True).data.cpu().numpy()
+    dense = z.transform(dimg).data
+    c = np.rint(edge).astype(int)
+    want = dense[:, torch.from_numpy(c[:, 1]).cuda(), torch.from_numpy(c[:, 0]).cuda()].cpu().numpy().T
+    fp32_close(got, want, rtol=2e-4, scale=3e-6)
+    assert z.transform_peaks(dimg, np.zeros((0, 2))).data.shape == (0, 91)
