@@ -25,7 +25,9 @@
 //   * K-chunked accumulation: the tensor core accumulates in fp32 with round-toward-zero, which
 //     biases a 512-step sum by ~1.5e-5 relative (measured); accumulators are therefore drained
 //     every 8 k-blocks into fp32 registers of the epilogue warps (round-to-nearest adds), with two
-//     accumulator buffers in TMEM so draining overlaps the next chunk's MMAs.
+//     accumulator buffers in TMEM so draining overlaps the next chunk's MMAs;
+//   * separate X (HBM, TMA or gathered) and B (L2, multicast) rings with their own producers; with
+//     p.gather the splitter warps fill the X ring themselves from a frame (K2 fused into K3).
 #include "zb200_common.cuh"
 #include "zb200_tc_ptx.cuh"
 
@@ -56,6 +58,7 @@ struct Params {
     int n_pad;            // UMMA N (operand rows, multiple of 16)
     int n_cols;           // meaningful accumulator columns
     int n_stages;
+    int b_stages;         // basis ring slots (tf32x3 kernel)
     int acc_bufs;         // 1 or 2
     int out_kind;         // ZB200_OUT_* or 100 = scores
     int row_len;          // output row length in floats (REAL: M, COMPLEX: 2Mc, ABS: Mc)
@@ -67,7 +70,6 @@ struct Params {
     int norm_kind;
     int chunk_kb;         // k-blocks per accumulation chunk (tf32x3 kernel)
     int lo_bufs;          // operand staging buffers in TMEM: 1, 2 or 4       (tf32x3 kernel)
-    int ts_hi;            // 1: the tf32 MMA also reads X from TMEM (raw copy)  (tf32x3 kernel)
     int epi_solo;         // 1: epilogue warpgroup 1 owns all columns, warpgroup 2 idles
     int cluster;          // CTAs per cluster sharing the B operand through TMA multicast (1, 2 or 4)
     int gather;           // 1: X tiles are gathered from a frame at peak windows instead of TMA-loaded (tf32x3)
@@ -310,14 +312,18 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t x_bytes = (uint32_t)p.subtiles * kTileRows * 128;
     const uint32_t b_bytes = (uint32_t)p.n_pad * 128;
-    const uint32_t stage_bytes = x_bytes + 2 * b_bytes;
-    auto stage_x = [&](int s) { return smem + (size_t)s * stage_bytes; };
-    auto stage_bhi = [&](int s) { return smem + (size_t)s * stage_bytes + x_bytes; };
-    auto stage_blo = [&](int s) { return smem + (size_t)s * stage_bytes + x_bytes + b_bytes; };
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
+    // two rings: X (HBM stream, deep: bytes in flight hide the DRAM latency) and B (L2 stream, 2 slots)
+    const uint32_t bst_bytes = 2 * b_bytes;                              // [Bhi | Bcb] of one k-block
+    uint8_t* b_ring = smem + (size_t)p.n_stages * x_bytes;
+    auto stage_x = [&](int s) { return smem + (size_t)s * x_bytes; };
+    auto stage_bhi = [&](int s) { return b_ring + (size_t)s * bst_bytes; };
+    auto stage_blo = [&](int s) { return b_ring + (size_t)s * bst_bytes + b_bytes; };
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_stages * bst_bytes);
     uint64_t* full = bars;                        // TMA landed                               [stages]
     uint64_t* empty = bars + p.n_stages;          // MMAs reading the stage retired           [stages]
-    uint64_t* lo_full = bars + 2 * p.n_stages;    // staged operands of a k-block are in TMEM [4]
+    uint64_t* bfull = bars + 2 * p.n_stages;      // B k-block landed                          [4]
+    uint64_t* bempty = bfull + 4;                 // MMAs reading it retired (whole cluster)    [4]
+    uint64_t* lo_full = bempty + 4;               // staged operands of a k-block are in TMEM [4]
     uint64_t* lo_empty = lo_full + 4;             // MMAs reading them retired                [4]
     uint64_t* acc_full = lo_empty + 4;            // accumulation chunk complete              [2]
     uint64_t* acc_empty = acc_full + 2;           // chunk drained by the epilogue            [2]
@@ -329,7 +335,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     //   warps 0-3 splitter | warps 4-11 epilogue (two warpgroups) | warp 12 TMA, 13 MMA, 14 TMEM alloc
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wg = warp >> 2;
-    constexpr int kWarpTma = 12, kWarpMma = 13, kWarpAlloc = 14;
+    constexpr int kWarpTma = 12, kWarpMma = 13, kWarpAlloc = 14, kWarpBasis = 15;
     const bool prof = (p.dbg & 16) != 0;
     unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;      // per-thread blocked-cycle counters (experiments)
 
@@ -341,9 +347,11 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], p.cluster);
+            mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 4; ++b) {
+            mbar_init(&bfull[b], 1);
+            mbar_init(&bempty[b], p.cluster);
             mbar_init(&lo_full[b], 4);
             mbar_init(&lo_empty[b], 1);
         }
@@ -385,20 +393,35 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const int tile = blockIdx.x + t * gridDim.x;
                     const int row0 = tile * p.subtiles * kTileRows;
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        if (p.gather) break;                       // X is gathered by the splitter warps
                         mbar_wait_t(&empty[s], ph ^ 1, w0, prof);
-                        mbar_arrive_expect_tx(&full[s], (p.gather ? 0u : x_bytes) + 2 * b_bytes);
-                        if (!p.gather) tma_load_2d(stage_x(s), &map_x, &full[s], kb * kBlockK, row0, kEvictFirst);
+                        mbar_arrive_expect_tx(&full[s], x_bytes);
+                        tma_load_2d(stage_x(s), &map_x, &full[s], kb * kBlockK, row0, kEvictFirst);
+                        if (++s == p.n_stages) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == kWarpBasis) {
+            // ===================== basis producer (L2 -> smem, multicast across the cluster) =====================
+            if (elect_one()) {
+                int sb = 0;
+                uint32_t phb = 0;
+                for (int t = 0; t < my_tiles; ++t) {
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(&bempty[sb], phb ^ 1);
+                        mbar_arrive_expect_tx(&bfull[sb], bst_bytes);
                         if (p.cluster == 1) {
-                            tma_load_2d(stage_bhi(s), &map_bhi, &full[s], kb * kBlockK, 0, kEvictLast);
-                            tma_load_2d(stage_blo(s), &map_blo, &full[s], kb * kBlockK, 0, kEvictLast);
+                            tma_load_2d(stage_bhi(sb), &map_bhi, &bfull[sb], kb * kBlockK, 0, kEvictLast);
+                            tma_load_2d(stage_blo(sb), &map_blo, &bfull[sb], kb * kBlockK, 0, kEvictLast);
                         } else {
                             const size_t off = (size_t)crank * b_rows * 128;
-                            tma_load_2d_mc(stage_bhi(s) + off, &map_bhi, &full[s], kb * kBlockK, (int)crank * b_rows, cmask,
+                            tma_load_2d_mc(stage_bhi(sb) + off, &map_bhi, &bfull[sb], kb * kBlockK, (int)crank * b_rows, cmask,
                                            kEvictLast);
-                            tma_load_2d_mc(stage_blo(s) + off, &map_blo, &full[s], kb * kBlockK, (int)crank * b_rows, cmask,
+                            tma_load_2d_mc(stage_blo(sb) + off, &map_blo, &bfull[sb], kb * kBlockK, (int)crank * b_rows, cmask,
                                            kEvictLast);
                         }
-                        if (++s == p.n_stages) { s = 0; ph ^= 1; }
+                        if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
                     }
                 }
             }
@@ -409,7 +432,11 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 const uint32_t idesc = make_idesc_tf32(p.n_pad);
                 const uint32_t idesc_c = make_idesc_bf16(p.n_pad);
                 const uint32_t x_lo0 = desc_lo_sw128(smem_u32(smem));
-                const uint32_t stage_step = stage_bytes >> 4;
+                const uint32_t stage_step = x_bytes >> 4;
+                const uint32_t b_lo0 = desc_lo_sw128(smem_u32(b_ring));
+                const uint32_t b_step = bst_bytes >> 4;
+                int sb = 0;
+                uint32_t phb = 0;
                 int s = 0;
                 uint32_t ph = 0;
                 uint32_t it = 0;            // running k-block counter  -> Xlo buffer / phase
@@ -425,14 +452,14 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                             const int lb = (int)(it & lo_mask);
                             const uint32_t lo_ph = (it >> lo_shift) & 1u;
-                            mbar_wait_t(&lo_full[lb], lo_ph, w1, prof);       // implies full[s] unless X is gathered
-                            if (p.gather) mbar_wait(&full[s], ph);
+                            mbar_wait_t(&lo_full[lb], lo_ph, w1, prof);       // implies X landed (TMA or gathered)
+                            mbar_wait(&bfull[sb], phb);
                             const long long t_fence = prof ? clock64() : 0;
                             tc_fence_after();
                             const long long t_issue = prof ? clock64() : 0;
                             if (prof) w0 += (unsigned long long)(t_issue - t_fence);   // (reported as mma.acc_empty+fence)
                             const uint32_t xl = x_lo0 + (uint32_t)s * stage_step;
-                            const uint32_t bhl = xl + (x_bytes >> 4);
+                            const uint32_t bhl = b_lo0 + (uint32_t)sb * b_step;
                             const uint32_t bcl = bhl + (b_bytes >> 4);
                             const uint32_t a0 = lo_base + (uint32_t)(lb * p.subtiles) * kBlockK;
                             const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
@@ -454,9 +481,11 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                             }
                             if (prof) w2 += (unsigned long long)(clock64() - t_issue);
                             const long long t_commit = prof ? clock64() : 0;
-                            if (p.cluster == 1) umma_commit(&empty[s]);
-                            else umma_commit_mc(&empty[s], cmask);
+                            umma_commit(&empty[s]);
+                            if (p.cluster == 1) umma_commit(&bempty[sb]);
+                            else umma_commit_mc(&bempty[sb], cmask);
                             umma_commit(&lo_empty[lb]);
+                            if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
                             if (kb == kb_end - 1) umma_commit(&acc_full[buf]);
                             if (prof) w3 += (unsigned long long)(clock64() - t_commit);
                             if (++s == p.n_stages) { s = 0; ph ^= 1; }
@@ -778,7 +807,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
 
     // tile shape: two 128-patch accumulators per tile when TMEM/smem allow and there is enough work
     // to keep every SM busy with 256-patch tiles
-    const int bar_bytes = 1024 + 8 * (2 * 8 + 12) + 16;
+    const int bar_bytes = 1024 + 8 * (2 * 8 + 20) + 16;
     auto stage_bytes = [&](int sub) { return sub * kTileRows * 128 + (x3 ? 2 : 1) * prm.n_pad * 128; };
     int sub = 2;
     if (scores && n_folds > kFusedFolds) {
@@ -788,7 +817,6 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     if (x3) {
         sub = prm.n_pad <= 96 ? 2 : 1;                    // 2 accumulator sets x sub x n_pad + staging <= 512 columns
         if (ceil_div(n, 256) < p->sm_count || (prm.dbg & 8)) sub = 1;
-        prm.ts_hi = 0;
         prm.epi_solo = (sub == 1 && prm.n_pad <= 16 * kMaxColChunks) ? 1 : 0;
         if (scores && sub == 1 && !prm.epi_solo) {
             set_error("fused n-fold scores in tf32x3 need <= 128 operand rows (have %d); use the unfused path", prm.n_pad);
@@ -801,6 +829,12 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
         if ((kSmemLimit - bar_bytes) / stage_bytes(sub) < 2 && sub == 2) sub = 1;
     }
     prm.subtiles = sub;
+    prm.b_stages = 3;
+    if (const char* e = getenv("ZB200_TC_BSTAGES")) { int v = atoi(e); if (v >= 1 && v <= 4) prm.b_stages = v; }
+    if (x3) {
+        const int bst = 2 * prm.n_pad * 128, xb = sub * kTileRows * 128;
+        prm.n_stages = (kSmemLimit - bar_bytes - prm.b_stages * bst) / xb;
+    } else
     prm.n_stages = (kSmemLimit - bar_bytes) / stage_bytes(sub);
     if (prm.n_stages > 8) prm.n_stages = 8;
     if (const char* e = getenv("ZB200_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < prm.n_stages) prm.n_stages = v; }
@@ -829,7 +863,8 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.cluster = cluster;
     const int lg = cluster == 4 ? 2 : (cluster == 2 ? 1 : 0);
 
-    const size_t smem = (size_t)prm.n_stages * stage_bytes(sub) + bar_bytes;
+    const size_t smem = x3 ? (size_t)prm.n_stages * sub * kTileRows * 128 + (size_t)prm.b_stages * 2 * prm.n_pad * 128 + bar_bytes
+                           : (size_t)prm.n_stages * stage_bytes(sub) + bar_bytes;
     int grid = prm.n_tiles < p->sm_count ? prm.n_tiles : p->sm_count;
     grid = (grid / cluster) * cluster;                               // whole clusters only (148 = 2*74 = 4*37)
     if (grid < cluster) grid = cluster;

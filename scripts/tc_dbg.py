@@ -18,10 +18,10 @@ for prec in ("tf32", "tf32x3"):
     for _ in range(20): z.transform(dx)
     e1.record(); torch.cuda.synchronize()
     out.append("%%s %%.4f ms" %% (prec, e0.elapsed_time(e1)/20))
-print("stages", os.environ.get("ZB200_TC_STAGES","-"), "cluster", os.environ.get("ZB200_TC_CLUSTER","-"), "dbg", os.environ.get("ZB200_TC_DEBUG","0"), " | ".join(out), flush=True)
+print("bstages", os.environ.get("ZB200_TC_BSTAGES","-"), "stages", os.environ.get("ZB200_TC_STAGES","-"), "cluster", os.environ.get("ZB200_TC_CLUSTER","-"), "dbg", os.environ.get("ZB200_TC_DEBUG","0"), " | ".join(out), flush=True)
 ''' % ROOT
-for cl, dbg, st in ((2, 0, 8), (2, 1, 8), (2, 2, 8), (2, 3, 8), (2, 4, 8), (2, 7, 8), (1, 0, 8), (2, 0, 3)):
-    env = dict(os.environ, ZB200_TC_DEBUG=str(dbg), ZB200_TC_CLUSTER=str(cl), ZB200_TC_STAGES=str(st))
+for cl, dbg, st, bs in ((2, 0, 8, 2), (2, 0, 8, 3), (2, 0, 8, 4), (2, 0, 4, 3), (2, 0, 3, 4), (1, 0, 8, 3)):
+    env = dict(os.environ, ZB200_TC_DEBUG=str(dbg), ZB200_TC_CLUSTER=str(cl), ZB200_TC_STAGES=str(st), ZB200_TC_BSTAGES=str(bs))
     try:
         subprocess.run([sys.executable, "-c", code], env=env, timeout=100)
     except subprocess.TimeoutExpired:
