@@ -252,6 +252,37 @@ class ZPs(BaseEstimator, TransformerMixin):
                                                  self._stream()), "project_patches")
         return out if out2 is None else (out, out2)
 
+    def symmetry_scores(self, images, n_folds, p=2, m_unselect=None):
+        """Fused ``transform(patches).rot_maps(n_folds, p, m_unselect)`` -> (N, F): the n-fold scores of a
+        patch stack computed in the projection kernel's epilogue (the moments never leave the SM).
+        Falls back to projection + score kernel when the fused epilogue is unavailable."""
+        self._validate_size(images)
+        if images.ndim != 3:
+            raise ValueError("Images must be 2D or 3D array.")
+        if m_unselect is None:
+            m_unselect = (0, 1)
+        elif 0 not in m_unselect:
+            raise ValueError("m=0 must be included in m_unselect.")
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        host_in = not is_torch(images)
+        dev = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32)) if host_in else images
+        dev = dev.to(device="cuda", dtype=torch.float32).contiguous()
+        wts, sel = rot_weight_tables(self.m, n_folds, m_unselect)
+        n_f = wts.shape[0]
+        prec = self._precision_code()
+        kind = norm_code(p)
+        fusable = n_f <= 8 and (prec == _lib.PREC_FP32 or len(self.n) <= (128 if prec == _lib.PREC_TF32X3 else 256))
+        if not fusable:
+            out = self._transform_patches(dev).rot_maps(n_folds, p=p, m_unselect=m_unselect)
+            return out.double().cpu().numpy() if host_in and self._want_host(images) else out
+        out = torch.empty((int(dev.shape[0]), n_f), dtype=torch.float32, device=dev.device)
+        w32 = np.ascontiguousarray(wts, dtype=np.float32)
+        _lib.check(lib.zb200_project_patches_scores_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]), prec,
+                                                        np_ptr(w32), np_ptr(sel), n_f, kind, int(out.data_ptr()),
+                                                        self._stream()), "project_patches_scores")
+        return _host_f64(out) if self._want_host(images) else out
+
     def transform_peaks(self, image, pts, kind: str = "real", fused=None):
         """Moments of the ``size x size`` windows centred at ``pts`` (rows of (x, y), as kept by
         ``clear_border``) of one frame -- ``KeyPoints(pts, image, size).extract_patches()`` followed by

@@ -463,3 +463,26 @@ def test_fused_gather_projection(api, torch):
     want = dense[:, torch.from_numpy(c[:, 1]).cuda(), torch.from_numpy(c[:, 0]).cuda()].cpu().numpy().T
     fp32_close(got, want, rtol=2e-4, scale=3e-6)
     assert z.transform_peaks(dimg, np.zeros((0, 2))).data.shape == (0, 91)
+
+
+def test_fused_patch_scores(api, golden, torch):
+    """rot_maps fused into the projection epilogue (zb200_project_patches_scores_f32)."""
+    g = golden("patches_nfold.npz")
+    p = g["patches"]
+    for prec in precisions(api, 12, 64):
+        z = api.ZPs(12, 64, precision=prec)
+        tol = 2e-3 if prec == "tf32" else 1e-5
+        got = z.symmetry_scores(p, [2, 3, 4, 6])
+        assert got.shape == g["z12_rot"].shape and np.abs(got - g["z12_rot"]).max() < tol
+        assert np.abs(z.symmetry_scores(p, [3, 6], p=1) - g["z12_rot_p1"]).max() < tol
+        assert np.abs(z.symmetry_scores(p, [2, 4], m_unselect=(0, 1, 2)) - g["z12_rot_unsel"]).max() < tol
+        dev = z.symmetry_scores(torch.from_numpy(p).cuda(), [2, 3, 4, 6])
+        assert dev.is_cuda and np.abs(dev.cpu().numpy() - g["z12_rot"]).max() < tol
+    big = np.random.default_rng(3).random((3000, 64, 64), dtype=np.float32)
+    _, _, v = zo.zernike_basis(12, 64)
+    n, m = zo.mode_table(12)
+    want = zo.rot_maps(zo.project_patches(big.astype(np.float64), v), n, m, [2, 3, 4, 5, 6, 8])
+    assert np.abs(api.ZPs(12, 64).symmetry_scores(big, [2, 3, 4, 5, 6, 8]) - want).max() < 1e-5
+    z20 = api.ZPs(20, 64)                                   # 231 modes: unfused fallback on the fp32-grade path
+    want20 = zo.rot_maps(g["z20_data"], *zo.mode_table(20), [3, 6])
+    assert np.abs(z20.symmetry_scores(p, [3, 6]) - want20).max() < 1e-5
