@@ -106,3 +106,27 @@ def nfold_patches(size: int = 64, n_fold: int = 3, count: int = 10, centre: bool
             out[i] += np.exp(-((xx - bx) ** 2 + (yy - by) ** 2) / (2 * sig ** 2))
         out[i] /= out[i].max()
     return out.astype(np.float32)
+
+
+def render_atoms_gpu(shape, pts, amps, sigma: float, r_factor: float = 3.0, out=None):
+    """GPU counterpart of the reference's ``add_tapered_gaussian`` (mtflearn/datasets/
+    _tapered_gaussian.py:3-97): draws the atoms ``pts`` (rows of (x, y), may lie outside the frame)
+    with per-atom or scalar amplitude into a float32 CUDA frame of ``shape`` = (H, W).  Pass
+    ``out`` (a CUDA float32 tensor) to add to an existing frame, e.g. the second sub-lattice."""
+    import ctypes as C
+    from . import _lib
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    h, w = shape
+    pts_np = np.ascontiguousarray(np.asarray(pts, dtype=np.float64).reshape(-1, 2))
+    d_pts = torch.from_numpy(pts_np).cuda()
+    scalar = np.ndim(amps) == 0
+    d_amps = None if scalar else torch.from_numpy(np.ascontiguousarray(np.asarray(amps, dtype=np.float64))).cuda()
+    if not scalar and d_amps.numel() != pts_np.shape[0]:
+        raise ValueError("If amplitude is array-like, its length must match number of points")
+    img = out if out is not None else torch.empty((h, w), dtype=torch.float32, device="cuda")
+    _lib.check(lib.zb200_render_atoms_f32(int(d_pts.data_ptr()), None if scalar else int(d_amps.data_ptr()),
+                                          float(amps) if scalar else 0.0, pts_np.shape[0], float(sigma), float(r_factor),
+                                          int(h), int(w), int(img.data_ptr()), 0 if out is None else 1,
+                                          C.c_void_p(_lib.current_stream_ptr())), "render_atoms")
+    return img

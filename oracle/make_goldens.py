@@ -154,8 +154,36 @@ def golden_lattice():
     save("lattice.npz", **arrays)
 
 
+
+
+def golden_render():
+    """Synthetic-frame renderer ("next" row f1): atoms + the frame the reference draws from them."""
+    from mtflearn.datasets._tapered_gaussian import add_tapered_gaussian
+    lat = HoneyCombLattice(size=160, l=12, seed=3, angle=17.0, jitter=0.2)
+    img = lat.to_image()
+    sigma = lat.l / 4.0
+    radius = int(np.ceil(3 * sigma))
+
+    def in_range(c):
+        keep = ((c[:, 0] >= -radius) & (c[:, 0] <= lat.size - 1 + radius)
+                & (c[:, 1] >= -radius) & (c[:, 1] <= lat.size - 1 + radius))
+        return c[keep]
+
+    a, b = in_range(lat._coords_A), in_range(lat._coords_B)
+    pts = np.vstack([a, b])
+    amps = np.concatenate([np.full(len(a), 1.0), np.full(len(b), 0.5)])
+    rng = np.random.default_rng(0)
+    amps2 = amps.copy()
+    amps2[rng.random(len(amps2)) < 0.05] = 0.0
+    amps2[rng.random(len(amps2)) < 0.05] *= 0.8
+    img2 = np.zeros((120, 160), dtype=np.float32)
+    add_tapered_gaussian(img2, pts, sigma, amplitude=amps2, r_factor=3.0)
+    save("render.npz", pts=pts, amps=amps, sigma=np.array(sigma), img=img, amps2=amps2, img2=img2)
+
+
 if __name__ == "__main__":
     golden_index()
     golden_basis()
     golden_patches()
     golden_lattice()
+    golden_render()

@@ -34,7 +34,7 @@ __all__ = [
     "project_patches", "moment_map_fft", "moment_map_direct", "valid_mask",
     "complex_matrix", "to_complex", "to_real", "normalize", "select_indices",
     "rotate", "rot_weights", "rot_maps", "mirror_map", "clear_border",
-    "extract_patches",
+    "extract_patches", "render_atoms",
 ]
 
 
@@ -366,3 +366,28 @@ def extract_patches(img: np.ndarray, pts: np.ndarray, size: int, flat: bool = Fa
     for i, (x, y) in enumerate(centres):
         out[i] = img[y - half:y - half + size, x - half:x - half + size]
     return out.reshape(len(centres), size * size) if flat else out
+
+
+# --------------------------------------------------------------------------- #
+# synthetic frames ("next" row f1)                                              #
+# --------------------------------------------------------------------------- #
+def render_atoms(shape_hw, pts: np.ndarray, amps, sigma: float, r_factor: float = 3.0) -> np.ndarray:
+    """Sum of tapered Gaussians drawn like the reference's synthetic frames --
+    mtflearn/datasets/_tapered_gaussian.py:3-97 (used by HoneyCombLattice.to_image,
+    _honeycomb_lattice.py:169-226): value A*exp(-r^2/(2 sigma^2))*(1-3t^2+2t^3), t=r/R, R=r_factor*sigma,
+    zero beyond R; evaluated in float64 and accumulated atom by atom into a float32 frame."""
+    h, w = shape_hw
+    img = np.zeros((h, w), dtype=np.float32)
+    amps = np.broadcast_to(np.asarray(amps, dtype=float), (len(pts),))
+    cut = r_factor * float(sigma)
+    for (x0, y0), a in zip(np.asarray(pts, dtype=float), amps):
+        xa, xb = max(int(np.floor(x0 - cut)), 0), min(int(np.ceil(x0 + cut)) + 1, w)
+        ya, yb = max(int(np.floor(y0 - cut)), 0), min(int(np.ceil(y0 + cut)) + 1, h)
+        if xa >= xb or ya >= yb:
+            continue
+        xx, yy = np.meshgrid(np.arange(xa, xb), np.arange(ya, yb), indexing="xy")
+        r = np.sqrt((xx - x0) ** 2 + (yy - y0) ** 2)
+        t = r / cut
+        val = np.where(r <= cut, a * np.exp(-0.5 * r ** 2 / float(sigma) ** 2) * (1.0 - 3.0 * t ** 2 + 2.0 * t ** 3), 0.0)
+        img[ya:yb, xa:xb] += val
+    return img

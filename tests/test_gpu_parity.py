@@ -486,3 +486,23 @@ def test_fused_patch_scores(api, golden, torch):
     z20 = api.ZPs(20, 64)                                   # 231 modes: unfused fallback on the fp32-grade path
     want20 = zo.rot_maps(g["z20_data"], *zo.mode_table(20), [3, 6])
     assert np.abs(z20.symmetry_scores(p, [3, 6]) - want20).max() < 1e-5
+
+
+def test_render_atoms_golden(golden, torch):
+    """"next" row f1: the GPU frame renderer against frames drawn by the live reference."""
+    from motif_learn_b200.datasets import render_atoms_gpu
+    g = golden("render.npz")
+    sigma = float(g["sigma"])
+    n_a = int((g["amps"] == 1.0).sum())
+    img = render_atoms_gpu((160, 160), g["pts"][:n_a], 1.0, sigma)                 # A sub-lattice ...
+    img = render_atoms_gpu((160, 160), g["pts"][n_a:], 0.5, sigma, out=img)        # ... then B, like to_image
+    assert img.is_cuda and img.dtype == torch.float32
+    np.testing.assert_allclose(img.cpu().numpy(), g["img"], rtol=0, atol=3e-7)
+    img2 = render_atoms_gpu((120, 160), g["pts"], g["amps2"], sigma)
+    np.testing.assert_allclose(img2.cpu().numpy(), g["img2"], rtol=0, atol=3e-7)
+    np.testing.assert_allclose(img2.cpu().numpy(), zo.render_atoms((120, 160), g["pts"], g["amps2"], sigma), rtol=0,
+                               atol=3e-7)
+    many = np.random.default_rng(0).random((5000, 2)) * [700, 300]                # list overflow path (dense atoms)
+    dense = render_atoms_gpu((300, 700), many, 0.3, 2.0)
+    np.testing.assert_allclose(dense.cpu().numpy(), zo.render_atoms((300, 700), many, 0.3, 2.0), rtol=0, atol=2e-6)
+    assert float(render_atoms_gpu((16, 16), np.zeros((0, 2)), 1.0, 3.0).abs().max()) == 0.0

@@ -195,3 +195,11 @@ def test_map_equals_patch_projection(golden):
     zp = zo.project_patches(patches, v)
     c = np.rint(pts).astype(int)
     np.testing.assert_allclose(z[:, c[:, 1], c[:, 0]].T, zp, rtol=0, atol=1e-14)
+
+
+def test_render_golden(golden):
+    g = golden("render.npz")
+    img = zo.render_atoms((160, 160), g["pts"], g["amps"], float(g["sigma"]))
+    np.testing.assert_array_equal(img, g["img"])
+    img2 = zo.render_atoms((120, 160), g["pts"], g["amps2"], float(g["sigma"]))
+    np.testing.assert_array_equal(img2, g["img2"])
