@@ -14,14 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libzernike_b200.so")
 
 # mirror of the #defines in zernike_b200.h
-PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16, PREC_F16X3 = 0, 1, 2, 3, 4
 OUT_REAL, OUT_COMPLEX, OUT_ABS, OUT_ABS_PHASE = 0, 1, 2, 3
 NORM_NONE, NORM_L1, NORM_L2, NORM_INF = 0, 1, 2, 3
 F32, F64 = 0, 1
 ENODEV = -3
 ABI_VERSION = 1
 
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3, "f16": PREC_F16, "f16x3": PREC_F16X3}
 
 _i32p = C.POINTER(C.c_int32)
 _u8p = C.POINTER(C.c_uint8)

@@ -96,6 +96,7 @@ extern "C" void zb200_plan_destroy(zb200_plan* p) {
     cudaFree(p->d_m);
     free_operand(p->real);
     free_operand(p->cplx);
+    free_map_half_operand(p);
     for (int i = 0; i < 2; ++i) {
         if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
         if (p->pin_out[i]) cudaFreeHost(p->pin_out[i]);
@@ -166,6 +167,7 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
     ZB_PLAN_TRY(launch_pack(p, nullptr));
     ZB_PLAN_CUDA(cudaDeviceSynchronize());
     ZB_PLAN_TRY(init_tensor_maps(p));
+    ZB_PLAN_TRY(init_map_half_operand(p));
     *out_plan = p;
     return ZB200_OK;
 }
@@ -189,6 +191,7 @@ extern "C" int zb200_plan_supports(const zb200_plan* p, int precision, int out_k
 extern "C" int zb200_plan_supports_map(const zb200_plan* p, int precision) {
     if (!p) return 0;
     if (precision == ZB200_PREC_FP32) return 1;
+    if (precision == ZB200_PREC_F16 || precision == ZB200_PREC_F16X3) return map_h_supported(p, precision) ? 1 : 0;
     return map_tc_supported(p, precision) ? 1 : 0;
 }
 
@@ -332,6 +335,8 @@ extern "C" int zb200_moment_map_f32(const zb200_plan* p, const float* d_img, int
     int rc = check_map_args(p, d_img, H, W, row0, rows);
     if (rc) return rc;
     ZB_CHECK_ARG(d_out || rows == 0, "map: null output");
+    if (precision == ZB200_PREC_F16 || precision == ZB200_PREC_F16X3)
+        return map_h(p, d_img, H, W, row0, rows, precision, d_out, nullptr, nullptr, nullptr, 0, 0, as_stream(stream));
     if (precision != ZB200_PREC_FP32)
         return map_tc(p, d_img, H, W, row0, rows, precision, d_out, nullptr, nullptr, nullptr, 0, 0, as_stream(stream));
     return map_simt(p, d_img, H, W, row0, rows, d_out, nullptr, nullptr, nullptr, 0, 0, as_stream(stream));
@@ -345,6 +350,8 @@ extern "C" int zb200_symmetry_map_f32(const zb200_plan* p, const float* d_img, i
     ZB_CHECK_ARG(d_scores || rows == 0, "symmetry map: null output");
     ZB_CHECK_ARG(norm_kind >= ZB200_NORM_NONE && norm_kind <= ZB200_NORM_INF, "symmetry map: bad norm kind");
     cudaStream_t s = as_stream(stream);
+    if (precision == ZB200_PREC_F16 || precision == ZB200_PREC_F16X3)
+        return map_h(p, d_img, H, W, row0, rows, precision, nullptr, d_scores, h_weights, h_select, n_folds, norm_kind, s);
     float* d_w = nullptr;
     uint8_t* d_sel = nullptr;
     rc = upload_weights(h_weights, h_select, n_folds, p->n_modes, p->real.rows_pad, s, &d_w, &d_sel);

@@ -73,6 +73,24 @@ struct Operand {
     bool has_tmap = false;
 };
 
+// fp16-split operand of the dense map (zb200_map_h.cu): b1 = RN_f16(V), b2 = RN_f16(V - b1), only the
+// 16-tap groups of each window row that touch the unit disk, packed in issue order.
+constexpr int kMapHalfMaxWindow = 128;
+struct MapHalf {
+    bool ready = false;
+    int n_groups = 0;            // 16-tap groups per window row
+    int a_first = 0, a_end = 0;  // window rows with taps inside the disk
+    int n_act = 0;               // group positions of the packed operand (incl. zero padding)
+    int n_kb = 0;                // 128-byte k-blocks (4 groups) per operand row
+    int n_blocks = 0;            // row blocks per tile (rows that share basis k-blocks)
+    int max_cluster = 1;
+    unsigned short act[kMapHalfMaxWindow] = {};
+    void* b1 = nullptr;          // half [rows_pad][n_kb*64]
+    void* b2 = nullptr;
+    CUtensorMap tmap_b1[2];
+    CUtensorMap tmap_b2[2];
+};
+
 }  // namespace zb200
 
 struct zb200_plan {
@@ -93,6 +111,7 @@ struct zb200_plan {
     int32_t h_m[1024];
     zb200::Operand real;          // real row order
     zb200::Operand cplx;          // complex-interleaved row order
+    zb200::MapHalf map_half;      // fp16-split dense-map operand (real row order)
     void* pin_in[2] = {nullptr, nullptr};   // pinned staging for the host entry point
     void* pin_out[2] = {nullptr, nullptr};
     void* dev_in[2] = {nullptr, nullptr};
@@ -130,6 +149,14 @@ bool map_tc_supported(const zb200_plan* plan, int precision);
 int map_tc(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows, int precision,
            float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
            cudaStream_t s);
+
+int init_map_half_operand(zb200_plan* plan);
+void free_map_half_operand(zb200_plan* plan);
+bool map_h_supported(const zb200_plan* plan, int precision);
+// h_w [n_folds][n_modes] / h_sel [n_modes] are HOST tables (they travel in the kernel parameters)
+int map_h(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows, int precision,
+          float* d_moments, float* d_scores, const float* h_w, const uint8_t* h_sel, int n_folds, int norm_kind,
+          cudaStream_t s);
 
 int upload_weights(const float* h_weights, const uint8_t* h_select, int n_folds, int n_cols, int cols_pad,
                    cudaStream_t s, float** d_w, uint8_t** d_sel);

@@ -1,0 +1,808 @@
+// K4 (fp16-split tensor-core variant) -- dense sliding-window Zernike correlation as an implicit GEMM
+// on tcgen05 / TMEM with the fused n-fold symmetry-score epilogue.
+// Replaces ZPs._transform_fft_convolve (mtflearn/features/_zps.py:159-193) and zmoments.rot_maps
+// (mtflearn/features/_zmoments.py:420-462):
+//   Z[j,y,x] = 1/area * sum_{a,b<k} img0[y-k/2+a, x-k/2+b] * V[j,a,b]        (img0 zero-extended)
+//
+// Same GEMM view as zb200_map_tc.cu (M = output pixels of one row, N = modes, K = window taps, the
+// Toeplitz A operand never materialised), but the arithmetic is kind::f16 instead of kind::tf32:
+//   frame  x' = x * 2^-e  (e from max|x|, so |x'| < 2^14),   x1 = RN_f16(x'), x2 = RN_f16(x' - x1)
+//   basis  b = V,                                             b1 = RN_f16(b),  b2 = RN_f16(b - b1)
+//   Z = 2^e/area * sum (x1.b1 + x2.b1 + x1.b2)                        -> 22-bit operands, fp32-grade
+// A K=16 f16 MMA costs what a K=8 tf32 MMA costs, so the three terms cost 1.5 tf32 passes instead of 3.
+//
+// Operand geometry.  kind::f16 core matrices are 8 rows x 16 B = 8 taps, and in the un-swizzled K-major
+// canonical layout rows of one core matrix are 16 B apart, so with MMA row i standing for pixel
+// x0 + 4i + r the pre-pass writes, per pixel phase r and part (x1|x2), the "overlapped" row
+//   E_r[q][t] = part(img[y][4q + t + r - pad]),  t = 0..7          (16 B per q; 2x duplication)
+// and element (i, tap t) of the 16-tap group g of window row a sits at  E_r + 16 (q0 + i + 4g) + 2t,
+// taps 8..15 at +32 B (leading byte offset 32 B, stride byte offset 128 B).  TMA loads rows of E
+// (zero fill outside the frame = the reference's zero extension).
+// Taps outside the unit disk are zero in every mode: 16-tap groups that lie entirely outside are never
+// issued, and the packed B operand (b1 | b2, 128-B swizzled k-blocks of 4 groups) only holds active groups.
+//
+// Tile = (output row, 512-pixel span, phase pair): two accumulators of 128 pixels x n_pad modes, two
+// accumulator sets in TMEM, drained every ~32 K-steps into fp32 registers (the tensor core accumulates
+// with round-toward-zero).  Warp roles (384 threads): warp 0 frame-row TMA producer, warp 1 basis TMA
+// producer (multicast across the cluster), warp 2 MMA issuer, warp 3 TMEM allocator, warpgroups 1-2
+// epilogue (one pixel phase each; thread == pixel, so the score is thread-local).
+#include "zb200_common.cuh"
+#include "zb200_tc_ptx.cuh"
+
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <vector>
+
+namespace zb200 {
+namespace hmap {
+
+using namespace tc;
+
+constexpr int kSpan = 512;              // pixels per tile span (4 phases x 128 MMA rows)
+constexpr int kMaxColChunks = 8;        // running sums per epilogue thread: 8 x 16 columns
+constexpr int kRegsCtl = 64, kRegsEpi = 208;     // (64 + 2*208) * 128 < 64 Ki registers
+constexpr int kMaxWindow = kMapHalfMaxWindow;
+constexpr int kFoldsPerLaunch = 8;
+
+struct MapParams {
+    int H, W;
+    int row0, rows;
+    int k, half, pad;
+    int n_pad, n_modes;
+    int n_terms;         // 1: x1.b1 only (11-bit operands);  3: fp32-grade split
+    int n_span;
+    long long n_tiles;   // rows * n_span * 2
+    int n_groups;        // 16-tap groups per window row (G)
+    int a_first, a_end;  // window rows with at least one tap inside the disk
+    int n_kb;            // basis k-blocks (4 groups of 16 taps each) per tile
+    int n_blocks;        // row blocks per tile: G<=2 -> 4/G window rows share one k-block, else one row = ceil(G/4) k-blocks
+    int chunk_blocks;    // row blocks per accumulator chunk
+    int copy_q, n_box, bw_q;   // one staged row copy: n_box TMA boxes of bw_q 16-byte units
+    int img_slots, b_stages;
+    int cluster;
+    float* out_moments;
+    float* out_scores;
+    const float* scale;  // [1]: 2^e / area, written by the pre-pass
+    int n_folds;
+    int norm_kind;
+    int dbg;             // ZB200_MAP_DEBUG experiment bits (results wrong when set)
+    int park_ns;         // suspend-time hint of the off-critical-path barrier waits (0 = plain try_wait)
+    // score tables live in the kernel parameters: with the column loops unrolled every weight is a
+    // constant-bank operand of its FFMA (no loads in the epilogue)
+    float selw[128];                  // 1 for modes that enter the norm (unselect()), else 0
+    float wts[kFoldsPerLaunch][128];  // construct_rot_maps_matrix rows, zero on unselected / padding modes
+};
+
+// un-swizzled K-major operand whose rows are 16 B apart: SBO (next group of 8 rows) = 128 B, LBO (next
+// 8-tap core matrix along K) = 32 B, descriptor version 1
+constexpr uint32_t kDescHiToeplitz = (uint32_t)(128 >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo_toeplitz(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (2u << 16); }
+__device__ __forceinline__ uint64_t desc_toeplitz(uint32_t lo) { return ((uint64_t)kDescHiToeplitz << 32) | lo; }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)),
+        "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+        : "memory");
+}
+
+// kind::f16 with fp16 inputs, fp32 accumulate, A and B K-major, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                     // c_format = F32;  a_format = b_format = 0 (F16)
+    d |= (uint32_t)(n >> 3) << 17;    // N / 8
+    d |= (uint32_t)(128 >> 4) << 24;  // M / 16
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ---- pre-pass 1: max |img| (bit pattern; non-negative floats order like their bits) ----------------
+__global__ void map_absmax_kernel(const float* __restrict__ img, long long n, unsigned int* __restrict__ out_bits) {
+    unsigned int m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(__ldg(img + i)) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out_bits, m);
+}
+
+// biased exponent of the frame maximum, clamped so that both 2^(140-E) and 2^(E-140) are normal floats
+__device__ __forceinline__ int frame_exponent(unsigned int absmax_bits) {
+    int E = (int)((absmax_bits >> 23) & 0xFFu);
+    if (absmax_bits == 0) E = 127;
+    return min(max(E, 16), 254);
+}
+
+// ---- pre-pass 2: frame -> overlapped fp16 operand planes [part][phase r][H][Wq][8] --------------------
+//   plane(part, r)[y][q][t] = part(img[y][4q + t + r - pad] * 2^(140-E)),   zero outside the row
+// also writes scale[0] = 2^(E-140) / area for the epilogue.
+__global__ void map_prepare_kernel(const float* __restrict__ img, int H, int W, int Wq, int pad, int n_parts,
+                                   const unsigned int* __restrict__ absmax_bits, double inv_area,
+                                   uint4* __restrict__ planes, float* __restrict__ scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long plane_units = (long long)H * Wq;
+    const int E = frame_exponent(*absmax_bits);
+    if (i == 0) *scale = (float)ldexp(inv_area, E - 140);
+    if (i >= plane_units) return;
+    const float mult = __uint_as_float((uint32_t)(267 - E) << 23);       // 2^(140-E)
+    const int y = (int)(i / Wq), q = (int)(i - (long long)y * Wq);
+    const float* row = img + (long long)y * W;
+    const int xb = 4 * q - pad;
+    __half h1[11], h2[11];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+        const int x = xb + j;
+        const float v = (x >= 0 && x < W) ? __ldg(row + x) * mult : 0.f;
+        h1[j] = __float2half_rn(v);
+        h2[j] = __float2half_rn(v - __half2float(h1[j]));
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t w1[4], w2[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            w1[t] = (uint32_t)__half_as_ushort(h1[r + 2 * t]) | ((uint32_t)__half_as_ushort(h1[r + 2 * t + 1]) << 16);
+            w2[t] = (uint32_t)__half_as_ushort(h2[r + 2 * t]) | ((uint32_t)__half_as_ushort(h2[r + 2 * t + 1]) << 16);
+        }
+        planes[(long long)r * plane_units + i] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        if (n_parts == 2) planes[(long long)(4 + r) * plane_units + i] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+    }
+}
+
+// ---- plan-time: packed fp16 basis operands, active 16-tap groups only ---------------------------------
+//   b1[r][gi*16 + t] = RN_f16(V[r][a][16 g + t]),  b2 = RN_f16(V - b1);  (a, g) = groups[gi];  zero for taps
+//   beyond the window row, padding rows and padding groups.  Row pitch = n_kb * 64 halves (128 B per k-block).
+__global__ void map_pack_basis_kernel(const double* __restrict__ basis, int n_modes, int rows_pad, int k,
+                                      const unsigned short* __restrict__ groups, int n_act, int n_kb,
+                                      __half* __restrict__ b1, __half* __restrict__ b2) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;       // gi * 16 + t
+    const int r = blockIdx.y;
+    if (col >= n_kb * 64) return;
+    const int gi = col >> 4, t = col & 15;
+    double v = 0.0;
+    if (r < n_modes && gi < n_act && groups[gi] != 0xFFFFu) {
+        const int a = groups[gi] >> 8, g = groups[gi] & 0xFF;
+        const int b = 16 * g + t;
+        if (b < k) v = basis[((size_t)r * k + a) * k + b];
+    }
+    const __half h = __double2half(v);
+    const size_t o = (size_t)r * n_kb * 64 + col;
+    b1[o] = h;
+    b2[o] = __double2half(v - (double)__half2float(h));
+}
+
+struct IssueCtx {
+    uint32_t idesc, slot_step, copy_step, b_step, bop_step, gsel, img_lo0, b_lo0, tmem_base;
+    uint16_t cmask;
+    long long my_tiles;
+    int n_chunks;
+    uint64_t *img_full, *img_empty, *b_full, *b_empty, *acc_full, *acc_empty;
+};
+
+// The MMA schedule of one issuer thread, specialised on G = 16-tap groups per window row.
+// Row block = the window rows that share basis k-blocks: G <= 2 -> 4/G rows in one k-block, else one row in
+// ceil(G/4) k-blocks (map_pack_basis_kernel lays the operand out in exactly this order).
+template <int G, bool kX3, bool kCluster2>
+__device__ __forceinline__ void issue_tiles(const MapParams& p, const IssueCtx& c) {
+    constexpr int RB = G <= 2 ? 4 / G : 1;           // window rows per row block
+    int si = 0, sb = 0;
+    uint32_t phi = 0, phb = 0;
+    uint32_t ck = 0;
+    auto b_release = [&]() {
+        if (kCluster2) umma_commit_mc(&c.b_empty[sb], c.cmask);
+        else umma_commit(&c.b_empty[sb]);
+        if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+    };
+    for (long long t = 0; t < c.my_tiles; ++t) {
+        int blk = 0;
+        for (int ch = 0; ch < c.n_chunks; ++ch, ++ck) {
+            const int buf = ck & 1;
+            mbar_wait(&c.acc_empty[buf], ((ck >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d0 = c.tmem_base + (uint32_t)((buf * 2 + (int)c.gsel) * p.n_pad);
+            const int blk_stop = min(p.n_blocks, blk + p.chunk_blocks);
+            uint32_t acc = 0u;
+            for (; blk < blk_stop; ++blk) {
+                mbar_wait(&c.b_full[sb], phb);
+                tc_fence_after();
+                uint32_t b0 = c.b_lo0 + (uint32_t)sb * c.b_step;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    if (RB > 1 && p.a_first + blk * RB + r >= p.a_end) break;      // partial last block
+                    mbar_wait(&c.img_full[si], phi);
+                    tc_fence_after();
+                    // copies of this window row: [phase g][part]; part 1 (x2) directly after part 0 (x1)
+                    const uint32_t a0 = c.img_lo0 + (uint32_t)si * c.slot_step;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        if (G > 4 && g == 4) {                                      // second k-block of a wide row
+                            b_release();
+                            mbar_wait(&c.b_full[sb], phb);
+                            tc_fence_after();
+                            b0 = c.b_lo0 + (uint32_t)sb * c.b_step;
+                        }
+                        const uint32_t ag = a0 + 4u * g;                            // 16 taps = 4 units of 16 B
+                        const uint32_t bg = b0 + 2u * (uint32_t)(RB > 1 ? r * G + g : g % 4);   // 16 fp16 taps = 32 B
+                        umma_f16(d0, desc_toeplitz(ag), desc_from_lo(bg), c.idesc, g == 0 ? acc : 1u);
+                        if (kX3) {
+                            umma_f16(d0, desc_toeplitz(ag + c.copy_step), desc_from_lo(bg), c.idesc, 1u);
+                            umma_f16(d0, desc_toeplitz(ag), desc_from_lo(bg + c.bop_step), c.idesc, 1u);
+                        }
+                    }
+                    acc = 1u;
+                    umma_commit(&c.img_empty[si]);
+                    if (++si == p.img_slots) { si = 0; phi ^= 1; }
+                }
+                b_release();
+            }
+            umma_commit(&c.acc_full[buf]);
+        }
+    }
+}
+
+template <bool kScores, bool kX3, bool kCluster2>
+__global__ void __launch_bounds__(384, 1)
+map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_b1,
+             const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ MapParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int n_bops = kX3 ? 2 : 1;
+    const uint32_t b_bytes = (uint32_t)p.n_pad * 128;                 // one basis operand k-block (4 groups)
+    const uint32_t b_stage = (uint32_t)n_bops * b_bytes;
+    const uint32_t copy_bytes = (uint32_t)p.copy_q * 16;              // one staged row of one (phase, part)
+    const uint32_t slot_bytes = 2u * n_bops * copy_bytes;             // [phase g][part]
+    uint8_t* b_ring = smem;
+    uint8_t* img_ring = smem + (size_t)p.b_stages * b_stage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(img_ring + (((size_t)p.img_slots * slot_bytes + 15) & ~(size_t)15));
+    uint64_t* img_full = bars;
+    uint64_t* img_empty = img_full + p.img_slots;
+    uint64_t* b_full = img_empty + p.img_slots;
+    uint64_t* b_empty = b_full + p.b_stages;
+    uint64_t* acc_full = b_empty + p.b_stages;      // [2]
+    uint64_t* acc_empty = acc_full + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wg = warp >> 2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_img);
+        prefetch_tmap(&map_b1);
+        prefetch_tmap(&map_b2);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.img_slots; ++s) {
+            mbar_init(&img_full[s], 1);
+            mbar_init(&img_empty[s], 2);                 // two issuer warps
+        }
+        for (int s = 0; s < p.b_stages; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 2 * p.cluster);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 2);
+            mbar_init(&acc_empty[b], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t crank = p.cluster > 1 ? cluster_rank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    const long long my_tiles = (p.n_tiles + gridDim.x - 1) / gridDim.x;      // lock-step within the cluster
+    const int n_chunks = (p.n_blocks + p.chunk_blocks - 1) / p.chunk_blocks;
+
+    auto decode = [&](long long tile, int& yl, int& span, int& pp) {
+        pp = (int)(tile & 1);
+        const long long rest = tile >> 1;
+        span = (int)(rest % p.n_span);
+        yl = (int)(rest / p.n_span);
+    };
+
+    if (wg == 0) {
+        reg_dec<kRegsCtl>();
+        if (warp == 0) {
+            // ===================== frame-row producer =====================
+            if (elect_one()) {
+                int s = 0;
+                uint32_t ph = 0;
+                for (long long t = 0; t < my_tiles; ++t) {
+                    const long long tile = blockIdx.x + t * gridDim.x;
+                    int yl, span, pp;
+                    decode(tile, yl, span, pp);
+                    const bool live = tile < p.n_tiles;
+                    const int y = p.row0 + yl;
+                    const int c0 = span * kSpan - p.half + p.pad;            // = 4 q0 (4-byte words of a plane row)
+                    for (int a = p.a_first; a < p.a_end; ++a) {
+                        mbar_wait_parked(&img_empty[s], ph ^ 1, p.park_ns);
+                        if (p.dbg & 1) {
+                            mbar_arrive(&img_full[s]);
+                            if (++s == p.img_slots) { s = 0; ph ^= 1; }
+                            continue;
+                        }
+                        mbar_arrive_expect_tx(&img_full[s], slot_bytes);
+                        uint8_t* slot = img_ring + (size_t)s * slot_bytes;
+                        // dead tiles (past the end, cluster padding) read far outside the frame: all zeros
+                        const int yy = live ? y - p.half + a : -4 * p.k;
+                        for (int g = 0; g < 2; ++g)
+                            for (int pt = 0; pt < n_bops; ++pt)
+                                for (int bx = 0; bx < p.n_box; ++bx)
+                                    tma_load_3d(slot + (size_t)(g * n_bops + pt) * copy_bytes + (size_t)bx * p.bw_q * 16, &map_img,
+                                                &img_full[s], c0 + bx * p.bw_q * 4, yy, pt * 4 + 2 * pp + g, kEvictLast);
+                        if (++s == p.img_slots) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ===================== basis producer =====================
+            if (elect_one()) {
+                const int b_rows = p.n_pad / p.cluster;
+                int s = 0;
+                uint32_t ph = 0;
+                for (long long t = 0; t < my_tiles; ++t) {
+                    for (int kb = 0; kb < p.n_kb; ++kb) {
+                        mbar_wait_parked(&b_empty[s], ph ^ 1, p.park_ns);
+                        if (p.dbg & 16) {
+                            mbar_arrive(&b_full[s]);
+                            if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                            continue;
+                        }
+                        mbar_arrive_expect_tx(&b_full[s], b_stage);
+                        uint8_t* st = b_ring + (size_t)s * b_stage;
+                        if (p.cluster == 1) {
+                            tma_load_2d(st, &map_b1, &b_full[s], kb * kBlockK, 0, kEvictLast);
+                            if (n_bops == 2) tma_load_2d(st + b_bytes, &map_b2, &b_full[s], kb * kBlockK, 0, kEvictLast);
+                        } else {
+                            const size_t off = (size_t)crank * b_rows * 128;
+                            tma_load_2d_mc(st + off, &map_b1, &b_full[s], kb * kBlockK, (int)crank * b_rows, cmask, kEvictLast);
+                            if (n_bops == 2)
+                                tma_load_2d_mc(st + b_bytes + off, &map_b2, &b_full[s], kb * kBlockK, (int)crank * b_rows, cmask,
+                                               kEvictLast);
+                        }
+                        if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ===================== MMA issuers: warp 2 -> accumulator 0, warp 3 -> accumulator 1 =====================
+            // MMAs of different threads are not ordered against each other, so one accumulator always belongs to
+            // one issuing thread.  The loop body is specialised on G (16-tap groups per window row) and fully
+            // unrolled per row block: at N = 96 an MMA lasts ~50 clk, and a loop with per-group branches, bit scans
+            // and register->uniform moves (~60 SASS instructions per group, ncu) is issue-bound at twice that.
+            if (elect_one()) {
+                IssueCtx ctx;
+                ctx.idesc = make_idesc_f16(p.n_pad);
+                ctx.slot_step = slot_bytes >> 4; ctx.copy_step = copy_bytes >> 4;
+                ctx.b_step = b_stage >> 4; ctx.bop_step = b_bytes >> 4;
+                ctx.gsel = warp == 3 ? 1u : 0u;
+                ctx.img_lo0 = desc_lo_toeplitz(smem_u32(img_ring)) + ctx.gsel * (uint32_t)n_bops * ctx.copy_step;
+                ctx.b_lo0 = desc_lo_sw128(smem_u32(b_ring));
+                ctx.tmem_base = tmem_base; ctx.cmask = cmask; ctx.my_tiles = my_tiles; ctx.n_chunks = n_chunks;
+                ctx.img_full = img_full; ctx.img_empty = img_empty; ctx.b_full = b_full; ctx.b_empty = b_empty;
+                ctx.acc_full = acc_full; ctx.acc_empty = acc_empty;
+                switch (p.n_groups) {
+                    case 1: issue_tiles<1, kX3, kCluster2>(p, ctx); break;
+                    case 2: issue_tiles<2, kX3, kCluster2>(p, ctx); break;
+                    case 3: issue_tiles<3, kX3, kCluster2>(p, ctx); break;
+                    case 4: issue_tiles<4, kX3, kCluster2>(p, ctx); break;
+                    case 5: issue_tiles<5, kX3, kCluster2>(p, ctx); break;
+                    case 6: issue_tiles<6, kX3, kCluster2>(p, ctx); break;
+                    case 7: issue_tiles<7, kX3, kCluster2>(p, ctx); break;
+                    default: issue_tiles<8, kX3, kCluster2>(p, ctx); break;
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue: warpgroup 1 -> phase 2pp, warpgroup 2 -> phase 2pp+1 =====================
+        reg_inc<kRegsEpi>();
+        const int g = wg - 1;
+        const int q = warp & 3;
+        const int n_cc = p.n_pad >> 4;
+        const float scale = __ldg(p.scale);
+        uint32_t ck = 0;
+        for (long long t = 0; t < my_tiles; ++t) {
+            const long long tile = blockIdx.x + t * gridDim.x;
+            int yl, span, pp;
+            decode(tile, yl, span, pp);
+            float sum[kMaxColChunks][16];
+#pragma unroll
+            for (int cc = 0; cc < kMaxColChunks; ++cc)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sum[cc][i] = 0.f;
+            for (int c = 0; c < n_chunks; ++c, ++ck) {
+                const int buf = ck & 1;
+                mbar_wait_parked(&acc_full[buf], (ck >> 1) & 1u, p.park_ns);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + g) * p.n_pad);
+#pragma unroll
+                for (int cc = 0; cc < kMaxColChunks; ++cc) {
+                    if (cc < n_cc && !(p.dbg & 8)) {
+                        uint32_t v[16];
+                        tmem_ld16(taddr + cc * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sum[cc][i] += __uint_as_float(v[i]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+            const int x = span * kSpan + 4 * (q * 32 + lane) + 2 * pp + g;
+            if (p.dbg & 4) {
+                if (tile < p.n_tiles && x < p.W) p.out_scores[(size_t)yl * p.W + x] = sum[0][0] + sum[5][15];
+            } else if (tile < p.n_tiles && x < p.W) {
+                if (kScores) {
+                    // pass 1: norms over the selected modes; the sums are squared in place
+                    float s1 = 0.f, s2 = 0.f, sm = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < kMaxColChunks; ++cc) {
+                        if (cc < n_cc) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float z = sum[cc][i] * scale * p.selw[cc * 16 + i];
+                                const float az = fabsf(z);
+                                s1 += az;
+                                s2 = fmaf(z, z, s2);
+                                sm = fmaxf(sm, az);
+                                sum[cc][i] = z * z;
+                            }
+                        }
+                    }
+                    float den = 1.f;
+                    if (p.norm_kind == ZB200_NORM_L1) den = s1 * s1;
+                    else if (p.norm_kind == ZB200_NORM_L2) den = s2;
+                    else if (p.norm_kind == ZB200_NORM_INF) den = sm * sm;
+                    // pass 2: four independent weighted sums at a time
+#pragma unroll
+                    for (int fb = 0; fb < kFoldsPerLaunch; fb += 4) {
+                        if (fb < p.n_folds) {
+                            float num[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int cc = 0; cc < kMaxColChunks; ++cc) {
+                                if (cc < n_cc) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i)
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) num[j] = fmaf(p.wts[fb + j][cc * 16 + i], sum[cc][i], num[j]);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (fb + j < p.n_folds) p.out_scores[((size_t)(fb + j) * p.rows + yl) * p.W + x] = num[j] / den;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int cc = 0; cc < kMaxColChunks; ++cc) {
+                        if (cc < n_cc) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int col = cc * 16 + i;
+                                if (col < p.n_modes) p.out_moments[((size_t)col * p.rows + yl) * p.W + x] = sum[cc][i] * scale;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();
+    if (warp == 3) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// 2-D view [rows][words] of 4-byte words (row pitch pitch_bytes), box = 32 words (one 128-B swizzle atom) x box_rows
+static int encode_basis(CUtensorMap* map, const void* base, uint64_t words, uint64_t rows, uint64_t pitch_bytes,
+                        uint32_t box_rows) {
+    auto enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ZB200_ECUDA;
+    }
+    cuuint64_t dims[2] = {words, rows};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(map basis) failed with CUresult %d", (int)r);
+        return ZB200_ECUDA;
+    }
+    return ZB200_OK;
+}
+
+}  // namespace hmap
+
+// Plan-time: which 16-tap groups of each window row touch the unit disk, and the packed fp16 basis.
+// The grid is the reference's (x_i = -1 + 2 i/(k-1), rho <= 1, _zps.py:68-75); a group is kept when any of its
+// taps has rho^2 <= 1 + 1e-9 (conservative: taps outside the disk are exact zeros of the basis anyway).
+int init_map_half_operand(zb200_plan* p) {
+    using namespace hmap;
+    MapHalf& mh = p->map_half;
+    mh.ready = false;
+    const int k = p->size;
+    if (p->cc_major != 10 || k > kMaxWindow || p->real.rows_pad > 128) return ZB200_OK;   // other map kernels serve these
+    const int G = (k + 15) / 16;
+    mh.n_groups = G;
+    std::vector<unsigned short> groups;
+    mh.a_first = -1;
+    mh.a_end = 0;
+    for (int a = 0; a < k; ++a) {
+        const double y = k > 1 ? -1.0 + 2.0 * a / (k - 1) : 0.0;
+        unsigned short m = 0;
+        for (int b = 0; b < k; ++b) {
+            const double x = k > 1 ? -1.0 + 2.0 * b / (k - 1) : 0.0;
+            if (x * x + y * y <= 1.0 + 1e-9) m |= (unsigned short)(1u << (b >> 4));
+        }
+        mh.act[a] = m;
+        if (m) {
+            if (mh.a_first < 0) mh.a_first = a;
+            mh.a_end = a + 1;
+        }
+    }
+    if (mh.a_first < 0) { mh.a_first = 0; mh.a_end = 1; mh.act[0] = 1; }
+    // rows between the first and the last active one are active (the disk is convex); every group of those
+    // rows is issued (skipping single groups saves 3-7 % of the MMAs and costs a branchy issue loop).
+    // Operand order = issue order: row blocks of RB rows in KB k-blocks of 4 groups (see issue_tiles).
+    const int RB = G <= 2 ? 4 / G : 1, KB = (G + 3) / 4;
+    const int n_rows = mh.a_end - mh.a_first;
+    mh.n_blocks = (n_rows + RB - 1) / RB;
+    mh.n_kb = mh.n_blocks * (G <= 2 ? 1 : KB);
+    groups.assign((size_t)mh.n_kb * 4, (unsigned short)0xFFFFu);
+    for (int i = 0; i < n_rows; ++i) {
+        const int a = mh.a_first + i, blk = i / RB, r = i % RB;
+        for (int g = 0; g < G; ++g) {
+            const int pos = G <= 2 ? blk * 4 + r * G + g : (blk * KB + g / 4) * 4 + g % 4;
+            groups[pos] = (unsigned short)((a << 8) | g);
+        }
+    }
+    mh.n_act = (int)groups.size();
+    const int rows_pad = p->real.rows_pad;
+    const size_t halves = (size_t)rows_pad * mh.n_kb * 64;
+    ZB_CUDA(cudaMalloc(&mh.b1, halves * 2));
+    ZB_CUDA(cudaMalloc(&mh.b2, halves * 2));
+    unsigned short* d_groups = nullptr;
+    ZB_CUDA(cudaMalloc(&d_groups, groups.size() * sizeof(unsigned short)));
+    ZB_CUDA(cudaMemcpy(d_groups, groups.data(), groups.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    dim3 grid((unsigned)ceil_div(mh.n_kb * 64, 128), (unsigned)rows_pad);
+    map_pack_basis_kernel<<<grid, 128>>>(p->basis64, p->n_modes, rows_pad, k, d_groups, mh.n_act, mh.n_kb,
+                                         static_cast<__half*>(mh.b1), static_cast<__half*>(mh.b2));
+    ZB_LAUNCHED();
+    ZB_CUDA(cudaDeviceSynchronize());
+    ZB_CUDA(cudaFree(d_groups));
+    mh.max_cluster = 1;
+    for (int lg = 0; lg < 2; ++lg) {
+        const int c = 1 << lg;
+        if (rows_pad % (8 * c) != 0) break;
+        int rc = encode_basis(&mh.tmap_b1[lg], mh.b1, (uint64_t)mh.n_kb * 32, (uint64_t)rows_pad, (uint64_t)mh.n_kb * 128,
+                              (uint32_t)(rows_pad / c));
+        if (rc) return rc;
+        rc = encode_basis(&mh.tmap_b2[lg], mh.b2, (uint64_t)mh.n_kb * 32, (uint64_t)rows_pad, (uint64_t)mh.n_kb * 128,
+                          (uint32_t)(rows_pad / c));
+        if (rc) return rc;
+        mh.max_cluster = c;
+    }
+    mh.ready = true;
+    return ZB200_OK;
+}
+
+void free_map_half_operand(zb200_plan* p) {
+    cudaFree(p->map_half.b1);
+    cudaFree(p->map_half.b2);
+    p->map_half = MapHalf();
+}
+
+bool map_h_supported(const zb200_plan* p, int precision) {
+    if (precision != ZB200_PREC_F16 && precision != ZB200_PREC_F16X3) return false;
+    return p->map_half.ready;
+}
+
+int map_h(const zb200_plan* p, const float* d_img, int H, int W, int row0, int rows, int precision,
+          float* d_moments, float* d_scores, const float* h_w, const uint8_t* h_sel, int n_folds, int norm_kind,
+          cudaStream_t s) {
+    using namespace hmap;
+    if (rows == 0) return ZB200_OK;
+    if (d_scores) {
+        ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
+        ZB_CHECK_ARG(h_w && h_sel, "weights/select must not be null");
+        if (n_folds > kFoldsPerLaunch) {
+            // the score tables of one launch hold kFoldsPerLaunch folds: split the fold list
+            for (int f0 = 0; f0 < n_folds; f0 += kFoldsPerLaunch) {
+                const int nf = n_folds - f0 < kFoldsPerLaunch ? n_folds - f0 : kFoldsPerLaunch;
+                int rc = map_h(p, d_img, H, W, row0, rows, precision, nullptr, d_scores + (size_t)f0 * rows * W,
+                               h_w + (size_t)f0 * p->n_modes, h_sel, nf, norm_kind, s);
+                if (rc) return rc;
+            }
+            return ZB200_OK;
+        }
+    }
+    if (!map_h_supported(p, precision)) {
+        set_error("fp16-split tcgen05 dense map unsupported for n_max=%d size=%d (needs sm_100, size <= %d, <= 128 operand rows)",
+                  p->n_max, p->size, kMaxWindow);
+        return ZB200_EUNSUP;
+    }
+    const MapHalf& mh = p->map_half;
+    const bool x3 = precision == ZB200_PREC_F16X3;
+    MapParams prm{};
+    prm.H = H; prm.W = W; prm.row0 = row0; prm.rows = rows;
+    prm.k = p->size; prm.half = p->size / 2;
+    prm.pad = 8 + (prm.half & 3);                                  // (pad - half) % 4 == 0, pad >= 8
+    prm.n_pad = p->real.rows_pad; prm.n_modes = p->n_modes;
+    prm.n_terms = x3 ? 3 : 1;
+    prm.n_span = (int)ceil_div(W, kSpan);
+    prm.n_tiles = (long long)rows * prm.n_span * 2;
+    prm.n_groups = mh.n_groups;
+    prm.a_first = mh.a_first; prm.a_end = mh.a_end;
+    prm.n_kb = mh.n_kb;
+    prm.n_blocks = mh.n_blocks;
+    const int nq = 128 + 4 * mh.n_groups - 2;                     // 16-byte units one staged row spans
+    prm.n_box = (int)ceil_div(nq, 64);
+    prm.bw_q = round_up((int)ceil_div(nq, prm.n_box), 8);          // TMA destinations stay 128-B aligned
+    prm.copy_q = prm.n_box * prm.bw_q;
+    {
+        // drain after ~16 groups (48 accumulating MMAs): the tensor core accumulates with round-toward-zero
+        const int rb = mh.n_groups <= 2 ? 4 / mh.n_groups : 1;
+        const int chunk_rows = 16 / mh.n_groups > 0 ? 16 / mh.n_groups : 1;
+        prm.chunk_blocks = chunk_rows / rb > 0 ? chunk_rows / rb : 1;
+    }
+    prm.out_moments = d_moments; prm.out_scores = d_scores;
+    prm.n_folds = n_folds; prm.norm_kind = norm_kind;
+    if (d_scores) {
+        for (int c = 0; c < p->n_modes; ++c) prm.selw[c] = h_sel[c] ? 1.f : 0.f;
+        for (int f = 0; f < n_folds; ++f)
+            for (int c = 0; c < p->n_modes; ++c) prm.wts[f][c] = h_sel[c] ? h_w[(size_t)f * p->n_modes + c] : 0.f;
+    }
+    if (const char* e = getenv("ZB200_MAP_DEBUG")) prm.dbg = atoi(e);
+    prm.park_ns = 0;
+    if (const char* e = getenv("ZB200_MAP_PARK")) prm.park_ns = atoi(e);
+
+    // operand planes of the frame: (x1 | x2) x 4 pixel phases, overlapped 16-byte units
+    const int n_parts = x3 ? 2 : 1;
+    const int Wq = (W - 1 + prm.pad) / 4 + 1;
+    const int n_maps = 4 * n_parts;
+    const size_t plane_bytes = (size_t)H * Wq * 16;
+    uint8_t* scratch = nullptr;
+    ZB_CUDA(cudaMallocAsync(&scratch, 256 + (size_t)n_maps * plane_bytes, s));
+    unsigned int* d_bits = reinterpret_cast<unsigned int*>(scratch);
+    float* d_scale = reinterpret_cast<float*>(scratch + 16);
+    uint4* planes = reinterpret_cast<uint4*>(scratch + 256);
+    prm.scale = d_scale;
+    {
+        cudaError_t e = cudaMemsetAsync(d_bits, 0, 16, s);
+        if (e != cudaSuccess) { cudaFreeAsync(scratch, s); set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e)); return ZB200_ECUDA; }
+        const long long n = (long long)H * W;
+        const int blocks = (int)(ceil_div(n, 256 * 8) < 4 * p->sm_count ? ceil_div(n, 256 * 8) : 4 * p->sm_count);
+        map_absmax_kernel<<<blocks, 256, 0, s>>>(d_img, n, d_bits);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        const long long units = (long long)H * Wq;
+        map_prepare_kernel<<<(unsigned)ceil_div(units, 128), 128, 0, s>>>(d_img, H, W, Wq, prm.pad, n_parts, d_bits, p->inv_area,
+                                                                           planes, d_scale);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    // 3-D TMA descriptor [plane][row][4-byte words], box = 4*bw_q words x 1 row x 1 plane, no swizzle, zero fill outside
+    CUtensorMap map_img;
+    {
+        auto enc = get_encode();
+        if (!enc) { cudaFreeAsync(scratch, s); set_error("cuTensorMapEncodeTiled is not available"); return ZB200_ECUDA; }
+        cuuint64_t dims[3] = {(cuuint64_t)Wq * 4, (cuuint64_t)H, (cuuint64_t)n_maps};
+        cuuint64_t strides[2] = {(cuuint64_t)Wq * 16, (cuuint64_t)plane_bytes};
+        cuuint32_t box[3] = {(cuuint32_t)prm.bw_q * 4, 1, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&map_img, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, planes, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            cudaFreeAsync(scratch, s);
+            set_error("cuTensorMapEncodeTiled(frame planes) failed with CUresult %d", (int)r);
+            return ZB200_ECUDA;
+        }
+    }
+
+    int cluster = 2;
+    if (const char* e = getenv("ZB200_TC_CLUSTER")) cluster = atoi(e);
+    if (cluster != 1 && cluster != 2) cluster = 2;
+    while (cluster > 1 && (cluster > mh.max_cluster || prm.n_tiles < 2 * cluster)) cluster >>= 1;
+    prm.cluster = cluster;
+    const int lg = cluster == 2 ? 1 : 0;
+
+    const int b_stage = (x3 ? 2 : 1) * prm.n_pad * 128;
+    const int slot_bytes = 2 * n_parts * prm.copy_q * 16;
+    prm.b_stages = 4;
+    prm.img_slots = 8;
+    if (const char* e = getenv("ZB200_MAP_BSTAGES")) prm.b_stages = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char* e = getenv("ZB200_MAP_SLOTS")) prm.img_slots = atoi(e) > 0 ? atoi(e) : 8;
+    const size_t smem = 1024 + (size_t)prm.b_stages * b_stage + (((size_t)prm.img_slots * slot_bytes + 15) & ~(size_t)15) +
+                        8 * (2 * prm.img_slots + 2 * prm.b_stages + 4) + 16;
+    if (smem > (size_t)kSmemLimit) {
+        cudaFreeAsync(scratch, s);
+        set_error("fp16-split dense map: window %d needs %zu B of shared memory", prm.k, smem);
+        return ZB200_EUNSUP;
+    }
+    long long grid = prm.n_tiles < p->sm_count ? prm.n_tiles : p->sm_count;
+    grid = (grid / cluster) * cluster;
+    if (grid < cluster) grid = cluster;
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    auto launch = [&](auto kernel) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err == cudaSuccess) err = cudaLaunchKernelEx(&cfg, kernel, map_img, mh.tmap_b1[lg], mh.tmap_b2[lg], prm);
+        return err;
+    };
+    const int variant = (d_scores ? 4 : 0) | (x3 ? 2 : 0) | (cluster == 2 ? 1 : 0);
+    switch (variant) {
+        case 0: e = launch(map_h_kernel<false, false, false>); break;
+        case 1: e = launch(map_h_kernel<false, false, true>); break;
+        case 2: e = launch(map_h_kernel<false, true, false>); break;
+        case 3: e = launch(map_h_kernel<false, true, true>); break;
+        case 4: e = launch(map_h_kernel<true, false, false>); break;
+        case 5: e = launch(map_h_kernel<true, false, true>); break;
+        case 6: e = launch(map_h_kernel<true, true, false>); break;
+        default: e = launch(map_h_kernel<true, true, true>); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaFreeAsync(scratch, s);
+    if (e != cudaSuccess) {
+        set_error("map_h_kernel launch failed: %s", cudaGetErrorString(e));
+        return ZB200_ECUDA;
+    }
+    ZB_CUDA(cudaGetLastError());
+    return ZB200_OK;
+}
+
+}  // namespace zb200

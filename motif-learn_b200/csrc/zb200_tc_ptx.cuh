@@ -39,6 +39,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same wait for warps that are off the critical path (epilogue, producers): the suspend-time hint lets the
+// hardware park the thread instead of re-issuing try_wait, which keeps issue slots free for the MMA warp.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+}
 // One elected lane of a fully converged warp; unlike `lane == 0` ptxas knows the region has exactly
 // one active thread and emits the uniform-datapath instructions (UTCHMMA, UTMALDG) without a
 // per-instruction election loop.

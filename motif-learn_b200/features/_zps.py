@@ -10,9 +10,11 @@ input), this class calls the C ABI of libzernike_b200.so: the basis is generated
 fp64 on the GPU and cached in HBM (plan), patch stacks go through the projection kernel,
 images through the sliding-window map kernel.  Extra, keyword-only options:
 
-``precision``  'auto' | 'fp32' | 'tf32x3' | 'tf32' -- arithmetic of the contraction.
-               'auto' picks the fp32-grade tensor-core path when the plan supports it,
-               otherwise the fp32 SIMT kernel.  Stated error bounds: DESIGN.md.
+``precision``  'auto' | 'fp32' | 'tf32x3' | 'tf32' | 'f16x3' | 'f16' -- arithmetic of the contraction.
+               'auto' picks the fp32-grade tensor-core path when the plan supports it (patch stacks:
+               'tf32x3'; dense maps: the fp16-split 'f16x3', then 'tf32x3'), otherwise the fp32 SIMT
+               kernel.  'f16x3'/'f16' are dense-map kernels; for patch stacks they mean 'tf32x3'/'tf32'.
+               Stated error bounds: DESIGN.md.
 ``output``     'auto' | 'numpy' | 'torch' -- 'auto' returns what it was given: numpy in ->
                float64 numpy out (like the reference); CUDA tensor in -> float32 CUDA tensor.
 """
@@ -99,8 +101,8 @@ class ZPs(BaseEstimator, TransformerMixin):
                 UserWarning,
                 stacklevel=2
             )
-        if precision not in ("auto", "fp32", "tf32", "tf32x3"):
-            raise ValueError("precision must be one of 'auto', 'fp32', 'tf32x3', 'tf32'")
+        if precision not in ("auto", "fp32", "tf32", "tf32x3", "f16", "f16x3"):
+            raise ValueError("precision must be one of 'auto', 'fp32', 'tf32x3', 'tf32', 'f16x3', 'f16'")
         if output not in ("auto", "numpy", "torch"):
             raise ValueError("output must be one of 'auto', 'numpy', 'torch'")
         self.n_max = n_max
@@ -173,10 +175,17 @@ class ZPs(BaseEstimator, TransformerMixin):
     def _precision_code(self, for_map: bool = False) -> int:
         lib = _lib.load()
         if self.precision == "auto":
-            ok = (lib.zb200_plan_supports_map(self._plan, _lib.PREC_TF32X3) if for_map
-                  else lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3, _lib.OUT_REAL))
+            if for_map:
+                for code in (_lib.PREC_F16X3, _lib.PREC_TF32X3):
+                    if lib.zb200_plan_supports_map(self._plan, code):
+                        return code
+                return _lib.PREC_FP32
+            ok = lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3, _lib.OUT_REAL)
             return _lib.PREC_TF32X3 if ok else _lib.PREC_FP32
-        return _lib.PRECISIONS[self.precision]
+        code = _lib.PRECISIONS[self.precision]
+        if not for_map and code in (_lib.PREC_F16, _lib.PREC_F16X3):
+            code = _lib.PREC_TF32 if code == _lib.PREC_F16 else _lib.PREC_TF32X3
+        return code
 
     def _want_host(self, given) -> bool:
         if self.output == "auto":

@@ -4,8 +4,8 @@ of the live reference.  Runs on the B200 box: ``pytest -m gpu``.
 Tolerances (DESIGN.md "Numerics"):
   * basis (fp64)            |ours - ref| <= 5e-12 (n_max<=12), 1e-8 (n_max=20: the REFERENCE's own
                             float-factorial error, ours is 2e-14 from exact)
-  * fp32-grade contraction  allclose(rtol=1e-4, atol=1e-6*max|ref|)      (fp32 SIMT, tf32x3)
-  * 1xTF32 contraction      |err| <= 1e-3*max|ref|                        (stated bound, fast mode)
+  * fp32-grade contraction  allclose(rtol=1e-4, atol=1e-6*max|ref|)      (fp32 SIMT, tf32x3, f16x3)
+  * 1xTF32 / 1xF16 map      |err| <= 1e-3*max|ref|                        (stated bound, fast modes)
   * n-fold scores           |err| <= 1e-5 (fp32-grade) on items with non-zero norm, NaN pattern equal
   * gather / index work     bit-exact
 """
@@ -53,6 +53,8 @@ def map_precisions(api, n_max, size):
     out = ["fp32"]
     if _lib.load().zb200_plan_supports_map(z._plan, _lib.PREC_TF32X3):
         out += ["tf32x3", "tf32"]
+    if _lib.load().zb200_plan_supports_map(z._plan, _lib.PREC_F16X3):
+        out += ["f16x3", "f16"]
     return out
 
 
@@ -272,7 +274,7 @@ def test_map_golden(api, golden, torch):
     img = g["map_img"]
     ys, xs = g["map_ys"], g["map_xs"]
     precs = map_precisions(api, 12, 48)
-    assert "tf32x3" in precs                      # the tensor-core map must be available for 48-px windows
+    assert "tf32x3" in precs and "f16x3" in precs   # the tensor-core maps must be available for 48-px windows
     for prec in precs:
         z = api.ZPs(12, 48, precision=prec)
         zm = z.transform(img)
@@ -280,7 +282,7 @@ def test_map_golden(api, golden, torch):
         np.testing.assert_array_equal(zm.valid_mask, g["map_valid"])
         fused = z.symmetry_map(img, [2, 3, 4, 6])
         assert fused.shape == (4, 160, 192)
-        if prec == "tf32":                        # fast mode: stated bounds
+        if prec in ("tf32", "f16"):               # fast modes: stated bounds
             assert np.abs(zm.data[:, ys, xs] - g["map_moments"]).max() <= 1e-3 * np.abs(g["map_moments"]).max()
             assert np.abs(fused - g["map_rot"]).max() < 2e-3
             continue
@@ -344,7 +346,7 @@ def test_map_equals_gather_plus_projection_at_config2_size(api, torch):
     n, m, v = zo.zernike_basis(12, 48)
     zref = zo.project_patches(patches.astype(np.float64), v)
     want = zo.rot_maps(zref, n, m, [2, 3, 4, 6])
-    for prec in [pr for pr in map_precisions(api, 12, 48) if pr != "tf32"]:
+    for prec in [pr for pr in map_precisions(api, 12, 48) if pr not in ("tf32", "f16")]:
         z = api.ZPs(12, 48, precision=prec)
         scores = z.symmetry_map(dimg, [2, 3, 4, 6])
         assert scores.shape == (4, 2048, 2048)
