@@ -34,7 +34,9 @@ FOLDS = [2, 3, 4, 6]
 # DRAM bytes per launch of the projection kernel at the default batch, from the committed ncu
 # captures (profiles/r01_prof_tc3_raw.csv, r01_prof_tc1_raw.csv): read + write
 NCU_TRAFFIC = {"tf32x3": 4.330278e9 + 45.745e6, "tf32": 4.317721e9 + 53.717e6}
-NCU_TRAFFIC_MAP = 136.456e6 + 48.684e6      # map_tc_kernel<scores>, 2048^2, profiles/r01_prof_map_raw.csv
+# dense-map kernels at 2048^2 (profiles/r01_prof_map_raw.csv, r01_prof_maph_raw.csv): read + write
+NCU_TRAFFIC_MAP = {"tf32x3": 136.456e6 + 48.684e6, "f16x3": 135.979e6 + 45.623e6}
+PREC_NAMES = {0: "fp32", 1: "tf32", 2: "tf32x3", 3: "f16", 4: "f16x3"}
 
 
 def peaks():
@@ -241,7 +243,7 @@ def bench_patches(torch, dist, rank, world, args, pk):
     from motif_learn_b200.features import ZPs, KeyPoints
     dev = torch.cuda.current_device()
     zp = ZPs(N_MAX, PATCH, precision=args.precision)
-    prec = {0: "fp32", 1: "tf32", 2: "tf32x3"}[zp._precision_code()]
+    prec = PREC_NAMES[zp._precision_code()]
     n_modes = len(zp.n)
 
     # synthetic input: patches gathered at the atom sites of lattice frames (K2), tiled to the batch
@@ -314,7 +316,7 @@ def bench_map(torch, dist, rank, world, args, pk, tiled=False):
     MAP_SIZE, MAP_WINDOW = (4096, 64) if tiled else (2048, 48)
     dev = torch.cuda.current_device()
     zp = ZPs(N_MAX, MAP_WINDOW, precision=args.precision)
-    prec = {0: "fp32", 1: "tf32", 2: "tf32x3"}[zp._precision_code(for_map=True)]
+    prec = PREC_NAMES[zp._precision_code(for_map=True)]
     if tiled:
         img, _ = honeycomb_image(MAP_SIZE, bond=12.0, seed=0, vacancy_frac=0.01, dopant_frac=0.005)
         row0, rows = row_band(MAP_SIZE, rank, world)
@@ -335,13 +337,26 @@ def bench_map(torch, dist, rank, world, args, pk, tiled=False):
     value = mpix * (1 if tiled else world) * steps / (ms / 1e3)
     flops = 2.0 * rows * MAP_SIZE * MAP_WINDOW * MAP_WINDOW * len(zp.n)
     ach = flops * steps / (ms / 1e3) / 1e12
-    tf32_peak = pk["bf16_tflops"] / 2.0
-    roof = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-            "traffic": NCU_TRAFFIC_MAP if (prec == "tf32x3" and not tiled) else None,
-            "peak_source": pk["source"] + " bf16 / 2 (tf32 dense rate)",
-            "kernel": "map_simt_kernel<scores>" if prec == "fp32" else "map_tc_kernel<scores>",
+    # denominator: the measured dense bf16 rate for the kind::f16 kernels (same tensor-pipe rate), half of it
+    # for the kind::tf32 kernels.  `achieved` counts ALGORITHMIC flops only; `executed_tflops` adds what the
+    # kernel really issues (three split terms, modes padded to 96, window rows padded to 16-tap groups).
+    f16_kernel = prec in ("f16", "f16x3")
+    peak = pk["bf16_tflops"] if f16_kernel else pk["bf16_tflops"] / 2.0
+    pad_modes = 96.0 / len(zp.n) if prec != "fp32" else 1.0
+    if f16_kernel:
+        xs = -1.0 + 2.0 * np.arange(MAP_WINDOW) / (MAP_WINDOW - 1)
+        rows_on = int(((xs[None, :] ** 2 + xs[:, None] ** 2) <= 1.0 + 1e-9).any(axis=1).sum())
+        pad_taps = rows_on * (-(-MAP_WINDOW // 16)) * 16.0 / (MAP_WINDOW * MAP_WINDOW)
+    else:
+        pad_taps = 1.0
+    executed = ach * {"fp32": 1, "tf32": 1, "tf32x3": 3, "f16": 1, "f16x3": 3}[prec] * pad_modes * pad_taps
+    roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": NCU_TRAFFIC_MAP.get(prec) if not tiled else None,
+            "peak_source": pk["source"] + (" bf16 dense (kind::f16 MMAs)" if f16_kernel else " bf16 / 2 (tf32 dense rate)"),
+            "kernel": {"fp32": "map_simt_kernel<scores>", "tf32": "map_tc_kernel<scores>", "tf32x3": "map_tc_kernel<scores>",
+                       "f16": "map_h_kernel<scores,x1>", "f16x3": "map_h_kernel<scores,x3>"}[prec],
             "algorithmic_flops_per_launch": flops,
-            "executed_tflops": ach * {"fp32": 1, "tf32": 1, "tf32x3": 3}[prec] * (96.0 / len(zp.n) if prec != "fp32" else 1.0)}
+            "executed_tflops": executed, "executed_frac": executed / peak}
     # end to end: numpy frame in, numpy scores out
     zp_host = ZPs(N_MAX, MAP_WINDOW, precision=args.precision, output="numpy")
     host = torch.empty((MAP_SIZE, MAP_SIZE), dtype=torch.float32, pin_memory=True)
@@ -358,7 +373,8 @@ def bench_map(torch, dist, rank, world, args, pk, tiled=False):
     e2e = {"value": mpix * (1 if tiled else world) * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": MAP_SIZE * MAP_SIZE * 4,
            "d2h_bytes_per_step": int(res.size * 8), "steps": e2e_steps, "api": "ZPs.symmetry_map(numpy) -> numpy"}
     return {"metric": "symmetry_map_mpix_per_sec", "value": value, "unit": "Mpix/s", "ms_per_step": ms / steps,
-            "steps": steps, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)"}[prec],
+            "steps": steps, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)", "f16": "f16",
+                                      "f16x3": "f16x3(f32-grade)"}[prec],
             "scaling": "strong" if tiled else "weak",
             "config": {"workload": f"symmetry map {MAP_SIZE}x{MAP_SIZE} n_max={N_MAX} window={MAP_WINDOW} "
                                    f"folds={FOLDS} (BASELINE configs[{3 if tiled else 1}])", "precision": prec,
@@ -375,7 +391,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="patches", choices=["patches", "map", "map4k"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "tf32x3", "f16", "f16x3"])
     ap.add_argument("--batch", type=int, default=262144, help="patches per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=65536)
     ap.add_argument("--map-steps", type=int, default=20)

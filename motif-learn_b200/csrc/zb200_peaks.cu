@@ -1,0 +1,254 @@
+// Peak detection ("next" row f2 of SURVEY section 8): the step right before the Zernike hot path.
+// Replaces mtflearn.features.local_max (mtflearn/features/_local_max_v2.py:6-66):
+//   peaks = skimage.feature.peak_local_max(image, min_distance=1, threshold_abs=threshold)
+//   keep  = filter_peaks_by_distance(image, peaks, min_distance)      # intensity-ordered radius NMS
+// skimage's routine at min_distance=1 reduces to (published algorithm, skimage/feature/peak.py):
+//   candidate <=> image == maximum_filter(image, 3x3, mode='nearest')  and  image > threshold,
+//   the 1-pixel frame border excluded, no candidate at all for a constant image; candidates ordered by
+//   intensity (descending, stable = raster order among equals); ensure_spacing(spacing=1) removes nothing
+//   (it rejects points strictly closer than 1 pixel).
+// The reference's greedy suppression (visit peaks by descending intensity; a visited, still-kept peak
+// suppresses every other peak within Euclidean distance <= min_distance) is sequential as written.  Here it
+// runs as a fixed point over a rank map of the frame: peak i is SUPPRESSED as soon as one higher-ranked
+// neighbour is KEPT, and KEPT as soon as all higher-ranked neighbours are SUPPRESSED -- the same set, a
+// handful of sweeps.  Ordering among exactly equal intensities is raster order (the reference leaves it to
+// numpy's unstable argsort).
+#include "zb200_common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+namespace zb200 {
+
+// order-preserving map float -> uint32 (ascending); -0 is folded onto +0 first (numpy compares them equal)
+__device__ __forceinline__ uint32_t float_order(float f) {
+    if (f == 0.f) f = 0.f;
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// [0] = min, [1] = max of the frame, as ordered uint32 (init: [0] = 0xFFFFFFFF, [1] = 0)
+__global__ void peaks_minmax_kernel(const float* __restrict__ img, long long n, uint32_t* __restrict__ mm) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t o = float_order(__ldg(img + i));
+        lo = min(lo, o);
+        hi = max(hi, o);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm, lo);
+        atomicMax(mm + 1, hi);
+    }
+}
+
+// candidates -> keys (descending-intensity order in the high word, raster index in the low word)
+__global__ void peaks_candidates_kernel(const float* __restrict__ img, int H, int W, int has_thr, double thr,
+                                        const uint32_t* __restrict__ mm, unsigned long long* __restrict__ keys,
+                                        unsigned long long capacity, unsigned long long* __restrict__ count) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    bool hit = false;
+    float v = 0.f;
+    if (mm[0] != mm[1] && x >= 1 && y >= 1 && x < W - 1 && y < H - 1) {      // constant frame: no peaks (skimage)
+        const float* c = img + (size_t)y * W + x;
+        v = __ldg(c);
+        float m = v;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) m = fmaxf(m, __ldg(c + dy * W + dx));
+        // threshold None -> image.min(): compare in the ordered domain so the default needs no host round trip
+        const bool above = has_thr ? ((double)v > thr) : (float_order(v) > mm[0]);
+        hit = (v == m) && above;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if (!ballot) return;
+    const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+    unsigned long long base = 0;
+    if (lane == (__ffs(ballot) - 1)) base = atomicAdd(count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+    if (hit) {
+        const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+        if (slot < capacity)
+            keys[slot] = ((unsigned long long)(~float_order(v)) << 32) | (unsigned long long)((unsigned)y * (unsigned)W + (unsigned)x);
+    }
+}
+
+__global__ void peaks_rank_kernel(const unsigned long long* __restrict__ keys, long long n, int* __restrict__ rank_map) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rank_map[(uint32_t)keys[i]] = (int)i;
+}
+
+// one sweep of the suppression fixed point; state: 0 undecided, 1 kept, 2 suppressed
+__global__ void peaks_nms_kernel(const unsigned long long* __restrict__ keys, long long n, const int* __restrict__ rank_map,
+                                 int H, int W, int R, double r2, unsigned char* __restrict__ state,
+                                 unsigned int* __restrict__ undecided) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || state[i] != 0) return;
+    const uint32_t pix = (uint32_t)keys[i];
+    const int y = (int)(pix / (uint32_t)W), x = (int)(pix - (uint32_t)y * (uint32_t)W);
+    bool pending = false, dead = false;
+    for (int dy = -R; dy <= R && !dead; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = -R; dx <= R; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= W || (double)(dx * dx + dy * dy) > r2) continue;
+            const int j = __ldg(rank_map + (size_t)yy * W + xx);
+            if (j < 0 || j >= i) continue;                 // not a peak / lower priority / itself
+            const unsigned char sj = state[j];
+            if (sj == 1) { dead = true; break; }
+            if (sj == 0) pending = true;
+        }
+    }
+    if (dead) state[i] = 2;
+    else if (!pending) state[i] = 1;
+    else atomicAdd(undecided, 1u);
+}
+
+__global__ void peaks_flags_kernel(const unsigned char* __restrict__ state, long long n, unsigned char* __restrict__ flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = state[i] == 1 ? 1 : 0;
+}
+
+__global__ void peaks_emit_kernel(const unsigned long long* __restrict__ keys, long long n, int W, int32_t* __restrict__ xy) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pix = (uint32_t)keys[i];
+    const uint32_t y = pix / (uint32_t)W;
+    xy[2 * i] = (int32_t)(pix - y * (uint32_t)W);
+    xy[2 * i + 1] = (int32_t)y;
+}
+
+}  // namespace zb200
+
+using namespace zb200;
+
+#define ZB_PEAKS_CUDA(call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            rc = ZB200_ECUDA;                                                                 \
+            goto done;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_distance, int has_threshold,
+                                   double threshold, int32_t* d_xy_out, int64_t capacity, int64_t* h_count,
+                                   int64_t* h_candidates, void* stream) {
+    ZB_CHECK_ARG(d_img && h_count, "local_max: null argument");
+    ZB_CHECK_ARG(H >= 1 && W >= 1 && (long long)H * W < (1ll << 31), "local_max: bad frame size %dx%d", H, W);
+    ZB_CHECK_ARG(min_distance >= 0.0 && min_distance <= 1024.0, "local_max: min_distance %g out of range", min_distance);
+    ZB_CHECK_ARG(capacity >= 0 && (d_xy_out || capacity == 0), "local_max: null output with non-zero capacity");
+    cudaStream_t s = as_stream(stream);
+    *h_count = 0;
+    if (h_candidates) *h_candidates = 0;
+    const long long n_pix = (long long)H * W;
+    // candidates of a 3x3 maximum filter: at most every pixel (plateaus); size the key buffers for that
+    const size_t key_bytes = sizeof(unsigned long long) * (size_t)n_pix;
+    int rc = ZB200_OK;
+    uint8_t* pool = nullptr;
+    void* cub_tmp = nullptr;
+    unsigned long long n_cand = 0;
+    long long n = 0;
+    // layout of the scratch block
+    const size_t off_keys0 = 256, off_keys1 = off_keys0 + key_bytes, off_rank = off_keys1 + key_bytes;
+    const size_t off_state = off_rank + sizeof(int) * (size_t)n_pix, off_flags = off_state + (size_t)n_pix;
+    const size_t total = off_flags + (size_t)n_pix + 256;
+    ZB_CUDA(cudaMallocAsync(&pool, total, s));
+    {
+        uint32_t* mm = reinterpret_cast<uint32_t*>(pool);                       // [0] min, [1] max
+        unsigned long long* count = reinterpret_cast<unsigned long long*>(pool + 16);
+        unsigned int* undecided = reinterpret_cast<unsigned int*>(pool + 32);
+        unsigned long long* n_sel = reinterpret_cast<unsigned long long*>(pool + 48);
+        unsigned long long* keys0 = reinterpret_cast<unsigned long long*>(pool + off_keys0);
+        unsigned long long* keys1 = reinterpret_cast<unsigned long long*>(pool + off_keys1);
+        int* rank_map = reinterpret_cast<int*>(pool + off_rank);
+        unsigned char* state = pool + off_state;
+        unsigned char* flags = pool + off_flags;
+        const uint32_t init[2] = {0xFFFFFFFFu, 0u};
+        ZB_PEAKS_CUDA(cudaMemsetAsync(pool, 0, 256, s));
+        ZB_PEAKS_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        {
+            const int blocks = (int)(ceil_div(n_pix, 256 * 8) < 1184 ? ceil_div(n_pix, 256 * 8) : 1184);
+            peaks_minmax_kernel<<<blocks, 256, 0, s>>>(d_img, n_pix, mm);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            dim3 blk(32, 8), grd((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8));
+            peaks_candidates_kernel<<<grd, blk, 0, s>>>(d_img, H, W, has_threshold, threshold, mm, keys0,
+                                                        (unsigned long long)n_pix, count);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        ZB_PEAKS_CUDA(cudaMemcpyAsync(&n_cand, count, sizeof(n_cand), cudaMemcpyDeviceToHost, s));
+        ZB_PEAKS_CUDA(cudaStreamSynchronize(s));
+        n = (long long)n_cand;
+        if (h_candidates) *h_candidates = n;
+        if (n == 0) goto done;
+        {
+            size_t tmp_bytes = 0;
+            ZB_PEAKS_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys0, keys1, (int)n, 0, 64, s));
+            ZB_PEAKS_CUDA(cudaMallocAsync(&cub_tmp, tmp_bytes, s));
+            ZB_PEAKS_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, tmp_bytes, keys0, keys1, (int)n, 0, 64, s));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ZB_PEAKS_CUDA(cudaFreeAsync(cub_tmp, s));
+            cub_tmp = nullptr;
+        }
+        ZB_PEAKS_CUDA(cudaMemsetAsync(rank_map, 0xFF, sizeof(int) * (size_t)n_pix, s));
+        ZB_PEAKS_CUDA(cudaMemsetAsync(state, 0, (size_t)n, s));
+        peaks_rank_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(keys1, n, rank_map);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        {
+            const int R = (int)floor(min_distance);
+            const double r2 = min_distance * min_distance;
+            for (int sweep = 0; sweep < 4096; ++sweep) {
+                unsigned int left = 0;
+                ZB_PEAKS_CUDA(cudaMemsetAsync(undecided, 0, sizeof(unsigned int), s));
+                peaks_nms_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(keys1, n, rank_map, H, W, R, r2, state, undecided);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                ZB_PEAKS_CUDA(cudaMemcpyAsync(&left, undecided, sizeof(left), cudaMemcpyDeviceToHost, s));
+                ZB_PEAKS_CUDA(cudaStreamSynchronize(s));
+                if (left == 0) break;
+            }
+        }
+        peaks_flags_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(state, n, flags);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        {
+            size_t tmp_bytes = 0;
+            ZB_PEAKS_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, keys1, flags, keys0, n_sel, (int)n, s));
+            ZB_PEAKS_CUDA(cudaMallocAsync(&cub_tmp, tmp_bytes, s));
+            ZB_PEAKS_CUDA(cub::DeviceSelect::Flagged(cub_tmp, tmp_bytes, keys1, flags, keys0, n_sel, (int)n, s));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ZB_PEAKS_CUDA(cudaFreeAsync(cub_tmp, s));
+            cub_tmp = nullptr;
+        }
+        unsigned long long kept = 0;
+        ZB_PEAKS_CUDA(cudaMemcpyAsync(&kept, n_sel, sizeof(kept), cudaMemcpyDeviceToHost, s));
+        ZB_PEAKS_CUDA(cudaStreamSynchronize(s));
+        *h_count = (int64_t)kept;
+        if ((int64_t)kept > capacity) {
+            if (capacity > 0 || d_xy_out) {
+                set_error("local_max: %llu peaks do not fit the output capacity %lld", kept, (long long)capacity);
+                rc = ZB200_EINVAL;
+            }
+            goto done;                                     // capacity 0 + null output = count-only query
+        }
+        if (kept) {
+            peaks_emit_kernel<<<(unsigned)ceil_div((long long)kept, 256), 256, 0, s>>>(keys0, (long long)kept, W, d_xy_out);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ZB_PEAKS_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+done:
+    if (cub_tmp) cudaFreeAsync(cub_tmp, s);
+    cudaFreeAsync(pool, s);
+    if (rc == ZB200_OK) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("local_max: %s", cudaGetErrorString(e)); rc = ZB200_ECUDA; }
+    }
+    return rc;
+}

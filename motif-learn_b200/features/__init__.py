@@ -5,6 +5,7 @@ from ._zmoments import zmoments
 from ._indexing import (construct_complex_matrix, construct_real_matrix, construct_rot_maps_matrix,
                         nm2j, nm2j_complex)
 from ._keypoint import KeyPoints, clear_border
+from ._local_max import local_max
 
 __all__ = ["ZPs", "zmoments", "construct_rot_maps_matrix", "construct_complex_matrix", "construct_real_matrix",
-           "KeyPoints", "clear_border", "nm2j", "nm2j_complex"]
+           "KeyPoints", "clear_border", "local_max", "nm2j", "nm2j_complex"]

@@ -181,9 +181,36 @@ def golden_render():
     save("render.npz", pts=pts, amps=amps, sigma=np.array(sigma), img=img, amps2=amps2, img2=img2)
 
 
+def golden_peaks():
+    """Peak detection ("next" row f2).  The reference's ``local_max`` calls skimage's ``peak_local_max``, and
+    scikit-image is absent from this image: the REAL ``mtflearn.features._local_max_v2.local_max`` (its own
+    swap of the columns and its own ``filter_peaks_by_distance``) is run with the oracle's restatement of the
+    skimage routine injected in place of the MagicMock stand-in.  Frames carry seeded noise so that no two
+    candidate intensities are equal (the reference's visiting order is then unique)."""
+    import mtflearn.features._local_max_v2 as lm
+    import zernike_oracle as zo
+    lm.peak_local_max = lambda image, min_distance=1, threshold_abs=None: zo.peak_local_max_md1(image, threshold_abs)
+    arrays = {}
+    rng = np.random.default_rng(7)
+    lat = HoneyCombLattice(size=192, l=12, seed=5, angle=9.0, jitter=0.3)
+    img_a = (lat.to_image() + rng.normal(0.0, 0.02, (192, 192))).astype(np.float32)
+    img_b = rng.random((96, 131)).astype(np.float32)                       # pure noise: dense candidates
+    for tag, img, cases in (("a", img_a, [(3.0, None), (5.0, 0.3), (7.5, None), (1.0, 0.5)]),
+                            ("b", img_b, [(2.0, None), (4.3, 0.6), (12.0, None)])):
+        cand = zo.peak_local_max_md1(img, None)
+        assert len(np.unique(img[cand[:, 0], cand[:, 1]])) == len(cand)     # no intensity ties
+        arrays[f"img_{tag}"] = img
+        arrays[f"cand_{tag}"] = cand
+        for i, (r, thr) in enumerate(cases):
+            arrays[f"pts_{tag}{i}"] = lm.local_max(img, r, thr)
+            arrays[f"arg_{tag}{i}"] = np.array([r, np.nan if thr is None else thr])
+    save("peaks.npz", **arrays)
+
+
 if __name__ == "__main__":
     golden_index()
     golden_basis()
     golden_patches()
     golden_lattice()
     golden_render()
+    golden_peaks()

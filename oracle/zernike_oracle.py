@@ -391,3 +391,57 @@ def render_atoms(shape_hw, pts: np.ndarray, amps, sigma: float, r_factor: float 
         val = np.where(r <= cut, a * np.exp(-0.5 * r ** 2 / float(sigma) ** 2) * (1.0 - 3.0 * t ** 2 + 2.0 * t ** 3), 0.0)
         img[ya:yb, xa:xb] += val
     return img
+
+
+# --------------------------------------------------------------------------- #
+# peak detection ("next" row f2)                                                #
+# --------------------------------------------------------------------------- #
+def peak_local_max_md1(image: np.ndarray, threshold_abs=None) -> np.ndarray:
+    """Restatement of ``skimage.feature.peak_local_max(image, min_distance=1, threshold_abs=t)`` as the
+    reference calls it (mtflearn/features/_local_max_v2.py:61).  scikit-image is a third-party dependency
+    that is NOT installed in this image and is unpinned in the reference's pyproject.toml, so this follows
+    its published algorithm (skimage/feature/peak.py, 0.19-0.25: ``_get_threshold``, ``_get_peak_mask``,
+    ``_exclude_border``, ``_get_high_intensity_peaks``):
+      threshold = threshold_abs if given else image.min();
+      mask = (image == maximum_filter(image, 3x3 footprint, mode='nearest')), all-False for a trivial
+      (constant) image, & (image > threshold); the 1-pixel border is cleared; coordinates sorted by
+      ``argsort(-intensity, kind='stable')``; ``ensure_spacing(spacing=1, p_norm=inf)`` only rejects points
+      strictly closer than 1 pixel, i.e. nothing.  Returns (N, 2) (row, col)."""
+    import scipy.ndimage as ndi
+    image = np.asarray(image)
+    threshold = image.min() if threshold_abs is None else threshold_abs
+    out = image == ndi.maximum_filter(image, footprint=np.ones((3, 3), dtype=bool), mode="nearest")
+    if np.all(out):
+        out[:] = False
+    out &= image > threshold
+    out[:1] = out[-1:] = False
+    out[:, :1] = out[:, -1:] = False
+    coord = np.nonzero(out)
+    order = np.argsort(-image[coord], kind="stable")
+    return np.transpose(coord)[order]
+
+
+def filter_peaks_by_distance(image: np.ndarray, peaks_xy: np.ndarray, min_distance: float) -> np.ndarray:
+    """mtflearn/features/_local_max_v2.py:6-43 -- visit peaks by descending intensity; a visited peak that
+    is still kept suppresses every other peak within Euclidean distance <= min_distance.  Equal
+    intensities are visited in the incoming (raster) order here (the reference: numpy's unstable argsort)."""
+    from scipy.spatial import cKDTree
+    peaks_xy = np.asarray(peaks_xy)
+    if len(peaks_xy) == 0:
+        return peaks_xy.reshape(0, 2)
+    vals = np.array([image[y, x] for x, y in peaks_xy])
+    peaks_xy = peaks_xy[np.argsort(-vals, kind="stable")]
+    tree = cKDTree(peaks_xy)
+    keep = np.ones(len(peaks_xy), dtype=bool)
+    for i, p in enumerate(peaks_xy):
+        if keep[i]:
+            for j in tree.query_ball_point(p, r=min_distance):
+                if j != i:
+                    keep[j] = False
+    return peaks_xy[keep]
+
+
+def local_max(image: np.ndarray, min_distance: float, threshold=None) -> np.ndarray:
+    """mtflearn/features/_local_max_v2.py:46-66: (N, 2) peaks as (x, y), brightest first."""
+    peaks = peak_local_max_md1(image, threshold)
+    return filter_peaks_by_distance(image, peaks[:, ::-1], min_distance)

@@ -508,3 +508,58 @@ def test_render_atoms_golden(golden, torch):
     dense = render_atoms_gpu((300, 700), many, 0.3, 2.0)
     np.testing.assert_allclose(dense.cpu().numpy(), zo.render_atoms((300, 700), many, 0.3, 2.0), rtol=0, atol=2e-6)
     assert float(render_atoms_gpu((16, 16), np.zeros((0, 2)), 1.0, 3.0).abs().max()) == 0.0
+
+
+# ---- "next" row f2: peak detection ------------------------------------------------------------------------
+def test_local_max_golden(api, golden, torch):
+    """CUDA local_max against the reference-generated goldens: identical peaks, identical order."""
+    g = golden("peaks.npz")
+    for tag in ("a", "b"):
+        img = g[f"img_{tag}"]
+        i = 0
+        while f"pts_{tag}{i}" in g.files:
+            r, thr = g[f"arg_{tag}{i}"]
+            thr = None if np.isnan(thr) else float(thr)
+            got = api.local_max(img, float(r), thr)
+            assert got.dtype == np.int64
+            np.testing.assert_array_equal(got, g[f"pts_{tag}{i}"])
+            dev = api.local_max(torch.from_numpy(img).cuda(), float(r), thr, as_tensor=True)
+            assert dev.is_cuda and torch.equal(dev.cpu().long(), torch.from_numpy(g[f"pts_{tag}{i}"]))
+            i += 1
+
+
+def test_local_max_vs_oracle_frame_and_edge_cases(api):
+    """A 1024^2 noisy lattice frame against the oracle; constant frame, plateaus, border maxima, ties."""
+    from motif_learn_b200.datasets import honeycomb_image
+    img, _ = honeycomb_image(1024, bond=12.0, seed=3, angle=5.0, jitter=0.2, noise=0.02)
+    for r, thr in ((6.0, None), (6.0, 0.25), (2.5, 0.1)):
+        np.testing.assert_array_equal(api.local_max(img, r, thr), zo.local_max(img, r, thr))
+    assert api.local_max(np.full((9, 11), 3.0, dtype=np.float32), 2.0).shape == (0, 2)
+    assert api.local_max(np.full((9, 11), 3.0, dtype=np.float32), 2.0, threshold=1.0).shape == (0, 2)
+    small = np.zeros((7, 7), dtype=np.float32)
+    small[0, 3] = 5.0
+    small[3, 3] = small[3, 4] = 2.0
+    np.testing.assert_array_equal(api.local_max(small, 1.0), [[3, 3]])
+    np.testing.assert_array_equal(api.local_max(small, 0.5), [[3, 3], [4, 3]])
+    # exact ties everywhere (noise-free lattice): our raster-order rule == the oracle's, and the result is a
+    # valid suppression (kept peaks pairwise farther than r apart)
+    clean, _ = honeycomb_image(256, bond=12.0, seed=0)
+    got = api.local_max(clean, 5.0)
+    np.testing.assert_array_equal(got, zo.local_max(clean, 5.0))
+    d = np.sqrt(((got[:, None, :] - got[None, :, :]) ** 2).sum(-1)) + np.eye(len(got)) * 1e9
+    assert d.min() > 5.0
+
+
+def test_local_max_feeds_keypoints_and_zps(api, torch):
+    """The path end to end on the device: frame -> local_max -> KeyPoints -> ZPs, against the oracle."""
+    from motif_learn_b200.datasets import honeycomb_image
+    img, _ = honeycomb_image(512, bond=12.0, seed=8, jitter=0.2, noise=0.01)
+    pts = api.local_max(img, 5.0, 0.3)
+    ref_pts = zo.local_max(img, 5.0, 0.3)
+    np.testing.assert_array_equal(pts, ref_pts)
+    kp = api.KeyPoints(pts, torch.from_numpy(img).cuda(), 32)
+    z = api.ZPs(10, 32).transform(kp.extract_patches())
+    n, m, v = zo.zernike_basis(10, 32)
+    kept = zo.clear_border(ref_pts, img.shape, 32)
+    ref = zo.project_patches(zo.extract_patches(img, kept, 32).astype(np.float64), v)
+    fp32_close(z.data.cpu().numpy(), ref)

@@ -203,3 +203,31 @@ def test_render_golden(golden):
     np.testing.assert_array_equal(img, g["img"])
     img2 = zo.render_atoms((120, 160), g["pts"], g["amps2"], float(g["sigma"]))
     np.testing.assert_array_equal(img2, g["img2"])
+
+
+# ---- peak detection ("next" row f2) ------------------------------------------------------------------
+def test_oracle_local_max_matches_reference_golden(golden):
+    """The oracle's local_max against the REAL reference filter run on the restated skimage candidates
+    (oracle/make_goldens.py:golden_peaks): same peaks in the same (brightest-first) order."""
+    g = golden("peaks.npz")
+    for tag in ("a", "b"):
+        img = g[f"img_{tag}"]
+        np.testing.assert_array_equal(zo.peak_local_max_md1(img, None), g[f"cand_{tag}"])
+        i = 0
+        while f"pts_{tag}{i}" in g.files:
+            r, thr = g[f"arg_{tag}{i}"]
+            got = zo.local_max(img, float(r), None if np.isnan(thr) else float(thr))
+            np.testing.assert_array_equal(got, g[f"pts_{tag}{i}"])
+            i += 1
+
+
+def test_oracle_peak_local_max_edge_cases():
+    assert zo.peak_local_max_md1(np.full((9, 11), 3.0, dtype=np.float32), None).shape == (0, 2)   # trivial image
+    assert zo.peak_local_max_md1(np.full((9, 11), 3.0, dtype=np.float32), 1.0).shape == (0, 2)
+    img = np.zeros((7, 7), dtype=np.float32)
+    img[0, 3] = 5.0          # on the excluded border
+    img[3, 3] = img[3, 4] = 2.0   # a two-pixel plateau: both survive (ensure_spacing rejects only d < 1)
+    got = zo.peak_local_max_md1(img, None)
+    np.testing.assert_array_equal(got, [[3, 3], [3, 4]])
+    np.testing.assert_array_equal(zo.local_max(img, 1.0), [[3, 3]])            # (x, y); the raster-first twin wins
+    np.testing.assert_array_equal(zo.local_max(img, 0.5), [[3, 3], [4, 3]])
