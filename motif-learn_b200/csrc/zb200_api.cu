@@ -4,7 +4,9 @@
 
 #include <math.h>
 #include <string.h>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace zb200 {
@@ -362,4 +364,74 @@ extern "C" int zb200_symmetry_map_f32(const zb200_plan* p, const float* d_img, i
         rc = map_simt(p, d_img, H, W, row0, rows, nullptr, d_scores, d_w, d_sel, n_folds, norm_kind, s);
     cudaFreeAsync(d_w, s);
     return rc;
+}
+
+// ---- result download: float32 in HBM -> float64 host array (what the reference returns) -----------------
+// Chunked D2H into two pinned staging buffers on a private stream, widened to float64 by a few host threads
+// while the next chunk is in flight (the destination's first-touch page faults are spread over the threads).
+namespace {
+struct Downloader {
+    std::mutex mu;
+    float* pin[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr, done[2] = {nullptr, nullptr};
+    int device = -1;
+    static constexpr int64_t kChunk = 8ll << 20;      // floats per chunk (32 MiB)
+};
+constexpr int kMaxDevices = 64;
+Downloader g_downloaders[kMaxDevices];
+
+void widen_parallel(const float* src, double* dst, int64_t n, int n_threads) {
+    if (n < (1 << 16) || n_threads <= 1) {
+        for (int64_t i = 0; i < n; ++i) dst[i] = (double)src[i];
+        return;
+    }
+    std::vector<std::thread> pool;
+    const int64_t per = (n + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        const int64_t a = t * per, b = a + per < n ? a + per : n;
+        if (a >= b) break;
+        pool.emplace_back([=]() { for (int64_t i = a; i < b; ++i) dst[i] = (double)src[i]; });
+    }
+    for (auto& th : pool) th.join();
+}
+}  // namespace
+
+extern "C" int zb200_download_as_f64(const float* d_src, int64_t n, double* h_dst, void* stream) {
+    ZB_CHECK_ARG(n >= 0, "download: negative count");
+    if (n == 0) return ZB200_OK;
+    ZB_CHECK_ARG(d_src && h_dst, "download: null pointer");
+    int dev = 0;
+    ZB_CUDA(cudaGetDevice(&dev));
+    ZB_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "download: device ordinal %d out of range", dev);
+    Downloader& g_dl = g_downloaders[dev];           // one staging set per device (each lives in that device's context)
+    std::lock_guard<std::mutex> lock(g_dl.mu);
+    if (g_dl.device != dev) {
+        for (int i = 0; i < 2; ++i) {
+            ZB_CUDA(cudaMallocHost(&g_dl.pin[i], sizeof(float) * Downloader::kChunk));
+            ZB_CUDA(cudaEventCreateWithFlags(&g_dl.done[i], cudaEventDisableTiming));
+        }
+        ZB_CUDA(cudaEventCreateWithFlags(&g_dl.ready, cudaEventDisableTiming));
+        ZB_CUDA(cudaStreamCreateWithFlags(&g_dl.stream, cudaStreamNonBlocking));
+        g_dl.device = dev;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n_threads = hw >= 16 ? 12 : (hw >= 4 ? (int)hw - 2 : 1);
+    // the producing kernels run on the caller's stream
+    ZB_CUDA(cudaEventRecord(g_dl.ready, as_stream(stream)));
+    ZB_CUDA(cudaStreamWaitEvent(g_dl.stream, g_dl.ready, 0));
+    const int64_t n_chunks = ceil_div(n, Downloader::kChunk);
+    auto count_of = [&](int64_t c) { const int64_t off = c * Downloader::kChunk; return n - off < Downloader::kChunk ? n - off : Downloader::kChunk; };
+    for (int64_t c = 0; c <= n_chunks; ++c) {
+        if (c < n_chunks) {
+            ZB_CUDA(cudaMemcpyAsync(g_dl.pin[c & 1], d_src + c * Downloader::kChunk, sizeof(float) * count_of(c),
+                                    cudaMemcpyDeviceToHost, g_dl.stream));
+            ZB_CUDA(cudaEventRecord(g_dl.done[c & 1], g_dl.stream));
+        }
+        if (c >= 1) {
+            ZB_CUDA(cudaEventSynchronize(g_dl.done[(c - 1) & 1]));
+            widen_parallel(g_dl.pin[(c - 1) & 1], h_dst + (c - 1) * Downloader::kChunk, count_of(c - 1), n_threads);
+        }
+    }
+    return ZB200_OK;
 }

@@ -33,12 +33,14 @@ from ._device import is_torch, np_ptr
 from ._zmoments import norm_code, rot_weight_tables, zmoments
 
 def _host_f64(t):
-    """float32 CUDA tensor -> float64 numpy (cast kernel on the GPU, then one D2H copy)."""
-    torch = _lib.require_cuda()
-    wide = torch.empty(t.shape, dtype=torch.float64, device=t.device)
-    _lib.check(_lib.load().zb200_cast(_lib.F32, int(t.data_ptr()), _lib.F64, int(wide.data_ptr()), t.numel(),
-                                      C.c_void_p(_lib.current_stream_ptr())), "cast")
-    return wide.cpu().numpy()
+    """float32 CUDA tensor -> float64 numpy: chunked D2H through pinned staging, widened on the host by a
+    few threads while the next chunk is in flight (zb200_download_as_f64)."""
+    _lib.require_cuda()
+    t = t.contiguous()
+    out = np.empty(tuple(t.shape), dtype=np.float64)
+    _lib.check(_lib.load().zb200_download_as_f64(int(t.data_ptr()), t.numel(), np_ptr(out),
+                                                 C.c_void_p(_lib.current_stream_ptr())), "download_as_f64")
+    return out
 
 
 _plans: dict = {}

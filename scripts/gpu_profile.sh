@@ -10,8 +10,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "launch list rc=$?"
 $CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:project_tc3 -s 3 -c 1 -f -o $OUT/prof_tc3 $CMD > $OUT/ncu_tc3.log 2>&1
 echo "tc3 rc=$?"
-$CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:map_tc_kernel -s 1 -c 1 -f -o $OUT/prof_map $CMD > $OUT/ncu_map.log 2>&1
-echo "map rc=$?"
+$CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:map_h_kernel -s 1 -c 1 -f -o $OUT/prof_maph $CMD > $OUT/ncu_maph.log 2>&1
+echo "map_h rc=$?"
 CMD2="python bench.py --steps 3 --warmup 3 --no-cpu --no-also --precision tf32"
 $CMD2 > $OUT/bench_prof_tf32.json 2>/dev/null && ncu --set full --clock-control none --import-source on -k regex:project_tc_kernel -s 3 -c 1 -f -o $OUT/prof_tc1 $CMD2 > $OUT/ncu_tc1.log 2>&1
 echo "tc1 rc=$?"
