@@ -52,14 +52,15 @@ struct MapParams {
     int n_pad, n_modes;
     int n_terms;         // 1: x1.b1 only (11-bit operands);  3: fp32-grade split
     int n_span;
-    long long n_tiles;   // rows * n_span * 2
+    long long n_tiles;   // n_pairs * n_span * 4
+    int pair0, n_pairs;  // absolute output-row pairs (2j, 2j+1) that overlap [row0, row0+rows)
     int n_groups;        // 16-tap groups per window row (G)
-    int a_first, a_end;  // window rows with at least one tap inside the disk
-    int n_kb;            // basis k-blocks (4 groups of 16 taps each) per tile
-    int n_blocks;        // row blocks per tile: G<=2 -> 4/G window rows share one k-block, else one row = ceil(G/4) k-blocks
-    int chunk_blocks;    // row blocks per accumulator chunk
+    int kb_per_row;      // basis k-blocks (4 groups) per window row = ceil(G/4)
+    int a_first, n_rows; // window rows with at least one tap inside the disk: [a_first, a_first+n_rows)
+    int chunk_steps;     // window-row steps per accumulator chunk
+    int n_chunks;
     int copy_q, n_box, bw_q;   // one staged row copy: n_box TMA boxes of bw_q 16-byte units
-    int img_slots, b_stages;
+    int img_slots, b_slots;
     int cluster;
     float* out_moments;
     float* out_scores;
@@ -67,7 +68,6 @@ struct MapParams {
     int n_folds;
     int norm_kind;
     int dbg;             // ZB200_MAP_DEBUG experiment bits (results wrong when set)
-    int park_ns;         // suspend-time hint of the off-critical-path barrier waits (0 = plain try_wait)
     // score tables live in the kernel parameters: with the column loops unrolled every weight is a
     // constant-bank operand of its FFMA (no loads in the epilogue)
     float selw[128];                  // 1 for modes that enter the norm (unselect()), else 0
@@ -184,68 +184,96 @@ __global__ void map_pack_basis_kernel(const double* __restrict__ basis, int n_mo
 }
 
 struct IssueCtx {
-    uint32_t idesc, slot_step, copy_step, b_step, bop_step, gsel, img_lo0, b_lo0, tmem_base;
+    uint32_t idesc1, idesc2;          // N = n_pad (one output row) / N = 2 n_pad (both rows of the pair)
+    uint32_t slot_step, copy_step, b_slot_step, b_ring_step, img_lo0, b_lo0, tmem_base;
     uint16_t cmask;
     long long my_tiles;
-    int n_chunks;
     uint64_t *img_full, *img_empty, *b_full, *b_empty, *acc_full, *acc_empty;
 };
 
-// The MMA schedule of one issuer thread, specialised on G = 16-tap groups per window row.
-// Row block = the window rows that share basis k-blocks: G <= 2 -> 4/G rows in one k-block, else one row in
-// ceil(G/4) k-blocks (map_pack_basis_kernel lays the operand out in exactly this order).
+// MMAs of one window-row step.  kMode: 0 = both output rows (N = 2 n_pad, B = the contiguous slot pair),
+// 1 = upper row only (first step: accumulator columns [n_pad, 2 n_pad), N = n_pad), 2 = lower row only (last step).
+// a0: descriptor word of the staged frame row (part x1; part x2 follows at +copy_step); bb: basis slot of the
+// first window row the step reads (mode 0: row a-1, row a follows at +b_slot_step); operand rings (k-block,
+// b1|b2) are b_ring_step apart.
+template <int G, bool kX3, int kMode>
+__device__ __forceinline__ void issue_step(const IssueCtx& c, uint32_t d, int n_pad, uint32_t a0, uint32_t bb,
+                                           uint32_t acc_first, bool split_first) {
+    constexpr int n_bops = kX3 ? 2 : 1;
+    const uint32_t dd = kMode == 1 ? d + (uint32_t)n_pad : d;
+    const uint32_t idesc = kMode == 0 ? c.idesc2 : c.idesc1;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const uint32_t ag = a0 + 4u * g;                                            // 16 taps = 4 units of 16 B
+        const uint32_t bg = bb + (uint32_t)((g / 4) * n_bops) * c.b_ring_step + 2u * (uint32_t)(g % 4);   // 32 B per group
+        if (g == 0) {
+            if (kMode == 0 && split_first) {
+                // first step that touches the lower row while the upper one already holds a partial sum
+                umma_f16(d, desc_toeplitz(ag), desc_from_lo(bg), c.idesc1, 0u);
+                umma_f16(d + (uint32_t)n_pad, desc_toeplitz(ag), desc_from_lo(bg + c.b_slot_step), c.idesc1, 1u);
+            } else {
+                umma_f16(dd, desc_toeplitz(ag), desc_from_lo(bg), idesc, acc_first);
+            }
+        } else {
+            umma_f16(dd, desc_toeplitz(ag), desc_from_lo(bg), idesc, 1u);
+        }
+        if (kX3) {
+            umma_f16(dd, desc_toeplitz(ag + c.copy_step), desc_from_lo(bg), idesc, 1u);
+            umma_f16(dd, desc_toeplitz(ag), desc_from_lo(bg + c.b_ring_step), idesc, 1u);
+        }
+    }
+}
+
+// The MMA schedule of the issuer thread, specialised on G = 16-tap groups per window row.  One tile = one pair
+// of output rows (y0, y0+1), 128 pixels of one phase; step s stages frame row y0 - k/2 + a_first + s, which is
+// window row a = a_first + s of output row y0 and window row a - 1 of output row y0 + 1: ONE MMA with
+// N = 2 n_pad whose B operand is the basis of window rows (a-1, a) -- adjacent slots of the basis ring -- feeds
+// both rows.  Against two N = n_pad MMAs this halves the A-side shared-memory reads (the N = 96 SS MMA is
+// shared-memory-bound: 7 KB per 48 tensor clk) and the number of instructions the issuing thread must retire.
 template <int G, bool kX3, bool kCluster2>
 __device__ __forceinline__ void issue_tiles(const MapParams& p, const IssueCtx& c) {
-    constexpr int RB = G <= 2 ? 4 / G : 1;           // window rows per row block
-    int si = 0, sb = 0;
-    uint32_t phi = 0, phb = 0;
+    const int S = p.b_slots;
+    int si = 0;
+    uint32_t phi = 0;
+    int sj = 0;                 // basis slot of the window row this step waits for
+    uint32_t pj = 0;
+    int sprev = 0;              // slot of the previous window row (released after this step)
     uint32_t ck = 0;
-    auto b_release = [&]() {
-        if (kCluster2) umma_commit_mc(&c.b_empty[sb], c.cmask);
-        else umma_commit(&c.b_empty[sb]);
-        if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+    auto release_prev = [&]() {
+        if (kCluster2) umma_commit_mc(&c.b_empty[sprev], c.cmask);
+        else umma_commit(&c.b_empty[sprev]);
     };
     for (long long t = 0; t < c.my_tiles; ++t) {
-        int blk = 0;
-        for (int ch = 0; ch < c.n_chunks; ++ch, ++ck) {
+        int s = 0;
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++ck) {
             const int buf = ck & 1;
             mbar_wait(&c.acc_empty[buf], ((ck >> 1) & 1u) ^ 1u);
             tc_fence_after();
-            const uint32_t d0 = c.tmem_base + (uint32_t)((buf * 2 + (int)c.gsel) * p.n_pad);
-            const int blk_stop = min(p.n_blocks, blk + p.chunk_blocks);
+            const uint32_t d = c.tmem_base + (uint32_t)(buf * 2 * p.n_pad);
+            const int s_stop = ch == p.n_chunks - 1 ? p.n_rows + 1 : s + p.chunk_steps;
             uint32_t acc = 0u;
-            for (; blk < blk_stop; ++blk) {
-                mbar_wait(&c.b_full[sb], phb);
+            for (; s < s_stop; ++s) {
+                mbar_wait(&c.img_full[si], phi);
+                const uint32_t a0 = c.img_lo0 + (uint32_t)si * c.slot_step;
+                if (s < p.n_rows) mbar_wait(&c.b_full[sj], pj);
                 tc_fence_after();
-                uint32_t b0 = c.b_lo0 + (uint32_t)sb * c.b_step;
-#pragma unroll
-                for (int r = 0; r < RB; ++r) {
-                    if (RB > 1 && p.a_first + blk * RB + r >= p.a_end) break;      // partial last block
-                    mbar_wait(&c.img_full[si], phi);
-                    tc_fence_after();
-                    // copies of this window row: [phase g][part]; part 1 (x2) directly after part 0 (x1)
-                    const uint32_t a0 = c.img_lo0 + (uint32_t)si * c.slot_step;
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        if (G > 4 && g == 4) {                                      // second k-block of a wide row
-                            b_release();
-                            mbar_wait(&c.b_full[sb], phb);
-                            tc_fence_after();
-                            b0 = c.b_lo0 + (uint32_t)sb * c.b_step;
-                        }
-                        const uint32_t ag = a0 + 4u * g;                            // 16 taps = 4 units of 16 B
-                        const uint32_t bg = b0 + 2u * (uint32_t)(RB > 1 ? r * G + g : g % 4);   // 16 fp16 taps = 32 B
-                        umma_f16(d0, desc_toeplitz(ag), desc_from_lo(bg), c.idesc, g == 0 ? acc : 1u);
-                        if (kX3) {
-                            umma_f16(d0, desc_toeplitz(ag + c.copy_step), desc_from_lo(bg), c.idesc, 1u);
-                            umma_f16(d0, desc_toeplitz(ag), desc_from_lo(bg + c.bop_step), c.idesc, 1u);
-                        }
-                    }
-                    acc = 1u;
-                    umma_commit(&c.img_empty[si]);
-                    if (++si == p.img_slots) { si = 0; phi ^= 1; }
+                if (s == 0) {
+                    // only output row y0 (upper accumulator half) has a window row on this frame row
+                    issue_step<G, kX3, 1>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sj * c.b_slot_step, 0u, false);
+                } else if (s == p.n_rows) {
+                    issue_step<G, kX3, 2>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sprev * c.b_slot_step, s == 1 ? 0u : acc, false);
+                } else {
+                    // slots (sprev, sprev + 1) hold window rows (a-1, a); slot S mirrors slot 0 for the wrap-around
+                    issue_step<G, kX3, 0>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sprev * c.b_slot_step, acc, s == 1);
                 }
-                b_release();
+                acc = 1u;
+                umma_commit(&c.img_empty[si]);
+                if (++si == p.img_slots) { si = 0; phi ^= 1; }
+                if (s >= 1) release_prev();
+                if (s < p.n_rows) {
+                    sprev = sj;
+                    if (++sj == S) { sj = 0; pj ^= 1; }
+                }
             }
             umma_commit(&c.acc_full[buf]);
         }
@@ -260,26 +288,27 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int n_bops = kX3 ? 2 : 1;
     const uint32_t b_bytes = (uint32_t)p.n_pad * 128;                 // one basis operand k-block (4 groups)
-    const uint32_t b_stage = (uint32_t)n_bops * b_bytes;
-    const uint32_t copy_bytes = (uint32_t)p.copy_q * 16;              // one staged row of one (phase, part)
-    const uint32_t slot_bytes = 2u * n_bops * copy_bytes;             // [phase g][part]
+    const uint32_t ring_bytes = (uint32_t)(p.b_slots + 1) * b_bytes;  // one (k-block, operand) ring incl. the mirror slot
+    const uint32_t n_rings = (uint32_t)(p.kb_per_row * n_bops);
+    const uint32_t copy_bytes = (uint32_t)p.copy_q * 16;              // one staged row of one part
+    const uint32_t slot_bytes = (uint32_t)n_bops * copy_bytes;        // [part]
     uint8_t* b_ring = smem;
-    uint8_t* img_ring = smem + (size_t)p.b_stages * b_stage;
+    uint8_t* img_ring = smem + (size_t)n_rings * ring_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(img_ring + (((size_t)p.img_slots * slot_bytes + 15) & ~(size_t)15));
     uint64_t* img_full = bars;
     uint64_t* img_empty = img_full + p.img_slots;
     uint64_t* b_full = img_empty + p.img_slots;
-    uint64_t* b_empty = b_full + p.b_stages;
-    uint64_t* acc_full = b_empty + p.b_stages;      // [2]
+    uint64_t* b_empty = b_full + p.b_slots;
+    uint64_t* acc_full = b_empty + p.b_slots;       // [2]
     uint64_t* acc_empty = acc_full + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     // Warp-role layout.  The SM's issue arbiter prefers the highest warp id of a sub-partition, so the
     // latency-critical single-thread roles take the LAST warpgroup: warps 0-7 epilogue (two warpgroups),
-    // warp 8 frame-row TMA, warp 9 basis TMA, warps 10/11 MMA issuers (11 also owns the TMEM allocation).
+    // warp 8 frame-row TMA, warp 9 basis TMA, warp 10 MMA issuer, warp 11 TMEM allocation.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wg = warp >> 2;
-    constexpr int kWarpFrame = 8, kWarpBasis = 9, kWarpMma1 = 11;
+    constexpr int kWarpFrame = 8, kWarpBasis = 9, kWarpMma = 10, kWarpAlloc = 11;
 
     if (warp == kWarpFrame && lane == 0) {
         prefetch_tmap(&map_img);
@@ -289,19 +318,19 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
     if (warp == kWarpBasis && lane == 0) {
         for (int s = 0; s < p.img_slots; ++s) {
             mbar_init(&img_full[s], 1);
-            mbar_init(&img_empty[s], 2);                 // two issuer warps
+            mbar_init(&img_empty[s], 1);
         }
-        for (int s = 0; s < p.b_stages; ++s) {
+        for (int s = 0; s < p.b_slots; ++s) {
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 2 * p.cluster);
+            mbar_init(&b_empty[s], p.cluster);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 2);
+            mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], 8);
         }
         fence_barrier_init();
     }
-    if (warp == kWarpMma1) {
+    if (warp == kWarpAlloc) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -315,13 +344,13 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
     const uint32_t crank = p.cluster > 1 ? cluster_rank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
     const long long my_tiles = (p.n_tiles + gridDim.x - 1) / gridDim.x;      // lock-step within the cluster
-    const int n_chunks = (p.n_blocks + p.chunk_blocks - 1) / p.chunk_blocks;
 
-    auto decode = [&](long long tile, int& yl, int& span, int& pp) {
-        pp = (int)(tile & 1);
-        const long long rest = tile >> 1;
+    // tile -> (output row pair, 512-pixel span, pixel phase r)
+    auto decode = [&](long long tile, int& y0, int& span, int& r) {
+        r = (int)(tile & 3);
+        const long long rest = tile >> 2;
         span = (int)(rest % p.n_span);
-        yl = (int)(rest / p.n_span);
+        y0 = 2 * (p.pair0 + (int)(rest / p.n_span));
     };
 
     if (wg == 2) {
@@ -333,13 +362,12 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
                 uint32_t ph = 0;
                 for (long long t = 0; t < my_tiles; ++t) {
                     const long long tile = blockIdx.x + t * gridDim.x;
-                    int yl, span, pp;
-                    decode(tile, yl, span, pp);
+                    int y0, span, r;
+                    decode(tile, y0, span, r);
                     const bool live = tile < p.n_tiles;
-                    const int y = p.row0 + yl;
                     const int c0 = span * kSpan - p.half + p.pad;            // = 4 q0 (4-byte words of a plane row)
-                    for (int a = p.a_first; a < p.a_end; ++a) {
-                        mbar_wait_parked(&img_empty[s], ph ^ 1, p.park_ns);
+                    for (int st = 0; st <= p.n_rows; ++st) {
+                        mbar_wait(&img_empty[s], ph ^ 1);
                         if (p.dbg & 1) {
                             mbar_arrive(&img_full[s]);
                             if (++s == p.img_slots) { s = 0; ph ^= 1; }
@@ -348,12 +376,11 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
                         mbar_arrive_expect_tx(&img_full[s], slot_bytes);
                         uint8_t* slot = img_ring + (size_t)s * slot_bytes;
                         // dead tiles (past the end, cluster padding) read far outside the frame: all zeros
-                        const int yy = live ? y - p.half + a : -4 * p.k;
-                        for (int g = 0; g < 2; ++g)
-                            for (int pt = 0; pt < n_bops; ++pt)
-                                for (int bx = 0; bx < p.n_box; ++bx)
-                                    tma_load_3d(slot + (size_t)(g * n_bops + pt) * copy_bytes + (size_t)bx * p.bw_q * 16, &map_img,
-                                                &img_full[s], c0 + bx * p.bw_q * 4, yy, pt * 4 + 2 * pp + g, kEvictLast);
+                        const int yy = live ? y0 - p.half + p.a_first + st : -4 * p.k - 8;
+                        for (int pt = 0; pt < n_bops; ++pt)
+                            for (int bx = 0; bx < p.n_box; ++bx)
+                                tma_load_3d(slot + (size_t)pt * copy_bytes + (size_t)bx * p.bw_q * 16, &map_img, &img_full[s],
+                                            c0 + bx * p.bw_q * 4, yy, pt * 4 + r, kEvictLast);
                         if (++s == p.img_slots) { s = 0; ph ^= 1; }
                     }
                 }
@@ -361,50 +388,54 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
             __syncwarp();
         } else if (warp == kWarpBasis) {
             // ===================== basis producer =====================
+            // window row i of the tile -> slot (running row counter mod S); a row that lands in slot 0 is also
+            // written to the mirror slot S, so that the slot pair (S-1, S) is contiguous like every other pair
             if (elect_one()) {
                 const int b_rows = p.n_pad / p.cluster;
+                const size_t off = (size_t)crank * b_rows * 128;
                 int s = 0;
                 uint32_t ph = 0;
                 for (long long t = 0; t < my_tiles; ++t) {
-                    for (int kb = 0; kb < p.n_kb; ++kb) {
-                        mbar_wait_parked(&b_empty[s], ph ^ 1, p.park_ns);
+                    for (int i = 0; i < p.n_rows; ++i) {
+                        mbar_wait(&b_empty[s], ph ^ 1);
                         if (p.dbg & 16) {
                             mbar_arrive(&b_full[s]);
-                            if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                            if (++s == p.b_slots) { s = 0; ph ^= 1; }
                             continue;
                         }
-                        mbar_arrive_expect_tx(&b_full[s], b_stage);
-                        uint8_t* st = b_ring + (size_t)s * b_stage;
-                        if (p.cluster == 1) {
-                            tma_load_2d(st, &map_b1, &b_full[s], kb * kBlockK, 0, kEvictLast);
-                            if (n_bops == 2) tma_load_2d(st + b_bytes, &map_b2, &b_full[s], kb * kBlockK, 0, kEvictLast);
-                        } else {
-                            const size_t off = (size_t)crank * b_rows * 128;
-                            tma_load_2d_mc(st + off, &map_b1, &b_full[s], kb * kBlockK, (int)crank * b_rows, cmask, kEvictLast);
-                            if (n_bops == 2)
-                                tma_load_2d_mc(st + b_bytes + off, &map_b2, &b_full[s], kb * kBlockK, (int)crank * b_rows, cmask,
-                                               kEvictLast);
+                        const int copies = s == 0 ? 2 : 1;
+                        mbar_arrive_expect_tx(&b_full[s], (uint32_t)copies * n_rings * b_bytes);
+                        for (int cp = 0; cp < copies; ++cp) {
+                            const int slot = cp == 0 ? s : p.b_slots;
+                            for (int kb = 0; kb < p.kb_per_row; ++kb) {
+                                const int kcol = (i * p.kb_per_row + kb) * kBlockK;
+                                for (int op = 0; op < n_bops; ++op) {
+                                    uint8_t* dst = b_ring + (size_t)(kb * n_bops + op) * ring_bytes + (size_t)slot * b_bytes;
+                                    const CUtensorMap* mp = op == 0 ? &map_b1 : &map_b2;
+                                    if (p.cluster == 1) tma_load_2d(dst, mp, &b_full[s], kcol, 0, kEvictLast);
+                                    else tma_load_2d_mc(dst + off, mp, &b_full[s], kcol, (int)crank * b_rows, cmask, kEvictLast);
+                                }
+                            }
                         }
-                        if (++s == p.b_stages) { s = 0; ph ^= 1; }
+                        if (++s == p.b_slots) { s = 0; ph ^= 1; }
                     }
                 }
             }
             __syncwarp();
-        } else {
-            // ===================== MMA issuers: warp 10 -> accumulator 0, warp 11 -> accumulator 1 =====================
-            // MMAs of different threads are not ordered against each other, so one accumulator always belongs to
-            // one issuing thread.  The loop body is specialised on G (16-tap groups per window row) and fully
-            // unrolled per row block: at N = 96 an MMA lasts ~50 clk, and a loop with per-group branches, bit scans
-            // and register->uniform moves (~60 SASS instructions per group, ncu) is issue-bound at twice that.
+        } else if (warp == kWarpMma) {
+            // ===================== MMA issuer =====================
+            // One elected thread; the loop body is specialised on G and fully unrolled per window-row step: at
+            // N = 96..192 an MMA lasts 50-100 clk, and a loop with per-group branches, bit scans and
+            // register->uniform moves (~60 SASS instructions per group, ncu) is issue-bound.
             if (elect_one()) {
                 IssueCtx ctx;
-                ctx.idesc = make_idesc_f16(p.n_pad);
+                ctx.idesc1 = make_idesc_f16(p.n_pad);
+                ctx.idesc2 = make_idesc_f16(2 * p.n_pad);
                 ctx.slot_step = slot_bytes >> 4; ctx.copy_step = copy_bytes >> 4;
-                ctx.b_step = b_stage >> 4; ctx.bop_step = b_bytes >> 4;
-                ctx.gsel = warp == kWarpMma1 ? 1u : 0u;
-                ctx.img_lo0 = desc_lo_toeplitz(smem_u32(img_ring)) + ctx.gsel * (uint32_t)n_bops * ctx.copy_step;
+                ctx.b_slot_step = b_bytes >> 4; ctx.b_ring_step = ring_bytes >> 4;
+                ctx.img_lo0 = desc_lo_toeplitz(smem_u32(img_ring));
                 ctx.b_lo0 = desc_lo_sw128(smem_u32(b_ring));
-                ctx.tmem_base = tmem_base; ctx.cmask = cmask; ctx.my_tiles = my_tiles; ctx.n_chunks = n_chunks;
+                ctx.tmem_base = tmem_base; ctx.cmask = cmask; ctx.my_tiles = my_tiles;
                 ctx.img_full = img_full; ctx.img_empty = img_empty; ctx.b_full = b_full; ctx.b_empty = b_empty;
                 ctx.acc_full = acc_full; ctx.acc_empty = acc_empty;
                 switch (p.n_groups) {
@@ -421,7 +452,7 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
             __syncwarp();
         }
     } else {
-        // ===================== epilogue: warpgroup 0 -> phase 2pp, warpgroup 1 -> phase 2pp+1 =====================
+        // ===== epilogue: warpgroup 0 -> accumulator columns [0, n_pad) = output row y0+1, warpgroup 1 -> [n_pad, 2 n_pad) = row y0
         reg_inc<kRegsEpi>();
         const int g = wg;
         const int q = warp & 3;
@@ -430,16 +461,16 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
         uint32_t ck = 0;
         for (long long t = 0; t < my_tiles; ++t) {
             const long long tile = blockIdx.x + t * gridDim.x;
-            int yl, span, pp;
-            decode(tile, yl, span, pp);
+            int y0, span, r;
+            decode(tile, y0, span, r);
             float sum[kMaxColChunks][16];
 #pragma unroll
             for (int cc = 0; cc < kMaxColChunks; ++cc)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) sum[cc][i] = 0.f;
-            for (int c = 0; c < n_chunks; ++c, ++ck) {
+            for (int c = 0; c < p.n_chunks; ++c, ++ck) {
                 const int buf = ck & 1;
-                mbar_wait_parked(&acc_full[buf], (ck >> 1) & 1u, p.park_ns);
+                mbar_wait(&acc_full[buf], (ck >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + g) * p.n_pad);
 #pragma unroll
@@ -456,10 +487,12 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }
-            const int x = span * kSpan + 4 * (q * 32 + lane) + 2 * pp + g;
+            const int x = span * kSpan + 4 * (q * 32 + lane) + r;
+            const int yl = y0 + (g == 0 ? 1 : 0) - p.row0;                 // local output row of this warpgroup's half
+            const bool live = tile < p.n_tiles && x < p.W && yl >= 0 && yl < p.rows;
             if (p.dbg & 4) {
-                if (tile < p.n_tiles && x < p.W) p.out_scores[(size_t)yl * p.W + x] = sum[0][0] + sum[5][15];
-            } else if (tile < p.n_tiles && x < p.W) {
+                if (live) p.out_scores[(size_t)yl * p.W + x] = sum[0][0] + sum[5][15];
+            } else if (live) {
                 if (kScores) {
                     // pass 1: norms over the selected modes; the sums are squared in place
                     float s1 = 0.f, s2 = 0.f, sm = 0.f;
@@ -519,7 +552,7 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();
-    if (warp == kWarpMma1) {
+    if (warp == kWarpAlloc) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
@@ -591,19 +624,14 @@ int init_map_half_operand(zb200_plan* p) {
     if (mh.a_first < 0) { mh.a_first = 0; mh.a_end = 1; mh.act[0] = 1; }
     // rows between the first and the last active one are active (the disk is convex); every group of those
     // rows is issued (skipping single groups saves 3-7 % of the MMAs and costs a branchy issue loop).
-    // Operand order = issue order: row blocks of RB rows in KB k-blocks of 4 groups (see issue_tiles).
-    const int RB = G <= 2 ? 4 / G : 1, KB = (G + 3) / 4;
+    // Operand order = issue order: window row i -> KB = ceil(G/4) k-blocks of 4 groups (see issue_tiles).
+    const int KB = (G + 3) / 4;
     const int n_rows = mh.a_end - mh.a_first;
-    mh.n_blocks = (n_rows + RB - 1) / RB;
-    mh.n_kb = mh.n_blocks * (G <= 2 ? 1 : KB);
+    mh.n_blocks = n_rows;
+    mh.n_kb = n_rows * KB;
     groups.assign((size_t)mh.n_kb * 4, (unsigned short)0xFFFFu);
-    for (int i = 0; i < n_rows; ++i) {
-        const int a = mh.a_first + i, blk = i / RB, r = i % RB;
-        for (int g = 0; g < G; ++g) {
-            const int pos = G <= 2 ? blk * 4 + r * G + g : (blk * KB + g / 4) * 4 + g % 4;
-            groups[pos] = (unsigned short)((a << 8) | g);
-        }
-    }
+    for (int i = 0; i < n_rows; ++i)
+        for (int g = 0; g < G; ++g) groups[(size_t)(i * KB + g / 4) * 4 + g % 4] = (unsigned short)(((mh.a_first + i) << 8) | g);
     mh.n_act = (int)groups.size();
     const int rows_pad = p->real.rows_pad;
     const size_t halves = (size_t)rows_pad * mh.n_kb * 64;
@@ -678,21 +706,22 @@ int map_h(const zb200_plan* p, const float* d_img, int H, int W, int row0, int r
     prm.n_pad = p->real.rows_pad; prm.n_modes = p->n_modes;
     prm.n_terms = x3 ? 3 : 1;
     prm.n_span = (int)ceil_div(W, kSpan);
-    prm.n_tiles = (long long)rows * prm.n_span * 2;
+    // output rows are paired by ABSOLUTE parity (2j, 2j+1), so a row's arithmetic does not depend on the band
+    prm.pair0 = row0 >> 1;
+    prm.n_pairs = ((row0 + rows - 1) >> 1) - prm.pair0 + 1;
+    prm.n_tiles = (long long)prm.n_pairs * prm.n_span * 4;
     prm.n_groups = mh.n_groups;
-    prm.a_first = mh.a_first; prm.a_end = mh.a_end;
-    prm.n_kb = mh.n_kb;
-    prm.n_blocks = mh.n_blocks;
+    prm.kb_per_row = (mh.n_groups + 3) / 4;
+    prm.a_first = mh.a_first; prm.n_rows = mh.a_end - mh.a_first;
     const int nq = 128 + 4 * mh.n_groups - 2;                     // 16-byte units one staged row spans
     prm.n_box = (int)ceil_div(nq, 64);
     prm.bw_q = round_up((int)ceil_div(nq, prm.n_box), 8);          // TMA destinations stay 128-B aligned
     prm.copy_q = prm.n_box * prm.bw_q;
-    {
-        // drain after ~16 groups (48 accumulating MMAs): the tensor core accumulates with round-toward-zero
-        const int rb = mh.n_groups <= 2 ? 4 / mh.n_groups : 1;
-        const int chunk_rows = 16 / mh.n_groups > 0 ? 16 / mh.n_groups : 1;
-        prm.chunk_blocks = chunk_rows / rb > 0 ? chunk_rows / rb : 1;
-    }
+    // drain after ~12 groups per output row (36 accumulating MMAs): the tensor core accumulates with
+    // round-toward-zero.  At least 2 steps (step 1 completes the first chunk's lower row), and the last chunk
+    // absorbs the remainder so that the final single-row step never stands alone.
+    prm.chunk_steps = 12 / mh.n_groups > 2 ? 12 / mh.n_groups : 2;
+    prm.n_chunks = prm.n_rows / prm.chunk_steps > 1 ? prm.n_rows / prm.chunk_steps : 1;
     prm.out_moments = d_moments; prm.out_scores = d_scores;
     prm.n_folds = n_folds; prm.norm_kind = norm_kind;
     if (d_scores) {
@@ -701,8 +730,6 @@ int map_h(const zb200_plan* p, const float* d_img, int H, int W, int row0, int r
             for (int c = 0; c < p->n_modes; ++c) prm.wts[f][c] = h_sel[c] ? h_w[(size_t)f * p->n_modes + c] : 0.f;
     }
     if (const char* e = getenv("ZB200_MAP_DEBUG")) prm.dbg = atoi(e);
-    prm.park_ns = 0;
-    if (const char* e = getenv("ZB200_MAP_PARK")) prm.park_ns = atoi(e);
 
     // operand planes of the frame: (x1 | x2) x 4 pixel phases, overlapped 16-byte units
     const int n_parts = x3 ? 2 : 1;
@@ -753,14 +780,18 @@ int map_h(const zb200_plan* p, const float* d_img, int H, int W, int row0, int r
     prm.cluster = cluster;
     const int lg = cluster == 2 ? 1 : 0;
 
-    const int b_stage = (x3 ? 2 : 1) * prm.n_pad * 128;
-    const int slot_bytes = 2 * n_parts * prm.copy_q * 16;
-    prm.b_stages = 4;
+    const int n_rings = prm.kb_per_row * (x3 ? 2 : 1);
+    const int slot_bytes = n_parts * prm.copy_q * 16;
     prm.img_slots = 8;
-    if (const char* e = getenv("ZB200_MAP_BSTAGES")) prm.b_stages = atoi(e) > 0 ? atoi(e) : 4;
+    prm.b_slots = prm.kb_per_row == 1 ? 4 : 2;
+    if (const char* e = getenv("ZB200_MAP_BSTAGES")) prm.b_slots = atoi(e) > 1 ? atoi(e) : prm.b_slots;
     if (const char* e = getenv("ZB200_MAP_SLOTS")) prm.img_slots = atoi(e) > 0 ? atoi(e) : 8;
-    const size_t smem = 1024 + (size_t)prm.b_stages * b_stage + (((size_t)prm.img_slots * slot_bytes + 15) & ~(size_t)15) +
-                        8 * (2 * prm.img_slots + 2 * prm.b_stages + 4) + 16;
+    auto smem_need = [&]() {
+        return 1024 + (size_t)n_rings * (prm.b_slots + 1) * prm.n_pad * 128 + (((size_t)prm.img_slots * slot_bytes + 15) & ~(size_t)15) +
+               8 * (2 * prm.img_slots + 2 * prm.b_slots + 4) + 16;
+    };
+    while (smem_need() > (size_t)kSmemLimit && prm.b_slots > 2) --prm.b_slots;
+    const size_t smem = smem_need();
     if (smem > (size_t)kSmemLimit) {
         cudaFreeAsync(scratch, s);
         set_error("fp16-split dense map: window %d needs %zu B of shared memory", prm.k, smem);
