@@ -301,6 +301,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 //   warpgroup 1,2  epilogue: running fp32 sums of up to 128 accumulator columns per thread
 //   warpgroup 3  splitter: Xlo = x - trunc_tf32(x) for its 128 rows, tcgen05.st into TMEM
 // ================================================================================================
+#ifndef ZB200_TC3_PROF
+#define ZB200_TC3_PROF 0
+#endif
 constexpr int kRegsCtl = 48, kRegsEpi = 176, kRegsSplit = 112;     // (48 + 2*176 + 112) * 128 = 64 Ki
 constexpr int kMaxColChunks = 8;     // 8 x 16 = 128 running sums per epilogue thread
 
@@ -336,7 +339,9 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wg = warp >> 2;
     constexpr int kWarpTma = 12, kWarpMma = 13, kWarpAlloc = 14, kWarpBasis = 15;
-    const bool prof = (p.dbg & 16) != 0;
+    // experiment hooks (blocked-cycle counters, ablation bits) are compiled out unless -DZB200_TC3_PROF=1:
+    // every extra branch or clock read in the single-thread issue loop costs issue slots (profiles/r01_maph_issue_study.md)
+    const bool prof = ZB200_TC3_PROF && (p.dbg & 16) != 0;
     unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;      // per-thread blocked-cycle counters (experiments)
 
     if (warp == kWarpTma && lane == 0) {
@@ -468,14 +473,14 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
                             for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
                                 umma_tf32(d0, desc_from_lo(xl + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc, k4 ? 1u : acc0);
-                                if (!(p.dbg & 1)) umma_bf16_ts(d0, a0 + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
+                                if (!(ZB200_TC3_PROF && (p.dbg & 1))) umma_bf16_ts(d0, a0 + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
                             }
                             if (p.subtiles == 2) {
 #pragma unroll
                                 for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
                                     umma_tf32(d0 + p.n_pad, desc_from_lo(xl + 1024 + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc,
                                               k4 ? 1u : acc0);
-                                    if (!(p.dbg & 1))
+                                    if (!(ZB200_TC3_PROF && (p.dbg & 1)))
                                         umma_bf16_ts(d0 + p.n_pad, a0 + kBlockK + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
                                 }
                             }
@@ -586,13 +591,13 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 }
                 mbar_wait_t(&lo_empty[lb], lo_ph ^ 1u, w1, prof);
                 tc_fence_after();
-                if (!(p.dbg & 2)) {
+                if (!(ZB200_TC3_PROF && (p.dbg & 2))) {
                     uint32_t lo[32];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) split8(x0[2 * c], x0[2 * c + 1], lo + 8 * c);
                     tmem_st32(lo_base + lane_addr + (uint32_t)(lb * p.subtiles + 0) * kBlockK, lo);
                 }
-                if (p.subtiles == 2 && !(p.dbg & 2)) {
+                if (p.subtiles == 2 && !(ZB200_TC3_PROF && (p.dbg & 2))) {
                     uint32_t lo[32];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) split8(x1[2 * c], x1[2 * c + 1], lo + 8 * c);
