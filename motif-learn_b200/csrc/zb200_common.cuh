@@ -135,6 +135,9 @@ struct GatherSource {
     const float* img;
     int H, W;
     const int2* xy0;      // top-left corner (x0, y0) of each window
+    // optional 16-byte gather source: 4 shifted zero-padded copies, plane r [y][u] = img0[y][u - L + r], pitch Wp
+    const float* planes = nullptr;
+    int Wp = 0, L = 0;
 };
 int project_tc(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind,
                void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,

@@ -53,6 +53,20 @@ __global__ void corners_kernel(const double* __restrict__ pts, long long n, int 
     xy0[i] = make_int2((int)rint(pts[2 * i]) - k / 2, (int)rint(pts[2 * i + 1]) - k / 2);
 }
 
+// shifted, zero-padded copies of the frame for the 16-byte gathers of the fused path:
+//   plane r [y][u] = img0[y][u - L + r]   (img0 = frame, zero outside), u in [0, Wp), Wp % 4 == 0
+__global__ void shift_planes_kernel(const float* __restrict__ img, int H, int W, int Wp, int L, float* __restrict__ planes) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)H * Wp;
+    if (i >= n) return;
+    const int y = (int)(i / Wp), u = (int)(i - (long long)y * Wp);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int x = u - L + r;
+        planes[(long long)r * n + i] = (x >= 0 && x < W) ? __ldg(img + (long long)y * W + x) : 0.f;
+    }
+}
+
 }  // namespace zb200
 
 extern "C" int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_img, int H, int W, const double* d_pts_xy,
@@ -70,7 +84,24 @@ extern "C" int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_im
     corners_kernel<<<(unsigned)ceil_div(n_pts, 256), 256, 0, s>>>(d_pts_xy, (long long)n_pts, plan->size, xy0);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     GatherSource src{d_img, H, W, xy0};
+    float* planes = nullptr;
+    if (plan->size % 4 == 0 && !getenv("ZB200_GATHER_4B")) {
+        // windows start at arbitrary columns; four copies shifted by 0..3 pixels make every window row 16-byte aligned
+        const int L = plan->size, Wp = round_up(W + 2 * L, 4);
+        if (cudaMallocAsync(&planes, sizeof(float) * 4 * (size_t)H * Wp, s) == cudaSuccess) {
+            const long long n = (long long)H * Wp;
+            shift_planes_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(d_img, H, W, Wp, L, planes);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            src.planes = planes;
+            src.Wp = Wp;
+            src.L = L;
+        } else {
+            cudaGetLastError();
+            planes = nullptr;                               // no memory for the planes: 4-byte gathers
+        }
+    }
     int rc = project_tc(plan, nullptr, n_pts, precision, out_kind, d_out, d_out2, nullptr, nullptr, 0, 0, s, &src);
+    if (planes) cudaFreeAsync(planes, s);
     cudaFreeAsync(xy0, s);
     return rc;
 }

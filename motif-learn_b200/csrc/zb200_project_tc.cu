@@ -74,6 +74,8 @@ struct Params {
     int cluster;          // CTAs per cluster sharing the B operand through TMA multicast (1, 2 or 4)
     int gather;           // 1: X tiles are gathered from a frame at peak windows instead of TMA-loaded (tf32x3)
     const float* g_img;   // frame [g_H][g_W]
+    const float* g_planes;  // optional: 4 shifted, zero-padded copies [4][g_H][g_Wp], plane r [y][u] = img0[y][u - g_L + r]
+    int g_Wp, g_L;          //   (16-byte gathers: a window row starting at column X is 16-B aligned in plane (X + g_L) % 4)
     int g_H, g_W, g_k;
     const int2* g_xy;     // top-left corner (x0, y0) of every patch window
     int dbg;              // ZB200_TC_DEBUG bitmask: experiments only (results are wrong when set)
@@ -540,21 +542,44 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             auto gather_issue = [&](int kbi, int sg, uint32_t phg) {
                 mbar_wait(&empty[sg], phg ^ 1u);                   // the stage's previous MMAs have retired
                 const int e0 = kbi * kBlockK;
-                int wr = e0 / p.g_k, wc = e0 - wr * p.g_k + lane;   // window row / column of this lane
-                if (wc >= p.g_k) { wc -= p.g_k; ++wr; }
                 const uint32_t xs = smem_u32(stage_x(sg)) + (uint32_t)(q * g_rows) * 128u;
-                for (int j = 0; j < g_rows; ++j) {
-                    const int2 src = (j & 32) ? cb : ca;
-                    const int x0 = __shfl_sync(0xffffffffu, src.x, j & 31);
-                    const int y0 = __shfl_sync(0xffffffffu, src.y, j & 31);
-                    const int yy = y0 + wr, xx = x0 + wc;
-                    const bool inb = yy >= 0 && yy < p.g_H && xx >= 0 && xx < p.g_W;
-                    const float* gp = p.g_img + (inb ? (size_t)yy * p.g_W + xx : 0);
-                    const int row = q * g_rows + j;                 // tile row (swizzle phase = row % 8)
-                    const uint32_t dst = xs + (uint32_t)j * 128u + ((((uint32_t)lane >> 2) ^ (uint32_t)(row & 7)) << 4) +
-                                         ((uint32_t)lane & 3u) * 4u;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(gp), "r"(inb ? 4 : 0)
-                                 : "memory");                       // src-size 0 -> zero fill outside the frame
+                if (p.g_planes) {
+                    // 16-byte copies from the shifted planes: 8 lanes move one 32-float segment, a warp instruction
+                    // moves the segments of 4 tile rows (4x fewer LSU operations than the 4-byte path)
+                    const int c = lane & 7;                          // 16-B chunk of the segment = 4 taps
+                    const int e = e0 + 4 * c;
+                    const int wr = e / p.g_k, wc = e - wr * p.g_k;   // g_k % 4 == 0: a chunk never straddles window rows
+                    for (int j0 = 0; j0 < g_rows; j0 += 4) {
+                        const int j = j0 + (lane >> 3);
+                        const int2 src = (j0 & 32) ? cb : ca;
+                        const int x0 = __shfl_sync(0xffffffffu, src.x, j & 31);
+                        const int y0 = __shfl_sync(0xffffffffu, src.y, j & 31);
+                        const int yy = y0 + wr;
+                        const int xl = x0 + wc + p.g_L;              // column in the padded frame
+                        const int rr = xl & 3, u = xl - rr;
+                        const bool inb = yy >= 0 && yy < p.g_H && xl >= 0 && u + 4 <= p.g_Wp;
+                        const float* gp = p.g_planes + (inb ? ((size_t)rr * p.g_H + yy) * p.g_Wp + u : 0);
+                        const int row = q * g_rows + j;              // tile row (swizzle phase = row % 8)
+                        const uint32_t dst = xs + (uint32_t)j * 128u + (((uint32_t)c ^ (uint32_t)(row & 7)) << 4);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(inb ? 16 : 0)
+                                     : "memory");                    // src-size 0 -> zero fill outside the frame
+                    }
+                } else {
+                    int wr = e0 / p.g_k, wc = e0 - wr * p.g_k + lane;   // window row / column of this lane
+                    if (wc >= p.g_k) { wc -= p.g_k; ++wr; }
+                    for (int j = 0; j < g_rows; ++j) {
+                        const int2 src = (j & 32) ? cb : ca;
+                        const int x0 = __shfl_sync(0xffffffffu, src.x, j & 31);
+                        const int y0 = __shfl_sync(0xffffffffu, src.y, j & 31);
+                        const int yy = y0 + wr, xx = x0 + wc;
+                        const bool inb = yy >= 0 && yy < p.g_H && xx >= 0 && xx < p.g_W;
+                        const float* gp = p.g_img + (inb ? (size_t)yy * p.g_W + xx : 0);
+                        const int row = q * g_rows + j;                 // tile row (swizzle phase = row % 8)
+                        const uint32_t dst = xs + (uint32_t)j * 128u + ((((uint32_t)lane >> 2) ^ (uint32_t)(row & 7)) << 4) +
+                                             ((uint32_t)lane & 3u) * 4u;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(gp), "r"(inb ? 4 : 0)
+                                     : "memory");                       // src-size 0 -> zero fill outside the frame
+                    }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
@@ -566,8 +591,10 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 } else {
                     // K2 fused: the four warps copy 32-float window segments (one per tile row, coalesced
                     // 128-B reads of the L2-resident frame) into the 128-B-swizzled K-major X stage with
-                    // 4-byte cp.async (no register staging, every copy of a k-block in flight at once),
-                    // one k-block ahead of the split so the L2 latency hides behind it.
+                    // cp.async (16-byte copies from the shifted planes, else 4-byte; no register staging, every
+                    // copy of a k-block in flight at once), one k-block ahead of the split so the L2 latency
+                    // hides behind it (two ahead measured no faster: the splitter warps' instruction stream,
+                    // not the latency, bounds this path).
                     if (kb == 0) gather_issue(0, s, ph);
                     if (kb + 1 < p.k_blocks) {
                         const int sn = (s + 1 == p.n_stages) ? 0 : s + 1;
@@ -802,6 +829,9 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     if (gsrc) {
         prm.gather = 1;
         prm.g_img = gsrc->img;
+        prm.g_planes = gsrc->planes;
+        prm.g_Wp = gsrc->Wp;
+        prm.g_L = gsrc->L;
         prm.g_H = gsrc->H;
         prm.g_W = gsrc->W;
         prm.g_k = p->size;
