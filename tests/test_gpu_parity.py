@@ -563,3 +563,29 @@ def test_local_max_feeds_keypoints_and_zps(api, torch):
     kept = zo.clear_border(ref_pts, img.shape, 32)
     ref = zo.project_patches(zo.extract_patches(img, kept, 32).astype(np.float64), v)
     fp32_close(z.data.cpu().numpy(), ref)
+
+
+def test_config4_full_size_map_property(api, torch):
+    """BASELINE config 4 at FULL size (4096x4096 frame with defects, 64-px window, n_max=12): the fused
+    symmetry map at sampled pixels (incl. span seams at multiples of 512, row-pair seams, frame borders)
+    equals rot_maps of the oracle projection of the window gathered at that pixel; four row bands (the 4-GPU
+    sharding, odd band starts included) reproduce the single-call result bit for bit."""
+    from motif_learn_b200.datasets import honeycomb_image
+    S = 4096
+    img, _ = honeycomb_image(S, bond=12.0, seed=2, vacancy_frac=0.01, dopant_frac=0.005)
+    dimg = torch.from_numpy(img).cuda()
+    z = api.ZPs(12, 64)
+    full = z.symmetry_map(dimg, [2, 3, 4, 6])
+    assert full.shape == (4, S, S)
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.integers(34, S - 34, 300), [511, 512, 513, 2047, 2048, 4000, 40, 4055]])
+    ys = np.concatenate([rng.integers(34, S - 34, 300), [1000, 1001, 2047, 2048, 2049, 33, 4060, 4061]])
+    pts = np.stack([xs, ys], axis=1).astype(np.float64)
+    n, m, v = zo.zernike_basis(12, 64)
+    zref = zo.project_patches(zo.extract_patches(img, pts, 64).astype(np.float64), v)
+    want = zo.rot_maps(zref, n, m, [2, 3, 4, 6])
+    got = full[:, torch.from_numpy(ys).cuda(), torch.from_numpy(xs).cuda()].cpu().numpy().T
+    assert np.abs(got - want).max() < 1e-5
+    bands = [(0, 1023), (1023, 1026), (2049, 999), (3048, 1048)]
+    parts = [z.symmetry_map(dimg, [2, 3, 4, 6], row0=r0, rows=r) for r0, r in bands]
+    assert torch.equal(torch.cat(parts, dim=1), full)
