@@ -82,7 +82,9 @@ struct MapHalf {
     int a_first = 0, a_end = 0;  // window rows with taps inside the disk
     int n_act = 0;               // group positions of the packed operand (incl. zero padding)
     int n_kb = 0;                // 128-byte k-blocks (4 groups) per operand row
-    int n_blocks = 0;            // row blocks per tile (rows that share basis k-blocks)
+    int n_blocks = 0;            // window rows per tile
+    int mode0 = 0, n_modes = 0;  // the modes [mode0, mode0 + n_modes) this operand holds (a plan with more than 128
+    int rows_pad = 0;            //   padded modes is served by several operands = several passes over the frame)
     int max_cluster = 1;
     unsigned short act[kMapHalfMaxWindow] = {};
     void* b1 = nullptr;          // half [rows_pad][n_kb*64]
@@ -111,7 +113,8 @@ struct zb200_plan {
     int32_t h_m[1024];
     zb200::Operand real;          // real row order
     zb200::Operand cplx;          // complex-interleaved row order
-    zb200::MapHalf map_half;      // fp16-split dense-map operand (real row order)
+    zb200::MapHalf map_half[4];   // fp16-split dense-map operands (real row order), <= 128 padded modes each
+    int n_map_parts = 0;
     void* pin_in[2] = {nullptr, nullptr};   // pinned staging for the host entry point
     void* pin_out[2] = {nullptr, nullptr};
     void* dev_in[2] = {nullptr, nullptr};

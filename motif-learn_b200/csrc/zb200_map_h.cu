@@ -164,7 +164,7 @@ __global__ void map_prepare_kernel(const float* __restrict__ img, int H, int W, 
 // ---- plan-time: packed fp16 basis operands, active 16-tap groups only ---------------------------------
 //   b1[r][gi*16 + t] = RN_f16(V[r][a][16 g + t]),  b2 = RN_f16(V - b1);  (a, g) = groups[gi];  zero for taps
 //   beyond the window row, padding rows and padding groups.  Row pitch = n_kb * 64 halves (128 B per k-block).
-__global__ void map_pack_basis_kernel(const double* __restrict__ basis, int n_modes, int rows_pad, int k,
+__global__ void map_pack_basis_kernel(const double* __restrict__ basis, int mode0, int n_modes, int rows_pad, int k,
                                       const unsigned short* __restrict__ groups, int n_act, int n_kb,
                                       __half* __restrict__ b1, __half* __restrict__ b2) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;       // gi * 16 + t
@@ -175,7 +175,7 @@ __global__ void map_pack_basis_kernel(const double* __restrict__ basis, int n_mo
     if (r < n_modes && gi < n_act && groups[gi] != 0xFFFFu) {
         const int a = groups[gi] >> 8, g = groups[gi] & 0xFF;
         const int b = 16 * g + t;
-        if (b < k) v = basis[((size_t)r * k + a) * k + b];
+        if (b < k) v = basis[((size_t)(mode0 + r) * k + a) * k + b];
     }
     const __half h = __double2half(v);
     const size_t o = (size_t)r * n_kb * 64 + col;
@@ -597,14 +597,14 @@ static int encode_basis(CUtensorMap* map, const void* base, uint64_t words, uint
 // Plan-time: which 16-tap groups of each window row touch the unit disk, and the packed fp16 basis.
 // The grid is the reference's (x_i = -1 + 2 i/(k-1), rho <= 1, _zps.py:68-75); a group is kept when any of its
 // taps has rho^2 <= 1 + 1e-9 (conservative: taps outside the disk are exact zeros of the basis anyway).
-int init_map_half_operand(zb200_plan* p) {
+static int init_one_map_operand(zb200_plan* p, MapHalf& mh, int mode0, int n_modes_part) {
     using namespace hmap;
-    MapHalf& mh = p->map_half;
-    mh.ready = false;
     const int k = p->size;
-    if (p->cc_major != 10 || k > kMaxWindow || p->real.rows_pad > 128) return ZB200_OK;   // other map kernels serve these
     const int G = (k + 15) / 16;
     mh.n_groups = G;
+    mh.mode0 = mode0;
+    mh.n_modes = n_modes_part;
+    mh.rows_pad = round_up(n_modes_part, 16);
     std::vector<unsigned short> groups;
     mh.a_first = -1;
     mh.a_end = 0;
@@ -633,7 +633,7 @@ int init_map_half_operand(zb200_plan* p) {
     for (int i = 0; i < n_rows; ++i)
         for (int g = 0; g < G; ++g) groups[(size_t)(i * KB + g / 4) * 4 + g % 4] = (unsigned short)(((mh.a_first + i) << 8) | g);
     mh.n_act = (int)groups.size();
-    const int rows_pad = p->real.rows_pad;
+    const int rows_pad = mh.rows_pad;
     const size_t halves = (size_t)rows_pad * mh.n_kb * 64;
     ZB_CUDA(cudaMalloc(&mh.b1, halves * 2));
     ZB_CUDA(cudaMalloc(&mh.b2, halves * 2));
@@ -641,7 +641,7 @@ int init_map_half_operand(zb200_plan* p) {
     ZB_CUDA(cudaMalloc(&d_groups, groups.size() * sizeof(unsigned short)));
     ZB_CUDA(cudaMemcpy(d_groups, groups.data(), groups.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     dim3 grid((unsigned)ceil_div(mh.n_kb * 64, 128), (unsigned)rows_pad);
-    map_pack_basis_kernel<<<grid, 128>>>(p->basis64, p->n_modes, rows_pad, k, d_groups, mh.n_act, mh.n_kb,
+    map_pack_basis_kernel<<<grid, 128>>>(p->basis64, mode0, n_modes_part, rows_pad, k, d_groups, mh.n_act, mh.n_kb,
                                          static_cast<__half*>(mh.b1), static_cast<__half*>(mh.b2));
     ZB_LAUNCHED();
     ZB_CUDA(cudaDeviceSynchronize());
@@ -662,48 +662,51 @@ int init_map_half_operand(zb200_plan* p) {
     return ZB200_OK;
 }
 
+// One operand holds at most 128 padded modes (two accumulator sets of 2 x n_pad TMEM columns); plans with more
+// modes (n_max >= 15) are split into equal parts, each a separate pass of the kernel over the frame.
+int init_map_half_operand(zb200_plan* p) {
+    using namespace hmap;
+    p->n_map_parts = 0;
+    if (p->cc_major != 10 || p->size > kMaxWindow) return ZB200_OK;      // the SIMT map serves these
+    const int parts = (int)ceil_div(p->n_modes, 128);
+    if (parts > 4) return ZB200_OK;
+    const int per = round_up((int)ceil_div(p->n_modes, parts), 16);
+    int done = 0;
+    for (int i = 0; i < parts && done < p->n_modes; ++i) {
+        const int cnt = p->n_modes - done < per ? p->n_modes - done : per;
+        int rc = init_one_map_operand(p, p->map_half[i], done, cnt);
+        if (rc) return rc;
+        done += cnt;
+        p->n_map_parts = i + 1;
+    }
+    return ZB200_OK;
+}
+
 void free_map_half_operand(zb200_plan* p) {
-    cudaFree(p->map_half.b1);
-    cudaFree(p->map_half.b2);
-    p->map_half = MapHalf();
+    for (MapHalf& mh : p->map_half) {
+        cudaFree(mh.b1);
+        cudaFree(mh.b2);
+        mh = MapHalf();
+    }
+    p->n_map_parts = 0;
 }
 
 bool map_h_supported(const zb200_plan* p, int precision) {
     if (precision != ZB200_PREC_F16 && precision != ZB200_PREC_F16X3) return false;
-    return p->map_half.ready;
+    return p->n_map_parts > 0;
 }
 
-int map_h(const zb200_plan* p, const float* d_img, int H, int W, int row0, int rows, int precision,
-          float* d_moments, float* d_scores, const float* h_w, const uint8_t* h_sel, int n_folds, int norm_kind,
-          cudaStream_t s) {
+// one pass of the kernel: the modes of one operand (all of them when the plan has a single part)
+static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img, int H, int W, int row0, int rows,
+                      int precision, float* d_moments, float* d_scores, const float* h_w, const uint8_t* h_sel,
+                      int n_folds, int norm_kind, cudaStream_t s) {
     using namespace hmap;
-    if (rows == 0) return ZB200_OK;
-    if (d_scores) {
-        ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
-        ZB_CHECK_ARG(h_w && h_sel, "weights/select must not be null");
-        if (n_folds > kFoldsPerLaunch) {
-            // the score tables of one launch hold kFoldsPerLaunch folds: split the fold list
-            for (int f0 = 0; f0 < n_folds; f0 += kFoldsPerLaunch) {
-                const int nf = n_folds - f0 < kFoldsPerLaunch ? n_folds - f0 : kFoldsPerLaunch;
-                int rc = map_h(p, d_img, H, W, row0, rows, precision, nullptr, d_scores + (size_t)f0 * rows * W,
-                               h_w + (size_t)f0 * p->n_modes, h_sel, nf, norm_kind, s);
-                if (rc) return rc;
-            }
-            return ZB200_OK;
-        }
-    }
-    if (!map_h_supported(p, precision)) {
-        set_error("fp16-split tcgen05 dense map unsupported for n_max=%d size=%d (needs sm_100, size <= %d, <= 128 operand rows)",
-                  p->n_max, p->size, kMaxWindow);
-        return ZB200_EUNSUP;
-    }
-    const MapHalf& mh = p->map_half;
     const bool x3 = precision == ZB200_PREC_F16X3;
     MapParams prm{};
     prm.H = H; prm.W = W; prm.row0 = row0; prm.rows = rows;
     prm.k = p->size; prm.half = p->size / 2;
     prm.pad = 8 + (prm.half & 3);                                  // (pad - half) % 4 == 0, pad >= 8
-    prm.n_pad = p->real.rows_pad; prm.n_modes = p->n_modes;
+    prm.n_pad = mh.rows_pad; prm.n_modes = mh.n_modes;
     prm.n_terms = x3 ? 3 : 1;
     prm.n_span = (int)ceil_div(W, kSpan);
     // output rows are paired by ABSOLUTE parity (2j, 2j+1), so a row's arithmetic does not depend on the band
@@ -838,6 +841,54 @@ int map_h(const zb200_plan* p, const float* d_img, int H, int W, int row0, int r
     }
     ZB_CUDA(cudaGetLastError());
     return ZB200_OK;
+}
+
+int map_h(const zb200_plan* p, const float* d_img, int H, int W, int row0, int rows, int precision,
+          float* d_moments, float* d_scores, const float* h_w, const uint8_t* h_sel, int n_folds, int norm_kind,
+          cudaStream_t s) {
+    using namespace hmap;
+    if (rows == 0) return ZB200_OK;
+    if (!map_h_supported(p, precision)) {
+        set_error("fp16-split tcgen05 dense map unsupported for n_max=%d size=%d (needs sm_100, size <= %d, <= 512 modes)",
+                  p->n_max, p->size, kMaxWindow);
+        return ZB200_EUNSUP;
+    }
+    if (d_scores) {
+        ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
+        ZB_CHECK_ARG(h_w && h_sel, "weights/select must not be null");
+    }
+    if (p->n_map_parts == 1) {
+        if (d_scores && n_folds > kFoldsPerLaunch) {
+            // the score tables of one launch hold kFoldsPerLaunch folds: split the fold list
+            for (int f0 = 0; f0 < n_folds; f0 += kFoldsPerLaunch) {
+                const int nf = n_folds - f0 < kFoldsPerLaunch ? n_folds - f0 : kFoldsPerLaunch;
+                int rc = map_h_part(p, p->map_half[0], d_img, H, W, row0, rows, precision, nullptr,
+                                    d_scores + (size_t)f0 * rows * W, h_w + (size_t)f0 * p->n_modes, h_sel, nf, norm_kind, s);
+                if (rc) return rc;
+            }
+            return ZB200_OK;
+        }
+        return map_h_part(p, p->map_half[0], d_img, H, W, row0, rows, precision, d_moments, d_scores, h_w, h_sel, n_folds,
+                          norm_kind, s);
+    }
+    // more than 128 padded modes (n_max >= 15): one pass per operand.  The scores need every mode of a pixel, so
+    // they are computed from the materialised moment maps by the rot-score kernel (zb200_algebra.cu).
+    float* moments = d_moments;
+    const size_t plane = (size_t)rows * W;
+    if (d_scores) ZB_CUDA(cudaMallocAsync(&moments, sizeof(float) * plane * p->n_modes, s));
+    int rc = ZB200_OK;
+    for (int i = 0; i < p->n_map_parts && rc == ZB200_OK; ++i) {
+        const MapHalf& mh = p->map_half[i];
+        rc = map_h_part(p, mh, d_img, H, W, row0, rows, precision, moments + plane * mh.mode0, nullptr, nullptr, nullptr, 0, 0, s);
+    }
+    if (rc == ZB200_OK && d_scores) {
+        std::vector<double> wd((size_t)n_folds * p->n_modes);
+        for (size_t i = 0; i < wd.size(); ++i) wd[i] = h_w[i];
+        rc = zb200_rot_scores(ZB200_F32, moments, (int64_t)plane, p->n_modes, 1, (int64_t)plane, wd.data(), h_sel, n_folds,
+                              norm_kind, d_scores, 1, (int64_t)plane, s);
+    }
+    if (d_scores) cudaFreeAsync(moments, s);
+    return rc;
 }
 
 }  // namespace zb200

@@ -589,3 +589,21 @@ def test_config4_full_size_map_property(api, torch):
     bands = [(0, 1023), (1023, 1026), (2049, 999), (3048, 1048)]
     parts = [z.symmetry_map(dimg, [2, 3, 4, 6], row0=r0, rows=r) for r0, r in bands]
     assert torch.equal(torch.cat(parts, dim=1), full)
+
+
+def test_map_many_modes_two_passes(api):
+    """n_max >= 15 gives more than 128 padded modes: the tensor-core map runs one pass per mode block and the
+    scores come from the materialised moments (n_max=16 -> 153 modes, n_max=20 -> 231 modes)."""
+    from motif_learn_b200 import _lib
+    from motif_learn_b200.datasets import honeycomb_image
+    img, _ = honeycomb_image((140, 600), bond=12.0, seed=9, angle=3.0)
+    for n_max, k in ((16, 40), (20, 64)):
+        z = api.ZPs(n_max, k)
+        assert _lib.load().zb200_plan_supports_map(z._plan, _lib.PREC_F16X3)
+        n, m, v = zo.zernike_basis(n_max, k)
+        ref = zo.moment_map_fft(img.astype(np.float64), v, n, chunk=32)
+        got = z.transform(img).data
+        assert got.shape == ref.shape
+        fp32_close(got, ref)
+        want = zo.rot_maps(ref, n, m, [2, 3, 4, 6])
+        assert np.nanmax(np.abs(z.symmetry_map(img, [2, 3, 4, 6]) - want)) < 1e-5
