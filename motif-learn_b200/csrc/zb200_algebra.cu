@@ -191,6 +191,43 @@ __global__ void mirror_kernel(const Cx<T>* __restrict__ in, long long n_items, i
     out[it] = best;
 }
 
+// Same score with the modes grouped by |m| first: sum_c Re(Zc^2 e^{-i m_c theta}) = sum_m (P_m cos m theta +
+// Q_m sin m theta) with P_m = sum_{c: m_c = m} Re(Zc^2), Q_m = sum Im(Zc^2).  A basis up to n_max has at most
+// n_max + 1 distinct m against (n_max/2 + 1)^2 complex modes, so the angle loop shrinks 3-4x (n_max = 12:
+// 11 slots instead of 40 modes).  slot[c] = group of mode c; tab[t][s] = (cos, sin)(m_s theta_t); kSlots >= groups.
+template <typename T, int kSlots>
+__global__ void mirror_grouped_kernel(const Cx<T>* __restrict__ in, long long n_items, int n_c, long long is,
+                                      long long ms, const int* __restrict__ slot, const float2* __restrict__ tab,
+                                      int n_theta, T* __restrict__ out) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    T P[kSlots], Q[kSlots];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) P[s] = Q[s] = 0;
+    for (int c = 0; c < n_c; ++c) {
+        const Cx<T> v = in[it * is + c * ms];
+        const T p = v.re * v.re - v.im * v.im, q = (T)2 * v.re * v.im;
+        const int sc = __ldg(slot + c);                       // warp-uniform
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s)
+            if (s == sc) { P[s] += p; Q[s] += q; }
+    }
+    T best = -INFINITY;
+    for (int t = 0; t < n_theta; ++t) {
+        const float2* row = tab + (size_t)t * kSlots;
+        T a0 = 0, a1 = 0;
+#pragma unroll
+        for (int s = 0; s < kSlots; s += 2) {
+            const float2 c0 = __ldg(row + s), c1 = __ldg(row + s + 1);
+            a0 += P[s] * (T)c0.x + Q[s] * (T)c0.y;
+            a1 += P[s + 1] * (T)c1.x + Q[s + 1] * (T)c1.y;
+        }
+        const T acc = a0 + a1;
+        best = acc > best ? acc : best;
+    }
+    out[it] = best;
+}
+
 template <typename T>
 __global__ void abs_phase_kernel(const Cx<T>* __restrict__ in, long long n, T* __restrict__ mag_out, T* __restrict__ ph_out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,11 +428,45 @@ extern "C" int zb200_mirror_scores(int dtype, const void* d_in, int64_t n_items,
     ZB_CHECK_ARG(d_in && d_out && h_m && h_theta && n_c > 0 && n_theta > 0 && n_items >= 0, "mirror_scores: bad arguments");
     if (n_items == 0) return ZB200_OK;
     cudaStream_t s = as_stream(stream);
+    // group the modes by m: slots[c] = index of m_c among the distinct m values
+    std::vector<int> distinct, slots(n_c);
+    for (int c = 0; c < n_c; ++c) {
+        int sidx = -1;
+        for (size_t i = 0; i < distinct.size(); ++i)
+            if (distinct[i] == h_m[c]) sidx = (int)i;
+        if (sidx < 0) { sidx = (int)distinct.size(); distinct.push_back(h_m[c]); }
+        slots[c] = sidx;
+    }
+    const int n_groups = (int)distinct.size();
+    Scratch sc(s);
+    if (n_groups <= 32) {
+        const int k_slots = n_groups <= 8 ? 8 : (n_groups <= 16 ? 16 : 32);
+        std::vector<unsigned char> blob(sizeof(int) * (size_t)n_c + 16 + sizeof(float2) * (size_t)n_theta * k_slots, 0);
+        const size_t tab_off = (sizeof(int) * (size_t)n_c + 15) & ~(size_t)15;
+        memcpy(blob.data(), slots.data(), sizeof(int) * (size_t)n_c);
+        float2* tab = reinterpret_cast<float2*>(blob.data() + tab_off);
+        for (int t = 0; t < n_theta; ++t)
+            for (int g = 0; g < n_groups; ++g)
+                tab[(size_t)t * k_slots + g] = make_float2((float)cos(distinct[g] * h_theta[t]), (float)sin(distinct[g] * h_theta[t]));
+        int rc = sc.upload(blob.data(), blob.size());
+        if (rc) return rc;
+        const int* d_slot = static_cast<const int*>(sc.ptr);
+        const float2* d_tab = reinterpret_cast<const float2*>(static_cast<const unsigned char*>(sc.ptr) + tab_off);
+        ZB_DISPATCH_DTYPE(dtype, {
+            const unsigned grid = grid_for(n_items, 128);
+            const Cx<T>* src = static_cast<const Cx<T>*>(d_in);
+            T* dst = static_cast<T*>(d_out);
+            if (k_slots == 8) mirror_grouped_kernel<T, 8><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
+            else if (k_slots == 16) mirror_grouped_kernel<T, 16><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
+            else mirror_grouped_kernel<T, 32><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
+        })
+        ZB_LAUNCHED();
+        return ZB200_OK;
+    }
     std::vector<float2> tab((size_t)n_theta * n_c);
     for (int t = 0; t < n_theta; ++t)
         for (int c = 0; c < n_c; ++c)
             tab[(size_t)t * n_c + c] = make_float2((float)cos(h_m[c] * h_theta[t]), (float)sin(h_m[c] * h_theta[t]));
-    Scratch sc(s);
     int rc = sc.upload(tab.data(), tab.size() * sizeof(float2));
     if (rc) return rc;
     ZB_DISPATCH_DTYPE(dtype, {
