@@ -361,8 +361,12 @@ def bench_map(torch, dist, rank, world, args, pk, tiled=False):
     zp_host = ZPs(N_MAX, MAP_WINDOW, precision=args.precision, output="numpy")
     host = torch.empty((MAP_SIZE, MAP_SIZE), dtype=torch.float32, pin_memory=True)
     host.copy_(dimg)
+    zp_host.symmetry_map(host.numpy(), FOLDS, row0=row0, rows=rows)      # warm-up: pinned staging, mempool growth
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    e2e_steps = 2
+    e2e_steps = 3
     for _ in range(e2e_steps):
         res = zp_host.symmetry_map(host.numpy(), FOLDS, row0=row0, rows=rows)
     dt = time.perf_counter() - t0
