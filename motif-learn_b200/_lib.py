@@ -67,6 +67,8 @@ SIGNATURES = {
     "zb200_render_atoms_f32": (_int, [_vp, _vp, C.c_double, _i64, C.c_double, C.c_double, _int, _int, _vp, _int, _vp]),
     "zb200_local_max_f32": (_int, [_vp, _int, _int, C.c_double, _int, C.c_double, _vp, _i64, C.POINTER(_i64),
                                    C.POINTER(_i64), _vp]),
+    "zb200_gram_f32": (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
+    "zb200_pca_scores_f32": (_int, [_vp, _i64, _int, _vp, _vp, _int, _vp, _vp]),
     "zb200_download_as_f64": (_int, [_vp, _i64, _vp, _vp]),
     "zb200_cast": (_int, [_int, _vp, _int, _vp, _i64, _vp]),
 }

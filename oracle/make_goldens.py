@@ -207,6 +207,19 @@ def golden_peaks():
     save("peaks.npz", **arrays)
 
 
+def golden_pca():
+    """PCA of a feature matrix ("next" row f4): the reference's own ``pca`` (scikit-learn underneath) on the
+    rotation-invariant features |Zc| of the three-fold test patches plus lattice patches."""
+    from mtflearn.features import pca
+    rng = np.random.default_rng(11)
+    p3 = get_zps_test_patches(size=32, n_fold=3, num_patches=400)
+    p4 = get_zps_test_patches(size=32, n_fold=4, num_patches=400)
+    patches = np.concatenate([p3, p4]).astype(np.float32)
+    patches += rng.normal(0, 0.01, patches.shape).astype(np.float32)
+    feats = np.abs(ZPs(10, 32).fit_transform(patches).to_complex().data).astype(np.float32)
+    save("pca.npz", feats=feats, pca2=pca(feats.astype(np.float64), 2), pca5=pca(feats.astype(np.float64), 5))
+
+
 if __name__ == "__main__":
     golden_index()
     golden_basis()
@@ -214,3 +227,4 @@ if __name__ == "__main__":
     golden_lattice()
     golden_render()
     golden_peaks()
+    golden_pca()

@@ -445,3 +445,26 @@ def local_max(image: np.ndarray, min_distance: float, threshold=None) -> np.ndar
     """mtflearn/features/_local_max_v2.py:46-66: (N, 2) peaks as (x, y), brightest first."""
     peaks = peak_local_max_md1(image, threshold)
     return filter_peaks_by_distance(image, peaks[:, ::-1], min_distance)
+
+
+# --------------------------------------------------------------------------- #
+# PCA of the feature matrix ("next" row f4)                                     #
+# --------------------------------------------------------------------------- #
+def pca(X: np.ndarray, n_components: int = 2) -> np.ndarray:
+    """mtflearn/features/_dimension_reduction.py:3-6 -- ``PCA(n_components).fit_transform(X)``.  scikit-learn
+    is a third-party dependency (unpinned in the reference's pyproject.toml; 1.9.0 in this image); this is its
+    covariance route (``svd_solver='covariance_eigh'``, chosen by 'auto' for n_samples >= 10 n_features):
+    C = (X^T X - n mu mu^T)/(n-1), eigh, components flipped so that their largest-magnitude entry is positive
+    (``svd_flip(u_based_decision=False)``), scores = (X - mu) V^T.  Pinned against the live reference in
+    tests/golden/pca.npz."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    mean = X.sum(axis=0) / n
+    cov = (X.T @ X - n * np.outer(mean, mean)) / (n - 1)
+    evals, evecs = np.linalg.eigh((cov + cov.T) * 0.5)
+    vt = evecs[:, ::-1].T[:n_components].copy()
+    idx = np.argmax(np.abs(vt), axis=1)
+    signs = np.sign(vt[np.arange(len(vt)), idx])
+    signs[signs == 0] = 1.0
+    vt *= signs[:, None]
+    return (X - mean) @ vt.T

@@ -607,3 +607,27 @@ def test_map_many_modes_two_passes(api):
         fp32_close(got, ref)
         want = zo.rot_maps(ref, n, m, [2, 3, 4, 6])
         assert np.nanmax(np.abs(z.symmetry_map(img, [2, 3, 4, 6]) - want)) < 1e-5
+
+
+# ---- "next" row f4: PCA of the feature matrix ---------------------------------------------------------
+def test_pca_golden_and_live_sklearn(api, golden, torch):
+    """CUDA pca against the goldens of the live reference (scikit-learn PCA.fit_transform), and against
+    scikit-learn itself on a tall matrix of device-computed features (float64 accumulation: 1e-10)."""
+    g = golden("pca.npz")
+    for c, key in ((2, "pca2"), (5, "pca5")):
+        got = api.pca(g["feats"], c)
+        assert got.shape == g[key].shape and got.dtype == np.float64
+        np.testing.assert_allclose(got, g[key], rtol=0, atol=1e-10)
+    from sklearn.decomposition import PCA
+    rng = np.random.default_rng(0)
+    base = rng.normal(size=(20000, 6)) @ rng.normal(size=(6, 91)) + 0.05 * rng.normal(size=(20000, 91))
+    X = (base + rng.normal(size=91)).astype(np.float32)
+    ref = PCA(n_components=3).fit_transform(X.astype(np.float64))
+    np.testing.assert_allclose(api.pca(X, 3), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+    dev = api.pca(torch.from_numpy(X).cuda(), 3)
+    assert dev.is_cuda and dev.dtype == torch.float64
+    np.testing.assert_allclose(dev.cpu().numpy(), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+    # more features than one 96-column tile (n_max=20 real moments: 231 columns)
+    Y = (rng.normal(size=(5000, 4)) @ rng.normal(size=(4, 231)) + 0.1 * rng.normal(size=(5000, 231))).astype(np.float32)
+    ref = PCA(n_components=2).fit_transform(Y.astype(np.float64))
+    np.testing.assert_allclose(api.pca(Y, 2), ref, rtol=0, atol=1e-9 * np.abs(ref).max())

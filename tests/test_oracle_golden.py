@@ -231,3 +231,10 @@ def test_oracle_peak_local_max_edge_cases():
     np.testing.assert_array_equal(got, [[3, 3], [3, 4]])
     np.testing.assert_array_equal(zo.local_max(img, 1.0), [[3, 3]])            # (x, y); the raster-first twin wins
     np.testing.assert_array_equal(zo.local_max(img, 0.5), [[3, 3], [4, 3]])
+
+
+# ---- PCA ("next" row f4) ---------------------------------------------------------------------------
+def test_oracle_pca_matches_reference_golden(golden):
+    g = golden("pca.npz")
+    for c, key in ((2, "pca2"), (5, "pca5")):
+        np.testing.assert_allclose(zo.pca(g["feats"], c), g[key], rtol=0, atol=1e-13)
