@@ -516,21 +516,43 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         uint32_t it = 0;
         // Eight k values (two 16-B chunks) -> 8 TMEM columns of bf16 pairs: columns 0..3 hold
         // Xlo[0..7], columns 4..7 hold Xhi[0..7] (K slot 2c in the low half-word, 2c+1 in the high).
-        auto lo_of = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
+        // The four splitter warps are this kernel's critical path (ncu source page: ~100 % of their samples sit in
+        // the per-k-block loop, 365 SASS instructions), so the split is written for instruction count: the pair
+        // (x0 - trunc(x0), x1 - trunc(x1)) is ONE packed add.f32x2 on (x, -(x & mask)), each negated truncation one
+        // LOP3 ((x & mask) ^ sign), and the tile rows are read with ld.shared.v4 from 32-bit shared addresses.
         auto pack2 = [](float even, float odd) {
-            const __nv_bfloat162 v = __floats2bfloat162_rn(even, odd);      // .x = low half-word
-            return *reinterpret_cast<const uint32_t*>(&v);
+            uint32_t v;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(odd), "f"(even));   // .x (low half-word) = even
+            return v;
+        };
+        auto lo_pair = [&](float x0, float x1) {
+            const uint32_t n0 = (__float_as_uint(x0) & 0xFFFFE000u) ^ 0x80000000u;   // -trunc_tf32(x0)
+            const uint32_t n1 = (__float_as_uint(x1) & 0xFFFFE000u) ^ 0x80000000u;
+            uint64_t a, b, d;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(__float_as_uint(x0)), "r"(__float_as_uint(x1)));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(n0), "r"(n1));
+            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+            uint32_t l0, l1;
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(l0), "=r"(l1) : "l"(d));
+            return pack2(__uint_as_float(l0), __uint_as_float(l1));
         };
         auto split8 = [&](const float4& a, const float4& b, uint32_t* w) {
-            w[0] = pack2(lo_of(a.x), lo_of(a.y));
-            w[1] = pack2(lo_of(a.z), lo_of(a.w));
-            w[2] = pack2(lo_of(b.x), lo_of(b.y));
-            w[3] = pack2(lo_of(b.z), lo_of(b.w));
+            w[0] = lo_pair(a.x, a.y);
+            w[1] = lo_pair(a.z, a.w);
+            w[2] = lo_pair(b.x, b.y);
+            w[3] = lo_pair(b.z, b.w);
             w[4] = pack2(a.x, a.y);
             w[5] = pack2(a.z, a.w);
             w[6] = pack2(b.x, b.y);
             w[7] = pack2(b.z, b.w);
         };
+        auto lds128 = [](uint32_t addr) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            return v;
+        };
+        const uint32_t x_ring_u32 = smem_u32(smem);
+        const uint32_t swz = (uint32_t)(r & 7) << 4;                  // logical 16-B chunk c sits at (c << 4) ^ swz
         const int g_rows = 32 * p.subtiles;                       // tile rows this warp gathers: [q*g_rows, +g_rows)
         for (int t = 0; t < my_tiles; ++t) {
             int2 ca = make_int2(-(1 << 28), -(1 << 28)), cb = ca;  // windows of the rows q*g_rows+lane (and +32)
@@ -606,15 +628,13 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     fence_proxy_async();                           // the MMA (async proxy) reads these rows
                     asm volatile("bar.sync 1, 128;" ::: "memory");  // all four gather warps done with this stage
                 }
-                const uint8_t* rowp = stage_x(s) + (size_t)r * 128;
+                const uint32_t rowp = x_ring_u32 + (uint32_t)s * x_bytes + (uint32_t)r * 128u;
                 float4 x0[8], x1[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c)                       // logical 16-B chunk c sits at c ^ (r % 8)
-                    x0[c] = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+                for (int c = 0; c < 8; ++c) x0[c] = lds128(rowp + (((uint32_t)c << 4) ^ swz));
                 if (p.subtiles == 2) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        x1[c] = *reinterpret_cast<const float4*>(rowp + kTileRows * 128 + ((c ^ (r & 7)) << 4));
+                    for (int c = 0; c < 8; ++c) x1[c] = lds128(rowp + kTileRows * 128u + (((uint32_t)c << 4) ^ swz));
                 }
                 mbar_wait_t(&lo_empty[lb], lo_ph ^ 1u, w1, prof);
                 tc_fence_after();
