@@ -157,13 +157,13 @@ __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return (
 __device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
 // kind::tf32, fp32 accumulate, A and B K-major, M=128, N=n
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n, int m = 128) {
     uint32_t d = 0;
     d |= 1u << 4;                   // c_format = F32
     d |= 2u << 7;                   // a_format = TF32
     d |= 2u << 10;                  // b_format = TF32
     d |= (uint32_t)(n >> 3) << 17;  // N / 8
-    d |= (uint32_t)(128 >> 4) << 24;  // M / 16
+    d |= (uint32_t)(m >> 4) << 24;  // M / 16   (256 with cta_group::2)
     return d;
 }
 
@@ -175,17 +175,71 @@ __device__ __forceinline__ float tf32_rn(float f) {
 }
 
 
+// ---- CTA-pair (cta_group::2) helpers: one thread of the leader CTA issues M=256 MMAs that run on both SMs of
+// the pair; each CTA supplies its own 128 rows of A (same shared-memory / TMEM offsets) and N/2 rows of B ----
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+// arrive on a barrier of another CTA of the cluster (address from mapa_cluster)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id): the cluster-scoped
+    // release compiles to MEMBAR.ALL.GPU + ERRBAR in front of every arrive and cost 30 % of the splitter loop
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on an own barrier whose arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_2(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all MMAs issued so far by this thread have completed on BOTH SMs) on the barrier at this offset in
+// every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_2mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // D[tmem] (+)= A[tmem] . B[smem]^T with bf16 operands (K = 16 per instruction), fp32 accumulate
-__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n, int m = 128) {
     uint32_t d = 0;
     d |= 1u << 4;                   // c_format = F32
     d |= 1u << 7;                   // a_format = BF16
     d |= 1u << 10;                  // b_format = BF16
     d |= (uint32_t)(n >> 3) << 17;  // N / 8
-    d |= (uint32_t)(128 >> 4) << 24;  // M / 16
+    d |= (uint32_t)(m >> 4) << 24;  // M / 16   (256 with cta_group::2)
     return d;
 }
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
