@@ -33,7 +33,7 @@ MAP_WINDOW = 48
 FOLDS = [2, 3, 4, 6]
 # DRAM bytes per launch of the projection kernel at the default batch, from the committed ncu
 # captures (profiles/r01_prof_tc3_raw.csv, r01_prof_tc1_raw.csv): read + write
-NCU_TRAFFIC = {"tf32x3": 4.333749e9 + 43.726e6, "tf32": 4.317544e9 + 52.794e6}
+NCU_TRAFFIC = {"tf32x3": 4.333988e9 + 44.654e6, "tf32": 4.317544e9 + 52.794e6}
 # dense-map kernels at 2048^2 (profiles/r01_prof_map_raw.csv, r01_prof_maph_raw.csv): read + write
 NCU_TRAFFIC_MAP = {"tf32x3": 136.456e6 + 48.684e6, "f16x3": 136.114e6 + 46.329e6}
 PREC_NAMES = {0: "fp32", 1: "tf32", 2: "tf32x3", 3: "f16", 4: "f16x3"}
@@ -269,7 +269,7 @@ def bench_patches(torch, dist, rank, world, args, pk):
             "traffic_source": "profiles/r01 ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch",
             "peak_source": pk["source"],
             "kernel": {"fp32": "project_simt_kernel", "tf32": "project_tc_kernel<plain>",
-                       "tf32x3": "project_tc3_kernel<plain>"}[prec],
+                       "tf32x3": "project_tc3_kernel<plain,pair>"}[prec],
             "algorithmic_bytes_per_launch": alg_bytes,
             "tflops": flops * args.steps / (ms / 1e3) / 1e12}
 
