@@ -18,14 +18,22 @@
 // and element (i, tap t) of the 16-tap group g of window row a sits at  E_r + 16 (q0 + i + 4g) + 2t,
 // taps 8..15 at +32 B (leading byte offset 32 B, stride byte offset 128 B).  TMA loads rows of E
 // (zero fill outside the frame = the reference's zero extension).
-// Taps outside the unit disk are zero in every mode: 16-tap groups that lie entirely outside are never
-// issued, and the packed B operand (b1 | b2, 128-B swizzled k-blocks of 4 groups) only holds active groups.
+// Window rows that lie entirely outside the unit disk are never issued; the packed B operand (b1 | b2, 128-B
+// swizzled k-blocks of 4 groups, ceil(G/4) k-blocks per window row) holds the remaining rows in issue order.
 //
-// Tile = (output row, 512-pixel span, phase pair): two accumulators of 128 pixels x n_pad modes, two
-// accumulator sets in TMEM, drained every ~32 K-steps into fp32 registers (the tensor core accumulates
-// with round-toward-zero).  Warp roles (384 threads): warp 0 frame-row TMA producer, warp 1 basis TMA
-// producer (multicast across the cluster), warp 2 MMA issuer, warp 3 TMEM allocator, warpgroups 1-2
-// epilogue (one pixel phase each; thread == pixel, so the score is thread-local).
+// Two output rows per MMA.  A staged frame row f is window row a = f - y0 + k/2 of output row y0 and window row
+// a - 1 of output row y0 + 1, so ONE MMA with N = 2 n_pad whose B operand is the basis of window rows (a-1, a) --
+// adjacent slots of the basis ring, slot S mirroring slot 0 for the wrap-around -- feeds both rows: accumulator
+// columns [0, n_pad) belong to row y0 + 1, [n_pad, 2 n_pad) to row y0.  An N = 96 SS MMA is shared-memory-bound
+// (7 KB per 48 tensor clk), the N = 192 one is tensor-bound.  Rows are paired by ABSOLUTE parity so that row bands
+// computed separately (image-tile sharding) reproduce the single-call result bit for bit.
+//
+// Tile = (row pair, 512-pixel span, pixel phase r): 128 pixels x 2 rows, two accumulator sets of 2 n_pad TMEM
+// columns, drained every ~12 groups per row into fp32 registers (the tensor core accumulates with
+// round-toward-zero).  Warp roles (384 threads): warps 0-7 epilogue (thread == pixel, so the score is
+// thread-local; warpgroup 0 = row y0+1, warpgroup 1 = row y0), warp 8 frame-row TMA producer, warp 9 basis TMA
+// producer (multicast across the cluster), warp 10 MMA issuer (loop specialised on G and unrolled per step: the
+// first version was issue-bound, profiles/r01_maph_issue_study.md), warp 11 TMEM allocator.
 #include "zb200_common.cuh"
 #include "zb200_tc_ptx.cuh"
 
