@@ -631,3 +631,15 @@ def test_pca_golden_and_live_sklearn(api, golden, torch):
     Y = (rng.normal(size=(5000, 4)) @ rng.normal(size=(4, 231)) + 0.1 * rng.normal(size=(5000, 231))).astype(np.float32)
     ref = PCA(n_components=2).fit_transform(Y.astype(np.float64))
     np.testing.assert_allclose(api.pca(Y, 2), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+
+
+def test_download_as_f64_multi_chunk(torch):
+    """zb200_download_as_f64 (the float64 host result every numpy-in call returns): several 32 MiB staging
+    chunks plus a ragged tail, threaded widening -- bit-identical to the float32 values."""
+    from motif_learn_b200.features._zps import _host_f64
+    t = torch.randn(20_000_003, device="cuda", dtype=torch.float32)
+    got = _host_f64(t)
+    assert got.dtype == np.float64 and got.shape == (20_000_003,)
+    np.testing.assert_array_equal(got, t.cpu().numpy().astype(np.float64))
+    small = torch.arange(7, device="cuda", dtype=torch.float32).reshape(7, 1)
+    np.testing.assert_array_equal(_host_f64(small), np.arange(7, dtype=np.float64).reshape(7, 1))
