@@ -393,7 +393,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // TMEM columns: [2 accumulator sets][lo_bufs x subtiles x (Xraw? 32 | bf16 pack 32)]
-    const uint32_t lo_base = tmem_base + (uint32_t)(2 * p.subtiles * p.n_pad);
+    const uint32_t lo_base = tmem_base + (uint32_t)(p.acc_bufs * p.subtiles * p.n_pad);
     const uint32_t lo_mask = (uint32_t)p.lo_bufs - 1u;               // lo_bufs is a power of two
     const uint32_t lo_shift = p.lo_bufs == 4 ? 2u : (p.lo_bufs == 2 ? 1u : 0u);
 
@@ -487,9 +487,12 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 uint32_t ck = 0;            // running chunk counter    -> accumulator buffer / phase
                 for (int t = 0; t < my_tiles; ++t) {
                     for (int c = 0; c < n_chunks; ++c, ++ck) {
-                        const int buf = ck & 1;
-                        if (kPair) mbar_wait_cluster(&acc_empty[buf], ((ck >> 1) & 1u) ^ 1u);
-                        else mbar_wait_t(&acc_empty[buf], ((ck >> 1) & 1u) ^ 1u, w0, prof);
+                        // two accumulator sets alternate; with one set (wide operands: TMEM goes to the staging
+                        // buffers instead) the chunk waits for its own drain
+                        const int buf = p.acc_bufs == 2 ? (int)(ck & 1) : 0;
+                        const uint32_t acc_par = p.acc_bufs == 2 ? ((ck >> 1) & 1u) : (ck & 1u);
+                        if (kPair) mbar_wait_cluster(&acc_empty[buf], acc_par ^ 1u);
+                        else mbar_wait_t(&acc_empty[buf], acc_par ^ 1u, w0, prof);
                         tc_fence_after();
                         const int kb_end = min(p.k_blocks, (c + 1) * p.chunk_kb);
                         const uint32_t d0 = tmem_base + (uint32_t)(buf * p.subtiles * p.n_pad);
@@ -749,8 +752,8 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
                 for (int i = 0; i < 16; ++i) sum[cc][i] = 0.f;
             for (int c = 0; c < n_chunks; ++c, ++ck) {
-                const int buf = ck & 1;
-                mbar_wait_t(&acc_full[buf], (ck >> 1) & 1u, w0, prof);
+                const int buf = p.acc_bufs == 2 ? (int)(ck & 1) : 0;
+                mbar_wait_t(&acc_full[buf], p.acc_bufs == 2 ? ((ck >> 1) & 1u) : (ck & 1u), w0, prof);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
                                        (uint32_t)((buf * p.subtiles + sub) * p.n_pad + c_beg);
@@ -964,7 +967,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.cluster = cluster;
     const int lg = cluster == 4 ? 2 : (cluster == 2 ? 1 : 0);
     // CTA pairs (cta_group::2) for the fp32-grade kernel: needs the 2-CTA cluster and the TMA-fed X ring
-    prm.pair = (x3 && cluster == 2 && !gsrc && op.rows_pad % 32 == 0) ? 1 : 0;
+    prm.pair = (x3 && cluster == 2 && !gsrc && op.rows_pad % 16 == 0) ? 1 : 0;
     if (const char* e = getenv("ZB200_TC_PAIR")) prm.pair = (prm.pair && atoi(e) != 0) ? 1 : 0;
 
     prm.b_stages = 3;
@@ -983,7 +986,20 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.acc_bufs = (2 * sub * prm.n_pad <= (int)kTmemCols) ? 2 : 1;
     {
         const int per_buf = sub * kBlockK;
-        const int room = ((int)kTmemCols - 2 * sub * prm.n_pad) / per_buf;
+        int room = ((int)kTmemCols - prm.acc_bufs * sub * prm.n_pad) / per_buf;
+        if (x3 && prm.acc_bufs == 2 && room < 2) {
+            // wide operands (n_max = 20: 240 rows): two accumulator sets would leave ONE staging buffer and serialise
+            // the splitter with the MMAs on every k-block; one set + four staging buffers only stalls at the drains
+            prm.acc_bufs = 1;
+            room = ((int)kTmemCols - sub * prm.n_pad) / per_buf;
+        }
+        if (const char* e = getenv("ZB200_TC_ACCBUFS")) {
+            const int v = atoi(e);
+            if (x3 && (v == 1 || (v == 2 && 2 * sub * prm.n_pad + per_buf <= (int)kTmemCols))) {
+                prm.acc_bufs = v;
+                room = ((int)kTmemCols - v * sub * prm.n_pad) / per_buf;
+            }
+        }
         prm.lo_bufs = room >= 4 ? 4 : (room >= 2 ? 2 : 1);
     }
     prm.n_tiles = (int)ceil_div(n, (int64_t)sub * kTileRows);
