@@ -132,6 +132,21 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
     cudaGetDevice(&p->device);
     p->inv_area = 1.0 / (M_PI * (double)size * (double)size / 4.0);    // area = pi k^2/4, _zps.py:154
     zb200_mode_table(n_max, p->h_n, p->h_m);
+    {
+        // k-blocks of 32 taps that contain a tap of the unit disk (grid x_i = -1 + 2 i/(k-1), rho <= 1, _zps.py:68-75;
+        // the 1e-9 margin only ever keeps a block): the tensor-core projection streams and multiplies only those
+        const int k = size;
+        int first = -1, last = 0;
+        for (int e = 0; e < p->kk; ++e) {
+            const double y = k > 1 ? -1.0 + 2.0 * (e / k) / (k - 1) : 0.0, x = k > 1 ? -1.0 + 2.0 * (e % k) / (k - 1) : 0.0;
+            if (x * x + y * y <= 1.0 + 1e-9) {
+                if (first < 0) first = e / 32;
+                last = e / 32 + 1;
+            }
+        }
+        p->kb_first = first < 0 ? 0 : first;
+        p->kb_last = first < 0 ? 1 : last;
+    }
 
 #define ZB_PLAN_TRY(expr)                      \
     do {                                       \

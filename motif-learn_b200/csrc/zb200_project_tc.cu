@@ -54,7 +54,8 @@ struct Params {
     long long n_patches;
     int n_tiles;          // ceil(n_patches / (128*subtiles))
     int subtiles;         // 1 or 2 accumulators (128 patches each) per tile
-    int k_blocks;         // k_pad / 32
+    int k_blocks;         // 32-tap k-blocks that hold taps inside the unit disk (window rows entirely outside are skipped)
+    int kb0;              // first of them: k-block kb of the loops is taps [(kb0 + kb) * 32, +32)
     int n_pad;            // UMMA N (operand rows, multiple of 16)
     int n_cols;           // meaningful accumulator columns
     int n_stages;
@@ -212,11 +213,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full[s], x_bytes + b_bytes);
-                    tma_load_2d(stage_x(s), &map_x, &full[s], kb * kBlockK, row0, kEvictFirst);
+                    tma_load_2d(stage_x(s), &map_x, &full[s], (p.kb0 + kb) * kBlockK, row0, kEvictFirst);
                     if (p.cluster == 1)
-                        tma_load_2d(stage_b(s), &map_b, &full[s], kb * kBlockK, 0, kEvictLast);
+                        tma_load_2d(stage_b(s), &map_b, &full[s], (p.kb0 + kb) * kBlockK, 0, kEvictLast);
                     else
-                        tma_load_2d_mc(stage_b(s) + (size_t)crank * b_rows * 128, &map_b, &full[s], kb * kBlockK,
+                        tma_load_2d_mc(stage_b(s) + (size_t)crank * b_rows * 128, &map_b, &full[s], (p.kb0 + kb) * kBlockK,
                                        (int)crank * b_rows, cmask, kEvictLast);
                     if (++s == p.n_stages) { s = 0; ph ^= 1; }
                 }
@@ -417,7 +418,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         if (p.gather) break;                       // X is gathered by the splitter warps
                         mbar_wait_t(&empty[s], ph ^ 1, w0, prof);
                         mbar_arrive_expect_tx(&full[s], x_bytes);
-                        tma_load_2d(stage_x(s), &map_x, &full[s], kb * kBlockK, row0, kEvictFirst);
+                        tma_load_2d(stage_x(s), &map_x, &full[s], (p.kb0 + kb) * kBlockK, row0, kEvictFirst);
                         if (++s == p.n_stages) { s = 0; ph ^= 1; }
                     }
                 }
@@ -435,20 +436,20 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                             // own half of the rows only, at the start of the stage (the M=256 MMA takes N/2 rows of B
                             // from each CTA of the pair)
                             mbar_arrive_expect_tx(&bfull[sb], bst_bytes);
-                            tma_load_2d(stage_bhi(sb), &map_bhi, &bfull[sb], kb * kBlockK, (int)crank * b_rows, kEvictLast);
-                            tma_load_2d(stage_blo(sb), &map_blo, &bfull[sb], kb * kBlockK, (int)crank * b_rows, kEvictLast);
+                            tma_load_2d(stage_bhi(sb), &map_bhi, &bfull[sb], (p.kb0 + kb) * kBlockK, (int)crank * b_rows, kEvictLast);
+                            tma_load_2d(stage_blo(sb), &map_blo, &bfull[sb], (p.kb0 + kb) * kBlockK, (int)crank * b_rows, kEvictLast);
                             if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
                             continue;
                         }
                         mbar_arrive_expect_tx(&bfull[sb], bst_bytes);
                         if (p.cluster == 1) {
-                            tma_load_2d(stage_bhi(sb), &map_bhi, &bfull[sb], kb * kBlockK, 0, kEvictLast);
-                            tma_load_2d(stage_blo(sb), &map_blo, &bfull[sb], kb * kBlockK, 0, kEvictLast);
+                            tma_load_2d(stage_bhi(sb), &map_bhi, &bfull[sb], (p.kb0 + kb) * kBlockK, 0, kEvictLast);
+                            tma_load_2d(stage_blo(sb), &map_blo, &bfull[sb], (p.kb0 + kb) * kBlockK, 0, kEvictLast);
                         } else {
                             const size_t off = (size_t)crank * b_rows * 128;
-                            tma_load_2d_mc(stage_bhi(sb) + off, &map_bhi, &bfull[sb], kb * kBlockK, (int)crank * b_rows, cmask,
+                            tma_load_2d_mc(stage_bhi(sb) + off, &map_bhi, &bfull[sb], (p.kb0 + kb) * kBlockK, (int)crank * b_rows, cmask,
                                            kEvictLast);
-                            tma_load_2d_mc(stage_blo(sb) + off, &map_blo, &bfull[sb], kb * kBlockK, (int)crank * b_rows, cmask,
+                            tma_load_2d_mc(stage_blo(sb) + off, &map_blo, &bfull[sb], (p.kb0 + kb) * kBlockK, (int)crank * b_rows, cmask,
                                            kEvictLast);
                         }
                         if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
@@ -631,7 +632,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
             auto gather_issue = [&](int kbi, int sg, uint32_t phg) {
                 mbar_wait(&empty[sg], phg ^ 1u);                   // the stage's previous MMAs have retired
-                const int e0 = kbi * kBlockK;
+                const int e0 = (p.kb0 + kbi) * kBlockK;
                 const uint32_t xs = smem_u32(stage_x(sg)) + (uint32_t)(q * g_rows) * 128u;
                 if (p.g_planes) {
                     // 16-byte copies from the shifted planes: 8 lanes move one 32-float segment, a warp instruction
@@ -908,7 +909,8 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.n_patches = n;
     prm.n_pad = op.rows_pad;
     prm.n_cols = op.rows;
-    prm.k_blocks = p->k_pad / kBlockK;
+    prm.kb0 = p->kb_first;                                  // leading / trailing k-blocks with an all-zero basis
+    prm.k_blocks = p->kb_last - p->kb_first;                //   (window rows outside the unit disk) are never loaded
     prm.out = static_cast<float*>(d_out);
     prm.out2 = static_cast<float*>(d_out2);
     prm.w = d_w;
