@@ -643,3 +643,18 @@ def test_download_as_f64_multi_chunk(torch):
     np.testing.assert_array_equal(got, t.cpu().numpy().astype(np.float64))
     small = torch.arange(7, device="cuda", dtype=torch.float32).reshape(7, 1)
     np.testing.assert_array_equal(_host_f64(small), np.arange(7, dtype=np.float64).reshape(7, 1))
+
+
+@pytest.mark.parametrize("n_max,k", [(0, 1), (1, 2), (2, 3), (4, 5), (6, 16), (8, 17), (12, 128)])
+def test_map_window_sizes_vs_oracle(api, n_max, k):
+    """Every window size runs on the tensor-core map: 1-pixel and odd windows, one / several 16-tap groups,
+    the 128-px maximum (two basis k-blocks per window row)."""
+    rng = np.random.default_rng(k)
+    shape = (k + 3, 140 + k) if k < 100 else (131, 300)
+    img = rng.random(shape).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        z = api.ZPs(n_max, k)
+    n, m, v = zo.zernike_basis(n_max, k)
+    ref = zo.moment_map_fft(img.astype(np.float64), v, n)
+    fp32_close(z.transform(img).data, ref)
