@@ -218,6 +218,12 @@ def test_no_silent_cpu_fallback():
     handle = ctypes.c_void_p()
     rc = _lib.load().zb200_plan_create(4, 8, ctypes.byref(handle))
     assert rc == _lib.ENODEV and "no CPU fallback" in _lib.last_error()
+    # the rows either side of the path (peak detection, PCA) refuse to run without the device as well
+    from motif_learn_b200.features import local_max, pca
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        local_max(np.zeros((16, 16), dtype=np.float32), 2.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pca(np.zeros((30, 4), dtype=np.float32), 2)
 
 
 # ---- basis arithmetic (the code the CUDA generator runs) via the host harness -------------------
