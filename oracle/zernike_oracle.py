@@ -22,6 +22,13 @@ versions unpinned in pyproject.toml:14-22; this image: numpy 2.3.5, scipy
 (pocketfft), ``scipy.special.factorial``, ``numpy.linalg.norm``.  The oracle
 calls the same library entry points for the same steps so that the
 ``cpu_baseline`` it provides is the reference's own CPU algorithm.
+
+"Next" rows: ``render_atoms`` and ``pca`` are pinned against the live reference
+(tests/golden/render.npz, pca.npz).  ``local_max`` is pinned only in part: its
+suppression step is the reference's own ``filter_peaks_by_distance`` run live
+(tests/golden/peaks.npz), but the candidate step restates scikit-image's
+``peak_local_max`` from its published algorithm -- scikit-image is absent from
+this image and unpinned in the reference: PARITY UNPINNED for that step.
 """
 from __future__ import annotations
 
@@ -34,7 +41,7 @@ __all__ = [
     "project_patches", "moment_map_fft", "moment_map_direct", "valid_mask",
     "complex_matrix", "to_complex", "to_real", "normalize", "select_indices",
     "rotate", "rot_weights", "rot_maps", "mirror_map", "clear_border",
-    "extract_patches", "render_atoms",
+    "extract_patches", "render_atoms", "peak_local_max_md1", "filter_peaks_by_distance", "local_max", "pca",
 ]
 
 
