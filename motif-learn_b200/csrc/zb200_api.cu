@@ -94,6 +94,7 @@ extern "C" int zb200_mode_table(int n_max, int32_t* h_n, int32_t* h_m) {
 extern "C" void zb200_plan_destroy(zb200_plan* p) {
     if (!p) return;
     cudaFree(p->basis64);
+    cudaFree(p->d_kmask);
     cudaFree(p->d_n);
     cudaFree(p->d_m);
     free_operand(p->real);
@@ -172,6 +173,17 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
         cudaGetLastError();
+    }
+    {
+        // 8-tap K steps that touch the unit disk, per 32-tap k-block (same rule as above)
+        const int k = size, nkb = p->k_pad / 32;
+        std::vector<unsigned char> km((size_t)nkb, 0);
+        for (int e = 0; e < p->kk; ++e) {
+            const double y = k > 1 ? -1.0 + 2.0 * (e / k) / (k - 1) : 0.0, x = k > 1 ? -1.0 + 2.0 * (e % k) / (k - 1) : 0.0;
+            if (x * x + y * y <= 1.0 + 1e-9) km[e / 32] |= (unsigned char)(1u << ((e % 32) / 8));
+        }
+        ZB_PLAN_CUDA(cudaMalloc(&p->d_kmask, (size_t)nkb));
+        ZB_PLAN_CUDA(cudaMemcpy(p->d_kmask, km.data(), (size_t)nkb, cudaMemcpyHostToDevice));
     }
     ZB_PLAN_CUDA(cudaMalloc(&p->basis64, sizeof(double) * (size_t)p->n_modes * p->kk));
     ZB_PLAN_CUDA(cudaMalloc(&p->d_n, sizeof(int32_t) * p->n_modes));

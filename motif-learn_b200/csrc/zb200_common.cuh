@@ -103,6 +103,7 @@ struct zb200_plan {
     int kk = 0;           // k*k
     int k_pad = 0;        // kk rounded up to 32
     int kb_first = 0, kb_last = 0;   // 32-tap k-blocks [kb_first, kb_last) contain every tap inside the unit disk
+    unsigned char* d_kmask = nullptr;   // [k_pad/32] bit j = taps [8j, 8j+8) of the k-block touch the unit disk
     int device = 0;
     int sm_count = 0;
     int cc_major = 0;

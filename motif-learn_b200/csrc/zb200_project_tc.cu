@@ -55,6 +55,8 @@ struct Params {
     int n_tiles;          // ceil(n_patches / (128*subtiles))
     int subtiles;         // 1 or 2 accumulators (128 patches each) per tile
     int k_blocks;         // 32-tap k-blocks that hold taps inside the unit disk (window rows entirely outside are skipped)
+    const unsigned char* kmask;   // per k-block (absolute index): bit j = taps [8j, 8j+8) of the block touch the unit disk
+                          //   (the tf32x3 issuer skips the MMAs of all-zero K steps: 16 % of them at k = 64)
     int kb0;              // first of them: k-block kb of the loops is taps [(kb0 + kb) * 32, +32)
     int n_pad;            // UMMA N (operand rows, multiple of 16)
     int n_cols;           // meaningful accumulator columns
@@ -498,7 +500,9 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         const int kb_end = min(p.k_blocks, (c + 1) * p.chunk_kb);
                         const uint32_t d0 = tmem_base + (uint32_t)(buf * p.subtiles * p.n_pad);
                         const int kb_begin = c * p.chunk_kb;
+                        uint32_t acc_run = 0u;                       // 0 until the chunk's first MMA has been issued
                         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                            const uint32_t km = __ldg(p.kmask + p.kb0 + kb);      // issued before the waits
                             const int lb = (int)(it & lo_mask);
                             const uint32_t lo_ph = (it >> lo_shift) & 1u;
                             if (kPair) {
@@ -516,22 +520,19 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                             const uint32_t bhl = b_lo0 + (uint32_t)sb * b_step;
                             const uint32_t bcl = bhl + (bop_bytes >> 4);
                             const uint32_t a0 = lo_base + (uint32_t)(lb * p.subtiles) * kBlockK;
-                            const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
                             // Xhi.Bhi (tf32; the tensor core truncates the raw X itself) and the bf16 correction
                             // Xlo.Bhi + Xhi.Blo, for the 4 K-steps of the k-block and each sub-tile
                             if constexpr (kPair) {
 #pragma unroll
                                 for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-                                    umma_tf32_2(d0, desc_from_lo(xl + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc, k4 ? 1u : acc0);
+                                    if (!((km >> k4) & 1u)) continue;           // 8 taps outside the unit disk: basis all zero
+                                    umma_tf32_2(d0, desc_from_lo(xl + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc, acc_run);
                                     umma_bf16_ts_2(d0, a0 + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
-                                }
-                                if (p.subtiles == 2) {
-#pragma unroll
-                                    for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-                                        umma_tf32_2(d0 + p.n_pad, desc_from_lo(xl + 1024 + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc,
-                                                    k4 ? 1u : acc0);
+                                    if (p.subtiles == 2) {
+                                        umma_tf32_2(d0 + p.n_pad, desc_from_lo(xl + 1024 + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc, acc_run);
                                         umma_bf16_ts_2(d0 + p.n_pad, a0 + kBlockK + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
                                     }
+                                    acc_run = 1u;
                                 }
                                 umma_commit_2mc(&empty[s], 3);
                                 umma_commit_2mc(&bempty[sb], 3);
@@ -543,17 +544,15 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                             }
 #pragma unroll
                             for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-                                umma_tf32(d0, desc_from_lo(xl + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc, k4 ? 1u : acc0);
+                                if (!((km >> k4) & 1u)) continue;               // 8 taps outside the unit disk: basis all zero
+                                umma_tf32(d0, desc_from_lo(xl + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc, acc_run);
                                 if (!(ZB200_TC3_PROF && (p.dbg & 1))) umma_bf16_ts(d0, a0 + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
-                            }
-                            if (p.subtiles == 2) {
-#pragma unroll
-                                for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-                                    umma_tf32(d0 + p.n_pad, desc_from_lo(xl + 1024 + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc,
-                                              k4 ? 1u : acc0);
+                                if (p.subtiles == 2) {
+                                    umma_tf32(d0 + p.n_pad, desc_from_lo(xl + 1024 + 2 * k4), desc_from_lo(bhl + 2 * k4), idesc, acc_run);
                                     if (!(ZB200_TC3_PROF && (p.dbg & 1)))
                                         umma_bf16_ts(d0 + p.n_pad, a0 + kBlockK + k4 * kUmmaK, desc_from_lo(bcl + 2 * k4), idesc_c, 1u);
                                 }
+                                acc_run = 1u;
                             }
                             if (prof) w2 += (unsigned long long)(clock64() - t_issue);
                             const long long t_commit = prof ? clock64() : 0;
@@ -909,6 +908,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.n_patches = n;
     prm.n_pad = op.rows_pad;
     prm.n_cols = op.rows;
+    prm.kmask = p->d_kmask;
     prm.kb0 = p->kb_first;                                  // leading / trailing k-blocks with an all-zero basis
     prm.k_blocks = p->kb_last - p->kb_first;                //   (window rows outside the unit disk) are never loaded
     prm.out = static_cast<float*>(d_out);
