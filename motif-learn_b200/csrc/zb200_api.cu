@@ -182,8 +182,10 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
             const double y = k > 1 ? -1.0 + 2.0 * (e / k) / (k - 1) : 0.0, x = k > 1 ? -1.0 + 2.0 * (e % k) / (k - 1) : 0.0;
             if (x * x + y * y <= 1.0 + 1e-9) km[e / 32] |= (unsigned char)(1u << ((e % 32) / 8));
         }
-        ZB_PLAN_CUDA(cudaMalloc(&p->d_kmask, (size_t)nkb));
+        // second half of the allocation: all steps on (ZB200_TC_KSKIP=0, A/B measurements)
+        ZB_PLAN_CUDA(cudaMalloc(&p->d_kmask, 2 * (size_t)nkb));
         ZB_PLAN_CUDA(cudaMemcpy(p->d_kmask, km.data(), (size_t)nkb, cudaMemcpyHostToDevice));
+        ZB_PLAN_CUDA(cudaMemset(p->d_kmask + nkb, 0x0F, (size_t)nkb));
     }
     ZB_PLAN_CUDA(cudaMalloc(&p->basis64, sizeof(double) * (size_t)p->n_modes * p->kk));
     ZB_PLAN_CUDA(cudaMalloc(&p->d_n, sizeof(int32_t) * p->n_modes));

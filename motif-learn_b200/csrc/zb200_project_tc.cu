@@ -909,6 +909,9 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.n_pad = op.rows_pad;
     prm.n_cols = op.rows;
     prm.kmask = p->d_kmask;
+    if (const char* e = getenv("ZB200_TC_KSKIP")) {
+        if (atoi(e) == 0) prm.kmask = p->d_kmask + p->k_pad / 32;      // every K step issued
+    }
     prm.kb0 = p->kb_first;                                  // leading / trailing k-blocks with an all-zero basis
     prm.k_blocks = p->kb_last - p->kb_first;                //   (window rows outside the unit disk) are never loaded
     prm.out = static_cast<float*>(d_out);
