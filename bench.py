@@ -33,9 +33,9 @@ MAP_WINDOW = 48
 FOLDS = [2, 3, 4, 6]
 # DRAM bytes per launch of the projection kernel at the default batch, from the committed ncu
 # captures (profiles/r01_prof_tc3_raw.csv, r01_prof_tc1_raw.csv): read + write
-NCU_TRAFFIC = {"tf32x3": 4.198504e9 + 45.023e6, "tf32": 4.180921e9 + 55.155e6}
+NCU_TRAFFIC = {"tf32x3": 4.198750e9 + 43.819e6, "tf32": 4.181859e9 + 53.549e6}
 # dense-map kernels at 2048^2 (profiles/r01_prof_map_raw.csv, r01_prof_maph_raw.csv): read + write
-NCU_TRAFFIC_MAP = {"tf32x3": 136.456e6 + 48.684e6, "f16x3": 136.990e6 + 45.496e6}
+NCU_TRAFFIC_MAP = {"tf32x3": 136.456e6 + 48.684e6, "f16x3": 136.000e6 + 47.324e6}
 PREC_NAMES = {0: "fp32", 1: "tf32", 2: "tf32x3", 3: "f16", 4: "f16x3"}
 
 
