@@ -78,6 +78,8 @@ struct MapParams {
     int dbg;             // ZB200_MAP_DEBUG experiment bits (results wrong when set)
     // score tables live in the kernel parameters: with the column loops unrolled every weight is a
     // constant-bank operand of its FFMA (no loads in the epilogue)
+    unsigned char step_mask[kMaxWindow + 1];   // per window-row step: bit g = 16-tap group g has taps inside the disk in
+                                      //   window row a_first+s or a_first+s-1 (all-zero basis otherwise: MMAs skipped)
     float selw[128];                  // 1 for modes that enter the norm (unselect()), else 0
     float wts[kFoldsPerLaunch][128];  // construct_rot_maps_matrix rows, zero on unselected / padding modes
 };
@@ -206,12 +208,13 @@ struct IssueCtx {
 // b1|b2) are b_ring_step apart.
 template <int G, bool kX3, int kMode>
 __device__ __forceinline__ void issue_step(const IssueCtx& c, uint32_t d, int n_pad, uint32_t a0, uint32_t bb,
-                                           uint32_t acc_first, bool split_first) {
+                                           uint32_t acc_first, bool split_first, uint32_t mask) {
     constexpr int n_bops = kX3 ? 2 : 1;
     const uint32_t dd = kMode == 1 ? d + (uint32_t)n_pad : d;
     const uint32_t idesc = kMode == 0 ? c.idesc2 : c.idesc1;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
+        if (!((mask >> g) & 1u)) continue;                                          // group outside the disk in both rows
         const uint32_t ag = a0 + 4u * g;                                            // 16 taps = 4 units of 16 B
         const uint32_t bg = bb + (uint32_t)((g / 4) * n_bops) * c.b_ring_step + 2u * (uint32_t)(g % 4);   // 32 B per group
         if (g == 0) {
@@ -267,12 +270,15 @@ __device__ __forceinline__ void issue_tiles(const MapParams& p, const IssueCtx& 
                 tc_fence_after();
                 if (s == 0) {
                     // only output row y0 (upper accumulator half) has a window row on this frame row
-                    issue_step<G, kX3, 1>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sj * c.b_slot_step, 0u, false);
+                    issue_step<G, kX3, 1>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sj * c.b_slot_step, 0u, false, 0xFFu);
                 } else if (s == p.n_rows) {
-                    issue_step<G, kX3, 2>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sprev * c.b_slot_step, s == 1 ? 0u : acc, false);
+                    issue_step<G, kX3, 2>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sprev * c.b_slot_step, s == 1 ? 0u : acc, false,
+                                          s == 1 ? 0xFFu : (uint32_t)p.step_mask[s]);
                 } else {
                     // slots (sprev, sprev + 1) hold window rows (a-1, a); slot S mirrors slot 0 for the wrap-around
-                    issue_step<G, kX3, 0>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sprev * c.b_slot_step, acc, s == 1);
+                    // the group-0 MMA carries the accumulate flag of a chunk's first step: skip nothing there
+                    issue_step<G, kX3, 0>(c, d, p.n_pad, a0, c.b_lo0 + (uint32_t)sprev * c.b_slot_step, acc, s == 1,
+                                          (acc && s != 1) ? (uint32_t)p.step_mask[s] : 0xFFu);
                 }
                 acc = 1u;
                 umma_commit(&c.img_empty[si]);
@@ -724,6 +730,15 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
     prm.n_groups = mh.n_groups;
     prm.kb_per_row = (mh.n_groups + 3) / 4;
     prm.a_first = mh.a_first; prm.n_rows = mh.a_end - mh.a_first;
+    {
+        const char* e = getenv("ZB200_MAP_GSKIP");
+        const bool skip = !(e && atoi(e) == 0);
+        for (int st = 0; st <= prm.n_rows; ++st) {
+            const unsigned up = st < prm.n_rows ? mh.act[mh.a_first + st] : 0u;
+            const unsigned lo = st >= 1 ? mh.act[mh.a_first + st - 1] : 0u;
+            prm.step_mask[st] = skip ? (unsigned char)((up | lo) & 0xFFu) : (unsigned char)0xFF;
+        }
+    }
     const int nq = 128 + 4 * mh.n_groups - 2;                     // 16-byte units one staged row spans
     prm.n_box = (int)ceil_div(nq, 64);
     prm.bw_q = round_up((int)ceil_div(nq, prm.n_box), 8);          // TMA destinations stay 128-B aligned
