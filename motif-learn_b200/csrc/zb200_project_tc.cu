@@ -925,6 +925,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                          : (out_kind == ZB200_OUT_REAL ? p->n_modes
                                                        : (out_kind == ZB200_OUT_COMPLEX ? 2 * p->n_complex : p->n_complex));
     prm.chunk_kb = 8;
+    if (const char* e = getenv("ZB200_TC_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) prm.chunk_kb = v; }
     if (gsrc) {
         prm.gather = 1;
         prm.g_img = gsrc->img;
