@@ -658,3 +658,33 @@ def test_map_window_sizes_vs_oracle(api, n_max, k):
     n, m, v = zo.zernike_basis(n_max, k)
     ref = zo.moment_map_fft(img.astype(np.float64), v, n)
     fp32_close(z.transform(img).data, ref)
+
+
+def test_integration_stubs_bind_the_c_abi_directly(torch):
+    """The two ctypes stubs of INTEGRATION.md section 2 (what a maintainer of the reference would add), run as
+    written against the shared library alone: patch route through zb200_project_patches_host, image route through
+    zb200_moment_map_f32 + zb200_download_as_f64."""
+    import ctypes as C
+    from motif_learn_b200 import _lib as ours
+    lib = C.CDLL(ours.LIB_PATH)
+    lib.zb200_plan_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.zb200_project_patches_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    lib.zb200_moment_map_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.zb200_download_as_f64.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.zb200_last_error.restype = C.c_char_p
+    rng = np.random.default_rng(5)
+    n, m, v = zo.zernike_basis(8, 24)
+    plan = C.c_void_p()
+    assert lib.zb200_plan_create(8, 24, C.byref(plan)) == 0, lib.zb200_last_error()
+    x = rng.random((300, 24, 24)).astype(np.float32)
+    out = np.empty((300, len(n)), dtype=np.float64)
+    assert lib.zb200_project_patches_host(plan, x.ctypes.data, 300, 2, out.ctypes.data) == 0, lib.zb200_last_error()
+    fp32_close(out, zo.project_patches(x.astype(np.float64), v))
+    image = rng.random((70, 90)).astype(np.float32)
+    img = torch.from_numpy(image).cuda()
+    dev = torch.empty((len(n), 70, 90), dtype=torch.float32, device="cuda")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.zb200_moment_map_f32(plan, img.data_ptr(), 70, 90, 0, 70, 4, dev.data_ptr(), stream) == 0, lib.zb200_last_error()
+    host = np.empty((len(n), 70, 90), dtype=np.float64)
+    assert lib.zb200_download_as_f64(dev.data_ptr(), dev.numel(), host.ctypes.data, stream) == 0
+    fp32_close(host, zo.moment_map_fft(image.astype(np.float64), v, n))
