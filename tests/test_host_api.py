@@ -258,3 +258,23 @@ def test_basis_recurrence_is_closer_to_exact_than_reference(basis_tool, tmp_path
     e_got = max(np.abs(got[:, r, c] - ex[:, i]).max() for i, (r, c) in enumerate(pts))
     e_ref = max(np.abs(ref[:, r, c] - ex[:, i]).max() for i, (r, c) in enumerate(pts))
     assert e_got < 1e-12 < e_ref
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/zernike_b200.h is a C header (no C++/torch types cross the boundary): a C99 translation unit that
+    calls the meta entry points compiles with -pedantic, links against the shared library and runs."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "zernike_b200.h"\n'
+                   'int main(void) { int32_t n[3], m[3];\n'
+                   '  if (zb200_abi_version() != ZB200_ABI_VERSION) return 1;\n'
+                   '  if (zb200_num_modes(12) != 91 || zb200_num_complex_modes(12) != 49) return 2;\n'
+                   '  if (zb200_mode_table(1, n, m) != 3 || m[1] != -1 || m[2] != 1) return 3;\n'
+                   '  printf("ok\\n"); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-lzernike_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True)
+    assert out.stdout.strip() == "ok"
