@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the B200 Zernike hot path (one JSON line on stdout, rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload patches|map] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload patches|map|map4k|c3|c5] [--impl reference]
 
-Workloads (BASELINE.json metric: "Zernike patches/sec (n_max=12, 64px) and symmetry-map
-Mpix/sec"):
-  patches  one step = ZPs(n_max=12, size=64) moments of a batch of synthetic 64x64 lattice
-           patches resident in HBM (batch >> L2, so every step streams from HBM)  [default]
-  map      one step = fused symmetry map (n-folds 2,3,4,6) of a 2048x2048 synthetic lattice
-           frame, n_max=12, 48-px window (BASELINE configs[1]); L2 is flushed between steps
-The default line carries the other workload under "also" so both headline numbers appear.
-Multi-GPU (torchrun): every rank runs the same step on its own shard (weak scaling), timed
-as max over ranks between barriers.
+BASELINE.json metric: "Zernike patches/sec (n_max=12, 64px) and symmetry-map Mpix/sec at 1/2/4/8 B200".
+Workloads (one step = one pass of the hot path over one batch of synthetic input resident in HBM):
+  patches  metric shape: ZPs(12, 64) real moments of 262 144 lattice patches per GPU (4.3 GB >> L2)     [default]
+  map      BASELINE configs[1]: fused symmetry map (folds 2,3,4,6) of a 2048^2 frame, 48-px window, one frame per GPU
+  map4k    BASELINE configs[3]: ONE 4096^2 frame with defects, 64-px window, output row bands over the GPUs
+  c3       BASELINE configs[2]: complex ZPs n_max=20 of 1 Mi 64x64 patches, patch ranges over the GPUs
+  c5       BASELINE configs[4]: 256 frames 2048^2: local_max -> KeyPoints -> |Zc| features, frames over the GPUs
+The line of the chosen workload carries every other one under "also" (a list), so one run records all five.
+
+Multi-GPU (torchrun, one rank per GPU): every rank works on its own shard; the timed step INCLUDES the final
+feature / score gather to every rank over NVLink -- `value` is with the gather, the
+`gather` object keeps the no-gather figure beside it.  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.  Every workload asserts parity of a sample of the timed batch's
+results against the CPU oracle before it reports a number.
 """
 from __future__ import annotations
 
@@ -28,35 +33,48 @@ sys.path.insert(0, ROOT)
 
 N_MAX = 12
 PATCH = 64
-MAP_SIZE = 2048
-MAP_WINDOW = 48
 FOLDS = [2, 3, 4, 6]
-# DRAM bytes per launch of the projection kernel at the default batch, from the committed ncu
-# captures (profiles/r01_prof_tc3_raw.csv, r01_prof_tc1_raw.csv): read + write
-NCU_TRAFFIC = {"tf32x3": 4.198750e9 + 43.819e6, "tf32": 4.181859e9 + 53.549e6}
-# dense-map kernels at 2048^2 (profiles/r01_prof_map_raw.csv, r01_prof_maph_raw.csv): read + write
-NCU_TRAFFIC_MAP = {"tf32x3": 136.456e6 + 48.684e6, "f16x3": 136.000e6 + 47.324e6}
+C3_NMAX, C3_TOTAL = 20, 1 << 20
+C5_FRAMES, C5_SIZE = 256, 2048
+PEAK_MIN_DISTANCE, PEAK_THRESHOLD = 5.0, 0.3
+WORKLOADS = ["patches", "map", "map4k", "c3", "c5"]
 PREC_NAMES = {0: "fp32", 1: "tf32", 2: "tf32x3", 3: "f16", 4: "f16x3"}
+DTYPES = {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)", "f16": "f16", "f16x3": "f16x3(f32-grade)"}
+# DRAM bytes per launch from the committed ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_TRAFFIC = {"tf32x3": 4.198750e9 + 43.819e6, "tf32": 4.181859e9 + 53.549e6}           # 262 144 patches
+NCU_TRAFFIC_MAP = {"tf32x3": 136.456e6 + 48.684e6, "f16x3": 136.000e6 + 47.324e6}        # 2048^2, k=48
 
 
 def peaks():
+    out = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
-                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+        out = {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+               "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    # tf32 / fp32-SIMT peaks measured by this repo the same way (scripts/measure_peaks.py -> profiles/peaks_tf32.json)
+    out["tf32_tflops"], out["tf32_source"] = out["bf16_tflops"] / 2.0, "bf16 / 2 (assumed)"
+    mine = os.path.join(ROOT, "profiles", "peaks_tf32.json")
+    if os.path.exists(mine):
+        with open(mine) as f:
+            q = json.load(f)
+        if q.get("tf32_tflops"):
+            out["tf32_tflops"], out["tf32_source"] = float(q["tf32_tflops"]), "profiles/peaks_tf32.json (measured)"
+        if q.get("fp32_simt_tflops"):
+            out["fp32_simt_tflops"] = float(q["fp32_simt_tflops"])
+    return out
 
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.002):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
+        self._ready = threading.Event()
         self._thread = None
 
     def _run(self):
@@ -74,6 +92,7 @@ class ClockSampler:
             }
             get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons",
                                   getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+            self._ready.set()
             while not self._stop.is_set():
                 self.samples.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                 if get_reasons is not None:
@@ -84,10 +103,13 @@ class ClockSampler:
                 time.sleep(self.period)
         except Exception as exc:  # NVML missing: report that rather than fail the bench
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+        finally:
+            self._ready.set()
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
+        self._ready.wait(timeout=5)          # NVML is initialised before the timed region starts
         return self
 
     def __exit__(self, *a):
@@ -96,10 +118,53 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_mhz_min": min(self.samples) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# --------------------------------------------------------------------------- reference arm
+def physical_gpu_index(local: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except (ValueError, IndexError):
+            pass
+    return local
+
+
+# --------------------------------------------------------------------------- shared configs (both arms print the same dict)
+def workload_config(name: str, world: int):
+    if name == "patches":
+        return {"workload": f"patches n_max={N_MAX} size={PATCH} (metric shape)", "modes": 91, "batch_per_gpu": 262144,
+                "l2": "input batch larger than L2 (no flush needed)",
+                "parallelism": f"patch shards x{world}" + (", final all-gather of the (N,91) moments over NVLink in the timed step" if world > 1 else "")}
+    if name == "map":
+        return {"workload": f"symmetry map 2048x2048 n_max={N_MAX} window=48 folds={FOLDS} (BASELINE configs[1])",
+                "l2": "256 MiB scratch write between steps", "parallelism": f"one frame per GPU x{world}, no collective"}
+    if name == "map4k":
+        return {"workload": f"symmetry map 4096x4096 with defects n_max={N_MAX} window=64 folds={FOLDS} (BASELINE configs[3])",
+                "l2": "256 MiB scratch write between steps",
+                "parallelism": f"one frame, {world} row bands with halo rows from the replicated frame"
+                               + (", score bands all-gathered over NVLink in the timed step" if world > 1 else "")}
+    if name == "c3":
+        return {"workload": f"complex ZPs n_max={C3_NMAX} size={PATCH}, {C3_TOTAL} patches (BASELINE configs[2])", "modes": 231,
+                "complex_modes": 121, "l2": "input larger than L2",
+                "parallelism": f"{C3_TOTAL} patches in {world} contiguous shards"
+                               + (", final all-gather of the complex64 (N,121) features in the timed step" if world > 1 else "")}
+    if name == "c5":
+        return {"workload": f"{C5_FRAMES} frames {C5_SIZE}x{C5_SIZE}: local_max -> KeyPoints -> ZPs({N_MAX},{PATCH}) |Zc| "
+                            f"(BASELINE configs[4])", "l2": "frame series larger than L2",
+                "parallelism": f"{C5_FRAMES} frames in {world} shards"
+                               + (", ragged all-gather of the (P,49) features in the timed step" if world > 1 else "")}
+    raise ValueError(name)
+
+
+METRICS = {"patches": ("zernike_patches_per_sec", "patches/s"), "map": ("symmetry_map_mpix_per_sec", "Mpix/s"),
+           "map4k": ("symmetry_map_mpix_per_sec", "Mpix/s"), "c3": ("zernike_patches_per_sec", "patches/s"),
+           "c5": ("zernike_patches_per_sec", "patches/s")}
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle port of the reference algorithm)
 def cpu_threads():
     """Give the BLAS behind numpy.dot every host core (torchrun exports OMP_NUM_THREADS=1) and
     return the thread count actually in use."""
@@ -112,34 +177,60 @@ def cpu_threads():
         return 1
 
 
-def cpu_patches(n_sample: int, repeats: int):
-    """The reference's CPU algorithm for the patch path (numpy.dot in float64, _zps.py:146-157),
-    through the oracle port, on n_sample patches of the bench batch.  Returns patches/s (best)."""
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
     import zernike_oracle as zo
-    from motif_learn_b200.datasets import honeycomb_image
-    img, pts = honeycomb_image(1024, bond=12.0, seed=0)
-    kept = zo.clear_border(pts, img.shape, PATCH)
-    base = zo.extract_patches(img, kept, PATCH)
-    reps = -(-n_sample // len(base))
-    sample = np.concatenate([base] * reps)[:n_sample]
-    _, _, basis = zo.zernike_basis(N_MAX, PATCH)
+    return zo
+
+
+_cpu_cache = {}
+
+
+def cpu_patch_sample(n_sample: int, size: int = PATCH):
+    """n_sample float32 lattice patches (the bench batch's generator at a smaller frame)."""
+    key = ("patches", n_sample, size)
+    if key not in _cpu_cache:
+        import numpy as np
+        zo = _oracle()
+        from motif_learn_b200.datasets import honeycomb_image
+        img, pts = honeycomb_image(1024, bond=12.0, seed=0)
+        base = zo.extract_patches(img, zo.clear_border(pts, img.shape, size), size)
+        reps = -(-n_sample // len(base))
+        _cpu_cache[key] = np.concatenate([base] * reps)[:n_sample]
+    return _cpu_cache[key]
+
+
+def cpu_patches(n_sample: int, repeats: int, n_max: int = N_MAX, kind: str = "real"):
+    """The reference's CPU algorithm for the patch path (numpy.dot in float64 incl. the float32->float64 cast and
+    the zmoments constructor copy, _zps.py:146-157, _zmoments.py:269-277; kind='complex': + to_complex,
+    _zmoments.py:300-316), through the oracle port.  Returns (patches/s best, [seconds])."""
+    import numpy as np
+    zo = _oracle()
+    sample = cpu_patch_sample(n_sample)
+    key = ("basis", n_max, PATCH)
+    if key not in _cpu_cache:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _cpu_cache[key] = zo.zernike_basis(n_max, PATCH)
+    n, m, basis = _cpu_cache[key]
     zo.project_patches(sample[:256], basis)
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
-        zo.project_patches(sample, basis)
+        z = zo.project_patches(sample, basis)
+        z = z[:, np.lexsort((m, n))]                      # the reference's constructor always copies
+        if kind == "complex":
+            zo.to_complex(z, n, m)
         times.append(time.perf_counter() - t0)
     return n_sample / min(times), times
 
 
-def cpu_map(size: int, repeats: int = 1, window: int = MAP_WINDOW):
+def cpu_map(size: int, repeats: int = 1, window: int = 48):
     """The reference's CPU algorithm for the map path (scipy fftconvolve per mode + rot_maps,
-    _zps.py:159-193, _zmoments.py:420-462) through the oracle port on a size x size crop."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    _zps.py:159-193, _zmoments.py:420-462) through the oracle port on a size x size frame."""
     import numpy as np
-    import zernike_oracle as zo
+    zo = _oracle()
     from motif_learn_b200.datasets import honeycomb_image
     img, _ = honeycomb_image(size, bond=12.0, seed=0)
     n, m, basis = zo.zernike_basis(N_MAX, window)
@@ -153,57 +244,120 @@ def cpu_map(size: int, repeats: int = 1, window: int = MAP_WINDOW):
     return size * size / 1e6 / best, best
 
 
+def cpu_c5(size: int = 1024):
+    """Reference pipeline of one frame on the host: local_max -> clear_border -> extract_patches -> numpy.dot ->
+    to_complex -> abs (oracle port; _local_max_v2.py:46-66, _keypoint.py:44-78, _zps.py:146-157)."""
+    import numpy as np
+    zo = _oracle()
+    from motif_learn_b200.datasets import honeycomb_image
+    img, _ = honeycomb_image(size, bond=12.0, seed=0, jitter=0.3, noise=0.01)
+    n, m, basis = zo.zernike_basis(N_MAX, PATCH)
+    t0 = time.perf_counter()
+    pk = zo.local_max(img, PEAK_MIN_DISTANCE, PEAK_THRESHOLD)
+    kept = zo.clear_border(pk, img.shape, PATCH)
+    patches = zo.extract_patches(img, kept, PATCH)
+    z = zo.project_patches(patches, basis)
+    np.abs(zo.to_complex(z, n, m)[0])
+    dt = time.perf_counter() - t0
+    return len(kept) / dt, dt, len(kept)
+
+
+def cpu_baseline_for(name: str, cores: int):
+    if name == "patches":
+        v, times = cpu_patches(20000, 8)
+        return {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
+                "sample": "20000 float32 64x64 lattice patches, numpy.dot float64 (reference algorithm _zps.py:146-157 "
+                          f"+ zmoments ctor copy, via the oracle port), best of {len(times)}"}
+    if name == "c3":
+        v, times = cpu_patches(20000, 4, n_max=C3_NMAX, kind="complex")
+        return {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
+                "sample": f"20000 float32 64x64 patches, n_max={C3_NMAX}: numpy.dot float64 + to_complex, best of {len(times)}"}
+    if name == "c5":
+        v, dt, cnt = cpu_c5(1024)
+        return {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
+                "sample": f"one 1024x1024 frame ({cnt} kept peaks): local_max + extract_patches + numpy.dot + to_complex + abs, {dt:.2f} s"}
+    window = 64 if name == "map4k" else 48
+    size = 384 if name == "map" else 512
+    mv, dt = cpu_map(size, window=window)
+    return {"value": mv, "unit": "Mpix/s", "cores": 1, "kind": "port",
+            "sample": f"{size}x{size} frame, window {window}: 91 scipy.fftconvolve (1 thread, reference algorithm "
+                      f"_zps.py:159-193 via the oracle port) + rot_maps, {dt:.1f} s"}
+
+
 def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm of the chosen workload on the host cores of rank 0, each step a
+    bounded sample of the workload (the oracle port; the Python reference itself does not exist on the GPU box)."""
     if rank != 0:
         return
     cores = cpu_threads()
-    if args.workload == "patches":
+    name = args.workload
+    metric, unit = METRICS[name]
+    per_step, units = [], 0
+    if name in ("patches", "c3"):
         n_sample = 20000
-        per_step = []
+        nm, kind = (N_MAX, "real") if name == "patches" else (C3_NMAX, "complex")
         for _ in range(args.warmup):
-            cpu_patches(n_sample, 1)
+            cpu_patches(n_sample, 1, nm, kind)
         for _ in range(args.steps):
-            v, t = cpu_patches(n_sample, 1)
+            _, t = cpu_patches(n_sample, 1, nm, kind)
             per_step.append(t[0])
-        total = sum(per_step)
-        value = n_sample * args.steps / total
-        line = {"metric": "zernike_patches_per_sec", "unit": "patches/s",
-                "config": {"workload": f"patches n_max={N_MAX} size={PATCH} (metric shape)", "modes": 91,
-                           "batch_per_step": n_sample, "precision": "f64 (numpy.dot)",
-                           "parallelism": "host cores of rank 0 (bounded sample of the same workload)"},
-                "sample": f"{n_sample} float32 64x64 lattice patches per step, numpy.dot float64 (reference algorithm)"}
+        units = n_sample
+        sample = f"{n_sample} float32 64x64 lattice patches per step, numpy.dot float64" + (" + to_complex" if kind == "complex" else "")
+    elif name == "c5":
+        for _ in range(min(args.warmup, 1)):
+            cpu_c5(512)
+        steps = max(1, min(args.steps, 5))
+        for _ in range(steps):
+            _, dt, cnt = cpu_c5(1024)
+            per_step.append(dt)
+            units = cnt
+        sample = f"one 1024x1024 frame per step ({units} peaks): local_max + extract_patches + numpy.dot + |to_complex|"
     else:
-        size = 512
-        window = 64 if args.workload == "map4k" else MAP_WINDOW
-        per_step = []
+        size, window = 512, (64 if name == "map4k" else 48)
         for _ in range(min(args.warmup, 1)):
             cpu_map(256, window=window)
         for _ in range(args.steps):
             _, dt = cpu_map(size, window=window)
             per_step.append(dt)
-        total = sum(per_step)
-        value = size * size * args.steps / 1e6 / total
-        line = {"metric": "symmetry_map_mpix_per_sec", "unit": "Mpix/s",
-                "config": {"workload": f"symmetry map n_max={N_MAX} window={window} folds={FOLDS}",
-                           "image": f"{size}x{size} crop of the {MAP_SIZE}x{MAP_SIZE} frame"},
-                "sample": f"{size}x{size} crop per step: 91 scipy.fftconvolve (1 thread) + rot_maps"}
-    line.update({"impl": "reference", "value": value, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                 "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                 "cpu_baseline": {"value": value, "unit": line["unit"], "cores": cores, "kind": "port",
-                                  "sample": line.pop("sample")},
-                 "e2e": {"value": value, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        units = size * size / 1e6
+        sample = f"{size}x{size} frame per step: 91 scipy.fftconvolve (1 thread) + rot_maps"
+        cores = 1
+    total = sum(per_step)
+    value = units * len(per_step) / total
+    line = {"metric": metric, "value": value, "unit": unit, "impl": "reference", "n_gpus": world, "steps": len(per_step),
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(per_step), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(name, world),
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------- our arm
-def flush_l2(torch, scratch):
-    scratch.zero_()            # > L2 capacity: evicts the previous step's lines
+# --------------------------------------------------------------------------- our arm: timing
+class Ctx:
+    def __init__(self, torch, dist, rank, world, local, args, pk):
+        self.torch, self.dist, self.rank, self.world, self.local, self.args, self.pk = torch, dist, rank, world, local, args, pk
+        self.gpu_index = physical_gpu_index(local)
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
 
 
-def timed(torch, dist, world, fn, steps, warmup, device_index, between=None):
-    """W warm-up steps, then exactly K timed steps with CUDA events on the launching stream,
-    barrier + synchronize on both sides, max over ranks.  Returns (ms_total, clocks, launches)."""
+def timed(ctx, fn, steps, warmup, between=None):
+    """W warm-up steps, then exactly K timed steps with CUDA events on the launching stream, barrier +
+    synchronize on both sides, max over ranks.  Returns (ms_total, clocks, launches)."""
+    torch, dist, world = ctx.torch, ctx.dist, ctx.world
     from motif_learn_b200 import _lib
     for _ in range(warmup):
         fn()
@@ -216,7 +370,7 @@ def timed(torch, dist, world, fn, steps, warmup, device_index, between=None):
     _lib.reset_launch_count()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    with ClockSampler(device_index) as clk:
+    with ClockSampler(ctx.gpu_index) as clk:
         for i in range(steps):
             ev0[i].record()
             fn()
@@ -231,179 +385,473 @@ def timed(torch, dist, world, fn, steps, warmup, device_index, between=None):
     # no L2 flush between steps: one interval over all K steps (launch gaps included);
     # with a flush between steps: sum of the per-step intervals (the flush is not the workload)
     ms = ev0[0].elapsed_time(ev1[-1]) if between is None else sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    return ms, clk.summary(), launches
+    return ctx.max_over_ranks(ms), clk.summary(), launches
 
 
-def bench_patches(torch, dist, rank, world, args, pk):
+def fp32_close(got, ref, what, rtol=1e-4, scale=1e-6):
+    """The parity gate of SURVEY.md 8d: allclose(rtol=1e-4, atol=1e-6 * max|ref|)."""
     import numpy as np
-    from motif_learn_b200 import _lib
-    from motif_learn_b200.datasets import honeycomb_image
-    from motif_learn_b200.features import ZPs, KeyPoints
-    dev = torch.cuda.current_device()
+    tol = scale * np.abs(ref).max()
+    bad = np.abs(got - ref) > tol + rtol * np.abs(ref)
+    if bad.any():
+        raise AssertionError(f"parity FAILED for {what}: {int(bad.sum())} of {bad.size} values outside rtol={rtol} "
+                             f"atol={scale}*max; max abs err {np.abs(got - ref).max():.3e}, max|ref| {np.abs(ref).max():.3e}")
+    return float(np.abs(got - ref).max() / np.abs(ref).max())
+
+
+def sample_rows(n: int, count: int = 4096):
+    """Row indices of a parity sample: first / middle (shard seam of a 2-GPU run) / last chunks."""
+    import numpy as np
+    c = min(count // 3, n // 3)
+    mid = n // 2 - c // 2
+    return np.concatenate([np.arange(0, c), np.arange(mid, mid + c), np.arange(n - c, n)])
+
+
+def make_patch_batch(ctx, n: int, seed: int):
+    """n device-resident 64x64 lattice patches: gathered (K2) at the atom sites of a 2048^2 frame, tiled to n."""
+    torch = ctx.torch
+    from motif_learn_b200.datasets import honeycomb_frame_gpu
+    from motif_learn_b200.features import KeyPoints
+    img, pts = honeycomb_frame_gpu(2048, bond=12.0, seed=seed)
+    base = KeyPoints(pts, img, PATCH).extract_patches()            # ~21 k patches, device-resident
+    reps = -(-n // base.shape[0])
+    out = torch.empty((n, PATCH, PATCH), dtype=torch.float32, device="cuda")
+    for r in range(reps):
+        lo = r * base.shape[0]
+        hi = min(n, lo + base.shape[0])
+        out[lo:hi] = base[: hi - lo]
+    return out
+
+
+def gather_report(ctx, ms_full, ms_nogather, steps, units_per_step, nbytes_in):
+    """What the K5 gather cost: both figures, whole job."""
+    return {"collective": "all_gather_into_tensor (NCCL over NVLink)", "in_timed_step": True,
+            "ms_per_step_with_gather": ms_full / steps, "ms_per_step_no_gather": ms_nogather / steps,
+            "ms_gather": (ms_full - ms_nogather) / steps, "value_no_gather": units_per_step * steps / (ms_nogather / 1e3),
+            "bytes_received_per_rank_per_step": nbytes_in}
+
+
+# --------------------------------------------------------------------------- patches (metric shape)
+def bench_patches(ctx):
+    import numpy as np
+    torch, args, pk, world = ctx.torch, ctx.args, ctx.pk, ctx.world
+    from motif_learn_b200.features import ZPs
+    from motif_learn_b200.parallel import gather_rows
+    zo = _oracle()
     zp = ZPs(N_MAX, PATCH, precision=args.precision)
     prec = PREC_NAMES[zp._precision_code()]
     n_modes = len(zp.n)
-
-    # synthetic input: patches gathered at the atom sites of lattice frames (K2), tiled to the batch
-    img, pts = honeycomb_image(2048, bond=12.0, seed=rank)
-    kp = KeyPoints(pts, torch.from_numpy(img).cuda(), PATCH)
-    base = kp.extract_patches()                                   # ~21 k patches, device-resident
     batch = args.batch
-    reps = -(-batch // base.shape[0])
-    patches = base.repeat(reps, 1, 1)[:batch].contiguous()        # batch*16 KiB >> 126 MB L2
-    del base
-    out_holder = {}
+    patches = make_patch_batch(ctx, batch, seed=ctx.rank)          # batch * 16 KiB >> 126 MB L2
+    gathered = torch.empty((world * batch, n_modes), dtype=torch.float32, device="cuda") if world > 1 else None
+    hold = {}
+
+    def compute():
+        hold["z"] = zp.transform(patches).data
 
     def step():
-        out_holder["z"] = zp.transform(patches).data
+        compute()
+        if world > 1:
+            gather_rows(hold["z"], out=gathered, sizes=[batch] * world)
 
-    ms, clocks, launches = timed(torch, dist, world, step, args.steps, args.warmup, dev)
-    value = batch * world * args.steps / (ms / 1e3)
+    # parity of the timed batch itself: a 4096-patch sample against the oracle (float64 numpy.dot)
+    compute()
+    rows = sample_rows(batch)
+    idx = torch.from_numpy(rows).cuda()
+    ref = zo.project_patches(patches[idx].cpu().numpy().astype(np.float64), zp.polynomials)
+    got = hold["z"][idx].double().cpu().numpy()
+    if prec == "tf32":
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        assert err <= 1e-3, f"parity FAILED (tf32 stated bound 1e-3*max): {err:.2e}"
+    else:
+        err = fp32_close(got, ref, "patches (metric shape)")
+    parity = {"sample": len(rows), "max_err_over_max": err,
+              "gate": "abs err <= 1e-3*max|ref| (tf32 fast mode)" if prec == "tf32" else "allclose(rtol=1e-4, atol=1e-6*max|ref|)"}
+
+    ms, clocks, launches = timed(ctx, step, args.steps, args.warmup)
+    total = batch * world
+    value = total * args.steps / (ms / 1e3)
+    gather = None
+    if world > 1:
+        ms_ng, _, _ = timed(ctx, compute, args.steps, 1)
+        gather = gather_report(ctx, ms, ms_ng, args.steps, total, (world - 1) * batch * n_modes * 4)
+        assert torch.equal(gathered[ctx.rank * batch:(ctx.rank + 1) * batch], hold["z"]), "gathered rows differ from the local shard"
+    else:
+        ms_ng = ms
     alg_bytes = batch * (PATCH * PATCH * 4 + n_modes * 4)
-    achieved = alg_bytes * args.steps / (ms / 1e3) / 1e9
+    achieved = alg_bytes * args.steps / (ms_ng / 1e3) / 1e9
     flops = 2.0 * batch * PATCH * PATCH * n_modes
-    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get(prec) if batch == 262144 else None,
-            "traffic_source": "profiles/r01 ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch",
-            "peak_source": pk["source"],
-            "kernel": {"fp32": "project_simt_kernel", "tf32": "project_tc_kernel<plain>",
-                       "tf32x3": "project_tc3_kernel<plain,pair>"}[prec],
-            "algorithmic_bytes_per_launch": alg_bytes,
-            "tflops": flops * args.steps / (ms / 1e3) / 1e12}
+    kernel = {"fp32": "project_simt_kernel", "tf32": "project_tc_kernel<plain>", "tf32x3": "project_tc3_kernel<plain,pair>"}[prec]
+    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "traffic": NCU_TRAFFIC.get(prec) if batch == 262144 else None,
+            "traffic_source": "profiles/ ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch",
+            "peak_source": pk["source"] + " burst copy bandwidth", "kernel": kernel, "algorithmic_bytes_per_launch": alg_bytes,
+            "tflops": flops * args.steps / (ms_ng / 1e3) / 1e12, "timed": "projection kernel only (the no-gather loop when N>1)"}
 
-    # end to end: the numpy user's call, pinned host buffers, H2D + D2H inside the timed region
-    n_e2e = min(batch, args.e2e_batch)
-    host = torch.empty((n_e2e, PATCH, PATCH), dtype=torch.float32, pin_memory=True)
-    host.copy_(patches[:n_e2e])
-    host_np = host.numpy()
-    zp_host = ZPs(N_MAX, PATCH, precision=args.precision, output="numpy")
-    zp_host.transform(host_np[:1024])
-    e2e_steps = max(2, min(args.steps, 5))
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = zp_host.transform(host_np)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    assert res.data.shape == (n_e2e, n_modes)
-    e2e = {"value": n_e2e * world * e2e_steps / dt, "unit": "patches/s",
-           "h2d_bytes_per_step": n_e2e * PATCH * PATCH * 4, "d2h_bytes_per_step": n_e2e * n_modes * 4,
-           "steps": e2e_steps, "api": "ZPs.transform(numpy pinned) -> zb200_project_patches_host"}
-    line = {"metric": "zernike_patches_per_sec", "value": value, "unit": "patches/s",
-            "ms_per_step": ms / args.steps, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)"}[prec],
-            "config": {"workload": f"patches n_max={N_MAX} size={PATCH} (metric shape)", "batch_per_gpu": batch,
-                       "modes": n_modes, "precision": prec, "l2": "input batch larger than L2 (no flush needed)",
-                       "parallelism": f"patch shards x{world}, no collective"},
-            "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
-    return line
+    # sustained leg: >= 2.5 s of back-to-back launches with the 2 ms clock sampler -- what a long job sees
+    sus_steps = max(args.steps, int(2500.0 / max(ms_ng / args.steps, 1e-3)))
+    ms_s, clocks_s, _ = timed(ctx, compute, sus_steps, 1)
+    roof["sustained"] = {"steps": sus_steps, "seconds": ms_s / 1e3, "ms_per_step": ms_s / sus_steps,
+                         "value": total * sus_steps / (ms_s / 1e3), "achieved": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9,
+                         "frac": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9 / pk["hbm_gbs"], "clocks": clocks_s}
+
+    e2e = e2e_patches(ctx, zp, n_modes)
+    cfg = workload_config("patches", world)
+    cfg["batch_per_gpu"] = batch
+    return {"metric": "zernike_patches_per_sec", "value": value, "unit": "patches/s", "ms_per_step": ms / args.steps,
+            "steps": args.steps, "dtype": DTYPES[prec], "precision": prec, "scaling": "weak", "config": cfg, "roofline": roof, "gather": gather,
+            "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
 
 
-def bench_map(torch, dist, rank, world, args, pk, tiled=False):
-    """tiled=False: BASELINE configs[1], one 2048^2 frame per GPU (weak scaling over frames).
-    tiled=True: BASELINE configs[3], ONE 4096^2 frame with defects, 64-px window, output row bands
-    spread over the GPUs (strong scaling; halo rows come from the replicated frame, no exchange)."""
+def e2e_patches(ctx, zp, n_modes):
+    """End to end through the public API with HOST buffers, copies inside the timed region.  Headline route = the
+    reference's own pipeline: frame + peak coordinates in, float64 moments out (KeyPoints.extract_patches ->
+    ZPs.transform; ZPs.transform_peaks_batch -> zb200_project_peaks_host); beside it the patch-stack route
+    ZPs.transform(numpy) with pageable and with pinned input (16 KB per patch cross the bus: PCIe-bound)."""
     import numpy as np
+    torch, args, world = ctx.torch, ctx.args, ctx.world
     from motif_learn_b200.datasets import honeycomb_image
+    from motif_learn_b200.features import ZPs, clear_border
+    zo = _oracle()
+    zp_host = ZPs(N_MAX, PATCH, precision=args.precision, output="numpy")
+    # --- frame route: 8 pinned 2048^2 frames per step (a short in-situ series), ~21 k peaks each
+    n_frames = 8
+    img, pts = honeycomb_image(1024, bond=12.0, seed=100 + ctx.rank)
+    tile = np.tile(img, (2, 2))                                             # 2048^2 without the slow host renderer
+    kept = np.concatenate([clear_border(pts + np.array([dx, dy]), tile.shape, PATCH) for dx in (0, 1024) for dy in (0, 1024)])
+    pinned = torch.empty((n_frames, 2048, 2048), dtype=torch.float32, pin_memory=True)
+    for f in range(n_frames):
+        pinned[f].copy_(torch.from_numpy(np.roll(tile, 7 * f, axis=1)))     # distinct frames, same lattice statistics
+    frames = [pinned[f].numpy() for f in range(n_frames)]
+    # (rolled columns move the atoms too: roll the peak columns and re-apply the border rule)
+    pts_list = []
+    for f in range(n_frames):
+        q = kept.copy()
+        q[:, 0] = (q[:, 0] + 7 * f) % 2048
+        pts_list.append(clear_border(q, tile.shape, PATCH))
+    res = zp_host.transform_peaks_batch(frames[:2], pts_list[:2])           # warm-up: staging buffers, pool threads
+    ref = zo.project_patches(zo.extract_patches(frames[1], pts_list[1][:512], PATCH).astype(np.float64), zp.polynomials)
+    fp32_close(res[1].data[:512], ref, "e2e frame route")
+    steps = max(2, min(args.steps, 5))
+    if world > 1:
+        ctx.dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = zp_host.transform_peaks_batch(frames, pts_list)
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    n_patches = sum(len(q) for q in pts_list)
+    assert sum(r.data.shape[0] for r in res) == n_patches and res[0].data.dtype == np.float64
+    out = {"value": ctx.sum_over_ranks(n_patches) * steps / dt, "unit": "patches/s",
+           "h2d_bytes_per_step": n_frames * 2048 * 2048 * 4 + n_patches * 16, "d2h_bytes_per_step": n_patches * n_modes * 4,
+           "steps": steps, "patches_per_step": n_patches,
+           "api": "ZPs.transform_peaks_batch(8 pinned numpy frames, peak lists) -> zb200_project_peaks_host -> float64 numpy"}
+    # --- patch-stack route, pageable (what a reference user holds) and pinned
+    n_e2e = min(args.batch, args.e2e_batch)
+    base = zo.extract_patches(frames[0], pts_list[0][:8192], PATCH)
+    pageable = np.concatenate([base] * (-(-n_e2e // len(base))))[:n_e2e]
+    pin = torch.empty((n_e2e, PATCH, PATCH), dtype=torch.float32, pin_memory=True)
+    pin.copy_(torch.from_numpy(pageable))
+    zp_host.transform(pageable[:1024])
+    for label, arr in (("pageable", pageable), ("pinned", pin.numpy())):
+        if world > 1:
+            ctx.dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = zp_host.transform(arr)
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        assert r.data.shape == (n_e2e, n_modes)
+        out[f"patch_stack_{label}"] = {"value": n_e2e * world * steps / dt, "unit": "patches/s",
+                                        "h2d_bytes_per_step": n_e2e * PATCH * PATCH * 4, "d2h_bytes_per_step": n_e2e * n_modes * 4,
+                                        "api": f"ZPs.transform({label} numpy stack) -> zb200_project_patches_host"}
+    return out
+
+
+# --------------------------------------------------------------------------- dense symmetry map (C2 and C4)
+def parity_map_sample(zp, dimg, scores, row0, rows, count=384):
+    """Scores of `count` random pixels of the band against the oracle: window gather (zero extension) + float64
+    numpy.dot + rot_maps (the map equals the projection of the window centred at the pixel)."""
+    import numpy as np
+    zo = _oracle()
+    k = zp.size
+    h, w = int(dimg.shape[0]), int(dimg.shape[1])
+    rng = np.random.default_rng(7)
+    ys = np.concatenate([rng.integers(row0, row0 + rows, count - 8), [row0] * 4, [row0 + rows - 1] * 4])
+    xs = np.concatenate([rng.integers(0, w, count - 8), [0, 1, w // 2, w - 1] * 2])
+    pad = dimg.new_zeros((h + 2 * k, w + 2 * k))
+    pad[k:k + h, k:k + w] = dimg
+    wins = np.stack([pad[y + k - k // 2: y + k - k // 2 + k, x + k - k // 2: x + k - k // 2 + k].cpu().numpy() for y, x in zip(ys, xs)])
+    z = zo.project_patches(wins.astype(np.float64), zp.polynomials)
+    ref = zo.rot_maps(z, zp.n, zp.m, FOLDS)
+    tix = lambda a: scores.new_tensor(a, dtype=scores.dtype).long()      # noqa: E731
+    got = scores[:, tix(ys - row0), tix(xs)].double().cpu().numpy().T
+    ok = np.isfinite(ref)
+    assert np.array_equal(ok, np.isfinite(got)), "parity FAILED: NaN pattern of the symmetry map differs from the oracle"
+    err = float(np.abs(got[ok] - ref[ok]).max())
+    return err, count
+
+
+def bench_map(ctx, tiled=False):
+    """tiled=False: BASELINE configs[1], one 2048^2 frame per GPU (weak scaling over frames).
+    tiled=True: BASELINE configs[3], ONE 4096^2 frame with defects, 64-px window, output row bands spread over
+    the GPUs (strong scaling; halo rows come from the replicated frame), score bands gathered to every rank."""
+    import numpy as np
+    torch, args, pk, world, rank = ctx.torch, ctx.args, ctx.pk, ctx.world, ctx.rank
+    from motif_learn_b200.datasets import honeycomb_frame_gpu
     from motif_learn_b200.features import ZPs
-    from motif_learn_b200.parallel import row_band
-    MAP_SIZE, MAP_WINDOW = (4096, 64) if tiled else (2048, 48)
-    dev = torch.cuda.current_device()
-    zp = ZPs(N_MAX, MAP_WINDOW, precision=args.precision)
+    from motif_learn_b200.parallel import gather_rows, row_band, shard_sizes
+    name = "map4k" if tiled else "map"
+    size, window = (4096, 64) if tiled else (2048, 48)
+    zp = ZPs(N_MAX, window, precision=args.precision)
     prec = PREC_NAMES[zp._precision_code(for_map=True)]
     if tiled:
-        img, _ = honeycomb_image(MAP_SIZE, bond=12.0, seed=0, vacancy_frac=0.01, dopant_frac=0.005)
-        row0, rows = row_band(MAP_SIZE, rank, world)
+        dimg, _ = honeycomb_frame_gpu(size, bond=12.0, seed=0, vacancy_frac=0.01, dopant_frac=0.005)
+        row0, rows = row_band(size, rank, world)
     else:
-        img, _ = honeycomb_image(MAP_SIZE, bond=12.0, seed=rank)
-        row0, rows = 0, MAP_SIZE
-    dimg = torch.from_numpy(img).cuda()
+        dimg, _ = honeycomb_frame_gpu(size, bond=12.0, seed=rank)
+        row0, rows = 0, size
     scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    holder = {}
+    hold = {}
+    do_gather = tiled and world > 1
+    # the band is (F, rows, W); gathering along rows = all-gather of (rows, F, W) blocks in rank order
+    full = torch.empty((size, len(FOLDS), size), dtype=torch.float32, device="cuda") if do_gather else None
+
+    def compute():
+        hold["s"] = zp.symmetry_map(dimg, FOLDS, row0=row0, rows=rows)
 
     def step():
-        holder["s"] = zp.symmetry_map(dimg, FOLDS, row0=row0, rows=rows)
+        compute()
+        if do_gather:
+            gather_rows(hold["s"].permute(1, 0, 2), out=full, sizes=shard_sizes(size, world))
+
+    compute()
+    err, n_px = parity_map_sample(zp, dimg, hold["s"], row0, rows)
+    bound = 1e-3 if prec in ("tf32", "f16") else 1e-5
+    assert err <= bound, f"parity FAILED for {name}: score error {err:.2e} > {bound}"
+    parity = {"sample": n_px, "max_abs_err": err, "gate": f"n-fold scores abs <= {bound}, NaN pattern equal"}
 
     steps = max(2, min(args.steps, args.map_steps))
-    ms, clocks, launches = timed(torch, dist, world, step, steps, min(args.warmup, 3) if args.warmup >= 3 else 3, dev,
-                                 between=lambda: flush_l2(torch, scratch))
-    mpix = MAP_SIZE * MAP_SIZE / 1e6
-    value = mpix * (1 if tiled else world) * steps / (ms / 1e3)
-    flops = 2.0 * rows * MAP_SIZE * MAP_WINDOW * MAP_WINDOW * len(zp.n)
-    ach = flops * steps / (ms / 1e3) / 1e12
-    # denominator: the measured dense bf16 rate for the kind::f16 kernels (same tensor-pipe rate), half of it
-    # for the kind::tf32 kernels.  `achieved` counts ALGORITHMIC flops only; `executed_tflops` adds what the
-    # kernel really issues (three split terms, modes padded to 96, window rows padded to 16-tap groups).
+    flush = lambda: scratch.zero_()                                      # noqa: E731  (> L2 capacity)
+    ms, clocks, launches = timed(ctx, step, steps, max(3, min(args.warmup, 5)), between=flush)
+    mpix = size * size / 1e6
+    units = mpix * (1 if tiled else world)
+    value = units * steps / (ms / 1e3)
+    gather = None
+    ms_ng = ms
+    if do_gather:
+        ms_ng, _, _ = timed(ctx, compute, steps, 1, between=flush)
+        gather = gather_report(ctx, ms, ms_ng, steps, units, (size - rows) * len(FOLDS) * size * 4)
+        assert torch.equal(full[row0:row0 + rows].permute(1, 0, 2), hold["s"]), "gathered band differs from the local one"
+    flops = 2.0 * rows * size * window * window * len(zp.n)
+    ach = flops * steps / (ms_ng / 1e3) / 1e12
+    # denominator: the measured dense bf16 rate for the kind::f16 kernels (same tensor-pipe rate), the tf32 rate for
+    # the kind::tf32 kernels.  `achieved` counts ALGORITHMIC flops only; `executed_tflops` adds what the kernel
+    # really issues (three split terms, modes padded to 96, window rows padded to 16-tap groups).
     f16_kernel = prec in ("f16", "f16x3")
-    peak = pk["bf16_tflops"] if f16_kernel else pk["bf16_tflops"] / 2.0
+    peak = pk["bf16_tflops"] if f16_kernel else pk["tf32_tflops"]
     pad_modes = 96.0 / len(zp.n) if prec != "fp32" else 1.0
+    pad_taps = 1.0
     if f16_kernel:
-        xs = -1.0 + 2.0 * np.arange(MAP_WINDOW) / (MAP_WINDOW - 1)
+        xs = -1.0 + 2.0 * np.arange(window) / (window - 1)
         rows_on = int(((xs[None, :] ** 2 + xs[:, None] ** 2) <= 1.0 + 1e-9).any(axis=1).sum())
-        pad_taps = rows_on * (-(-MAP_WINDOW // 16)) * 16.0 / (MAP_WINDOW * MAP_WINDOW)
-    else:
-        pad_taps = 1.0
+        pad_taps = rows_on * (-(-window // 16)) * 16.0 / (window * window)
     executed = ach * {"fp32": 1, "tf32": 1, "tf32x3": 3, "f16": 1, "f16x3": 3}[prec] * pad_modes * pad_taps
     roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "traffic": NCU_TRAFFIC_MAP.get(prec) if not tiled else None,
-            "peak_source": pk["source"] + (" bf16 dense (kind::f16 MMAs)" if f16_kernel else " bf16 / 2 (tf32 dense rate)"),
+            "peak_source": pk["source"] + (" bf16 dense (kind::f16 MMAs)" if f16_kernel else " tf32: " + pk["tf32_source"]),
             "kernel": {"fp32": "map_simt_kernel<scores>", "tf32": "map_tc_kernel<scores>", "tf32x3": "map_tc_kernel<scores>",
                        "f16": "map_h_kernel<scores,x1>", "f16x3": "map_h_kernel<scores,x3>"}[prec],
-            "algorithmic_flops_per_launch": flops,
-            "executed_tflops": executed, "executed_frac": executed / peak}
-    # end to end: numpy frame in, numpy scores out
-    zp_host = ZPs(N_MAX, MAP_WINDOW, precision=args.precision, output="numpy")
-    host = torch.empty((MAP_SIZE, MAP_SIZE), dtype=torch.float32, pin_memory=True)
+            "algorithmic_flops_per_launch": flops, "executed_tflops": executed, "executed_frac": executed / peak,
+            "note": "fp32-grade accuracy costs 3 split MMAs per tap on fp16/tf32 tensor cores: executed_frac is the pipe's "
+                    "utilisation, frac the algorithmic one (DESIGN.md section 4)"}
+    # end to end: numpy frame in, numpy scores out (float64, like the reference); over the bus: fp32 frame up, fp32 scores down
+    zp_host = ZPs(N_MAX, window, precision=args.precision, output="numpy")
+    host = torch.empty((size, size), dtype=torch.float32, pin_memory=True)
     host.copy_(dimg)
     zp_host.symmetry_map(host.numpy(), FOLDS, row0=row0, rows=rows)      # warm-up: pinned staging, mempool growth
     torch.cuda.synchronize()
     if world > 1:
-        dist.barrier()
+        ctx.dist.barrier()
     t0 = time.perf_counter()
     e2e_steps = 3
     for _ in range(e2e_steps):
         res = zp_host.symmetry_map(host.numpy(), FOLDS, row0=row0, rows=rows)
-    dt = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-    e2e = {"value": mpix * (1 if tiled else world) * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": MAP_SIZE * MAP_SIZE * 4,
-           "d2h_bytes_per_step": int(res.size * 8), "steps": e2e_steps, "api": "ZPs.symmetry_map(numpy) -> numpy"}
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": units * e2e_steps / dt, "unit": "Mpix/s", "h2d_bytes_per_step": size * size * 4,
+           "d2h_bytes_per_step": int(res.size * 4), "steps": e2e_steps, "api": "ZPs.symmetry_map(numpy) -> float64 numpy"}
+    cfg = workload_config(name, world)
     return {"metric": "symmetry_map_mpix_per_sec", "value": value, "unit": "Mpix/s", "ms_per_step": ms / steps,
-            "steps": steps, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)", "f16": "f16",
-                                      "f16x3": "f16x3(f32-grade)"}[prec],
-            "scaling": "strong" if tiled else "weak",
-            "config": {"workload": f"symmetry map {MAP_SIZE}x{MAP_SIZE} n_max={N_MAX} window={MAP_WINDOW} "
-                                   f"folds={FOLDS} (BASELINE configs[{3 if tiled else 1}])", "precision": prec,
-                       "l2": "256 MiB scratch write between steps",
-                       "parallelism": (f"one frame, {world} row bands with halo rows from the replicated frame, no collective"
-                                       if tiled else f"one frame per GPU x{world}, no collective")},
-            "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+            "steps": steps, "dtype": DTYPES[prec], "precision": prec, "scaling": "strong" if tiled else "weak", "config": cfg, "roofline": roof,
+            "gather": gather, "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+
+
+# --------------------------------------------------------------------------- C3: complex n_max=20 on 1 Mi patches
+def bench_c3(ctx):
+    import warnings
+    import numpy as np
+    torch, args, pk, world, rank = ctx.torch, ctx.args, ctx.pk, ctx.world, ctx.rank
+    from motif_learn_b200.features import ZPs
+    from motif_learn_b200.parallel import gather_rows, shard_range, shard_sizes
+    zo = _oracle()
+    total = args.c3_total
+    lo, hi = shard_range(total, rank, world)
+    n = hi - lo
+    zp = ZPs(C3_NMAX, PATCH, precision=args.precision)
+    prec = PREC_NAMES[zp._precision_code()]
+    n_c = 121
+    patches = make_patch_batch(ctx, n, seed=1000 + rank)                 # 16 KiB per patch: 16.4 GiB at N=1
+    gathered = torch.empty((total, n_c), dtype=torch.complex64, device="cuda") if world > 1 else None
+    hold = {}
+
+    def compute(kind="complex"):
+        hold["z"] = zp.transform_features(patches, kind)
+
+    def step():
+        compute()
+        if world > 1:
+            gather_rows(torch.view_as_real(hold["z"]).reshape(n, 2 * n_c), out=torch.view_as_real(gathered).reshape(total, 2 * n_c),
+                        sizes=shard_sizes(total, world))
+
+    compute()
+    rows = sample_rows(n)
+    idx = torch.from_numpy(rows).cuda()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nn, mm, basis = zo.zernike_basis(C3_NMAX, PATCH)
+    refz = zo.to_complex(zo.project_patches(patches[idx].cpu().numpy().astype(np.float64), basis), nn, mm)[0]
+    got = hold["z"][idx].cpu().numpy().astype(np.complex128)
+    if prec == "tf32":
+        err = float(np.abs(got - refz).max() / np.abs(refz).max())
+        assert err <= 1e-3, f"parity FAILED (tf32 stated bound): {err:.2e}"
+    else:
+        # one array [Re | Im]: atol is 1e-6 * max over the whole moment array, as for the real representation
+        err = fp32_close(np.concatenate([got.real, got.imag], axis=1), np.concatenate([refz.real, refz.imag], axis=1), "c3 complex moments")
+    parity = {"sample": len(rows), "max_err_over_max": err, "gate": "allclose(rtol=1e-4, atol=1e-6*max|ref|) on [Re | Im]"}
+
+    steps = max(2, min(args.steps, 10))
+    ms, clocks, launches = timed(ctx, step, steps, 3)
+    value = total * steps / (ms / 1e3)
+    gather = None
+    ms_ng = ms
+    if world > 1:
+        ms_ng, _, _ = timed(ctx, compute, steps, 1)
+        gather = gather_report(ctx, ms, ms_ng, steps, total, (total - n) * n_c * 8)
+        assert torch.equal(gathered[lo:hi], hold["z"]), "gathered rows differ from the local shard"
+    ms_abs, _, _ = timed(ctx, lambda: compute("abs"), steps, 1)
+    alg_bytes = n * (PATCH * PATCH * 4 + n_c * 8)
+    flops = 2.0 * n * PATCH * PATCH * 231
+    gbs = alg_bytes * steps / (ms_ng / 1e3) / 1e9
+    tfl = flops * steps / (ms_ng / 1e3) / 1e12
+    f_h, f_t = gbs / pk["hbm_gbs"], tfl / pk["tf32_tflops"]
+    roof = {"bound": "hbm" if f_h >= f_t else "tensor", "achieved": gbs if f_h >= f_t else tfl,
+            "peak": pk["hbm_gbs"] if f_h >= f_t else pk["tf32_tflops"], "unit": "GB/s" if f_h >= f_t else "TFLOP/s",
+            "frac": max(f_h, f_t), "hbm": {"achieved": gbs, "peak": pk["hbm_gbs"], "frac": f_h},
+            "tensor": {"achieved": tfl, "peak": pk["tf32_tflops"], "frac": f_t, "peak_source": pk["tf32_source"]},
+            "traffic": None, "kernel": "project_tc3_kernel<plain> on the complex-interleaved operand" if prec == "tf32x3" else "project_tc_kernel",
+            "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": flops,
+            "note": "SURVEY.md 8d: report both fractions, the larger one binds"}
+    cfg = workload_config("c3", world)
+    return {"metric": "zernike_patches_per_sec", "value": value, "unit": "patches/s", "ms_per_step": ms / steps, "steps": steps,
+            "dtype": DTYPES[prec], "precision": prec, "scaling": "strong", "config": cfg,
+            "details": {"total_patches": total, "patches_per_gpu": n}, "roofline": roof, "gather": gather, "parity": parity,
+            "abs_features": {"ms_per_step": ms_abs / steps, "value": total * steps / (ms_abs / 1e3), "unit": "patches/s",
+                             "what": "|Zc| epilogue instead of complex (no gather)"},
+            "e2e": None, "gpu_launches": launches, "clocks": clocks}
+
+
+# --------------------------------------------------------------------------- C5: frame series -> peaks -> gather -> |Zc|
+def bench_c5(ctx):
+    import numpy as np
+    torch, args, pk, world, rank = ctx.torch, ctx.args, ctx.pk, ctx.world, ctx.rank
+    from motif_learn_b200.datasets import honeycomb_frame_gpu
+    from motif_learn_b200.features import ZPs, KeyPoints, clear_border, local_max
+    from motif_learn_b200.parallel import gather_rows, shard_range
+    zo = _oracle()
+    n_frames_total = args.c5_frames
+    lo, hi = shard_range(n_frames_total, rank, world)
+    zp = ZPs(N_MAX, PATCH, precision=args.precision)
+    prec = PREC_NAMES[zp._precision_code()]
+    n_c = 49
+    rng = np.random.default_rng(12345)
+    angles = rng.uniform(0.0, 60.0, n_frames_total)
+    frames = torch.empty((hi - lo, C5_SIZE, C5_SIZE), dtype=torch.float32, device="cuda")
+    for f in range(lo, hi):                                             # in-situ series: seeds 0..255, random angle, jitter 0.3 px
+        img, _ = honeycomb_frame_gpu(C5_SIZE, bond=12.0, seed=f, angle=float(angles[f]), jitter=0.3, noise=0.01)
+        frames[f - lo] = img
+    hold = {}
+
+    def compute():
+        feats, counts = [], []
+        for f in range(hi - lo):
+            pts = local_max(frames[f], PEAK_MIN_DISTANCE, PEAK_THRESHOLD)            # (P,2) host int64, brightest first
+            kept = clear_border(pts, (C5_SIZE, C5_SIZE), PATCH)
+            feats.append(zp.transform_peaks(frames[f], kept, "abs"))                 # gather kernel + |Zc| epilogue
+            counts.append(len(kept))
+        hold["feats"], hold["counts"] = feats, counts
+
+    def step():
+        compute()
+        if world > 1:
+            hold["all"] = gather_rows(torch.cat(hold["feats"]))                      # ragged: sizes exchanged first
+
+    compute()
+    # parity: frame 0 of this rank -- peaks vs the oracle's local_max, features of 512 of them vs numpy
+    f0 = frames[0].cpu().numpy()
+    pk_ref = zo.clear_border(zo.local_max(f0, PEAK_MIN_DISTANCE, PEAK_THRESHOLD), f0.shape, PATCH)
+    pk_got = clear_border(local_max(frames[0], PEAK_MIN_DISTANCE, PEAK_THRESHOLD), f0.shape, PATCH)
+    assert np.array_equal(pk_ref, pk_got), "parity FAILED: peaks of frame 0 differ from the oracle"
+    sub = pk_ref[:: max(1, len(pk_ref) // 512)][:512]
+    ref = np.abs(zo.to_complex(zo.project_patches(zo.extract_patches(f0, sub, PATCH).astype(np.float64), zp.polynomials), zp.n, zp.m)[0])
+    got = zp.transform_peaks(frames[0], sub, "abs").double().cpu().numpy()
+    err = float(np.abs(got - ref).max() / ref.max())
+    assert err <= 3e-6, f"parity FAILED for c5 |Zc| features: {err:.2e} * max"
+    parity = {"peaks_frame0": int(len(pk_ref)), "peaks_equal_oracle": True, "feature_sample": int(len(sub)),
+              "max_err_over_max": err, "gate": "identical peak list; |Zc| abs err <= 3e-6*max|ref|"}
+
+    steps = max(2, min(args.steps, 3))
+    ms, clocks, launches = timed(ctx, step, steps, 1)
+    n_patches = ctx.sum_over_ranks(float(sum(hold["counts"])))
+    value = n_patches * steps / (ms / 1e3)
+    gather = None
+    if world > 1:
+        ms_ng, _, _ = timed(ctx, compute, steps, 1)
+        mine = float(sum(hold["counts"]))
+        gather = gather_report(ctx, ms, ms_ng, steps, n_patches, int((n_patches - mine) * n_c * 4))
+        assert hold["all"].shape[0] == int(n_patches)
+    cfg = workload_config("c5", world)
+    details = {"frames_total": n_frames_total, "frames_per_gpu": hi - lo, "patches_total": int(n_patches),
+               "peaks": f"local_max(min_distance={PEAK_MIN_DISTANCE}, threshold={PEAK_THRESHOLD}) on the GPU"}
+    per_frame_bytes = C5_SIZE * C5_SIZE * 4
+    return {"metric": "zernike_patches_per_sec", "value": value, "unit": "patches/s", "ms_per_step": ms / steps, "steps": steps,
+            "frames_per_sec": n_frames_total * steps / (ms / 1e3), "dtype": DTYPES[prec], "precision": prec, "scaling": "strong",
+            "config": cfg, "details": details,
+            "roofline": {"bound": "latency", "note": "per frame: peak detection (sort + suppression with host round trips), "
+                         "gather kernel, projection kernel; ~1 ms per frame, none of the three near its roofline at 21 k patches",
+                         "frame_bytes_per_sec": n_frames_total * per_frame_bytes * steps / (ms / 1e3)},
+            "gather": gather, "parity": parity, "e2e": None, "gpu_launches": launches, "clocks": clocks}
+
+
+RUNNERS = {"patches": bench_patches, "map": lambda c: bench_map(c, tiled=False), "map4k": lambda c: bench_map(c, tiled=True),
+           "c3": bench_c3, "c5": bench_c5}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="patches", choices=["patches", "map", "map4k"])
+    ap.add_argument("--workload", default="patches", choices=WORKLOADS)
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "tf32x3", "f16", "f16x3"])
-    ap.add_argument("--batch", type=int, default=262144, help="patches per GPU per step")
+    ap.add_argument("--batch", type=int, default=262144, help="patches per GPU per step (metric shape)")
     ap.add_argument("--e2e-batch", type=int, default=65536)
     ap.add_argument("--map-steps", type=int, default=20)
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary workload")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--c3-total", type=int, default=C3_TOTAL)
+    ap.add_argument("--c5-frames", type=int, default=C5_FRAMES)
+    ap.add_argument("--also", default="all", help="comma list of the other workloads to carry under 'also' (all | none | names)")
+    ap.add_argument("--no-also", action="store_true", help="same as --also none")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)                                   # timing rule: at least 3 warm-up steps
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -432,41 +880,31 @@ def main():
             sys.stdout.flush()
             os.dup2(keep, 1)
             os.close(keep)
-    pk = peaks()
-    if args.workload == "map4k":
-        primary = lambda *a: bench_map(*a, tiled=True)          # noqa: E731
-        secondary = bench_patches
-    else:
-        primary = bench_patches if args.workload == "patches" else bench_map
-        secondary = bench_map if args.workload == "patches" else bench_patches
-    line = primary(torch, dist, rank, world, args, pk)
-    line.setdefault("steps", args.steps)
-    line.setdefault("scaling", "weak")
-    line.update({"n_gpus": world, "warmup": args.warmup, "higher_is_better": True,
-                 "vs_baseline": None, "data": "synthetic"})
-    if not args.no_also:
+    ctx = Ctx(torch, dist, rank, world, local, args, peaks())
+    line = RUNNERS[args.workload](ctx)
+    line.update({"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
+    others = [] if (args.no_also or args.also == "none") else (
+        [w for w in WORKLOADS if w != args.workload] if args.also == "all" else [w for w in args.also.split(",") if w in WORKLOADS])
+    also = []
+    for name in others:
+        torch.cuda.empty_cache()
         try:
-            other = secondary(torch, dist, rank, world, args, pk)
-            line["also"] = {k: other[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "config",
-                                                  "roofline", "e2e", "gpu_launches")}
-        except Exception as exc:  # the secondary number must never sink the primary line
-            line["also"] = {"error": f"{type(exc).__name__}: {exc}"}
+            other = RUNNERS[name](ctx)
+            other["workload"] = name
+            also.append(other)
+        except Exception as exc:  # a secondary number must never sink the primary line (all ranks fail alike: same code path)
+            also.append({"workload": name, "error": f"{type(exc).__name__}: {exc}"})
+    if also:
+        line["also"] = also
     if rank == 0 and not args.no_cpu:
         cores = cpu_threads()
-        if args.workload == "patches":
-            v, times = cpu_patches(20000, 8)
-            line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
-                                    "sample": "20000 float32 64x64 patches, numpy.dot float64 (reference algorithm "
-                                              f"_zps.py:146-157 via oracle port), best of {len(times)}"}
-            if "also" in line and "error" not in line["also"]:
-                mv, dt = cpu_map(384)
-                line["also"]["cpu_baseline"] = {"value": mv, "unit": "Mpix/s", "cores": 1, "kind": "port",
-                                                "sample": f"384x384 crop, 91 scipy.fftconvolve + rot_maps, {dt:.1f} s"}
-        else:
-            mv, dt = cpu_map(512, window=64 if args.workload == "map4k" else MAP_WINDOW)
-            line["cpu_baseline"] = {"value": mv, "unit": "Mpix/s", "cores": 1, "kind": "port",
-                                    "sample": f"512x512 crop, 91 scipy.fftconvolve (1 thread, reference algorithm "
-                                              f"_zps.py:159-193 via oracle port) + rot_maps, {dt:.1f} s"}
+        line["cpu_baseline"] = cpu_baseline_for(args.workload, cores)
+        for other in also:
+            if "error" not in other:
+                try:
+                    other["cpu_baseline"] = cpu_baseline_for(other["workload"], cores)
+                except Exception as exc:
+                    other["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

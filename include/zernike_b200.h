@@ -17,6 +17,10 @@
  *   - layouts are C-order, exactly the reference's: patches (N,k,k); real moments
  *     (N,M) with modes ordered n ascending, m=-n,-n+2..n (j=((n+2)n+m)/2); complex
  *     moments (N,Mc) ordered by nm2j_complex; maps (M,H,W) / (F,H,W).
+ *   - threads: device-pointer entry points may be called concurrently from several host threads (they only
+ *     enqueue on the given stream).  The HOST-buffer entry points (zb200_project_patches_host,
+ *     zb200_project_peaks_host, zb200_download_as_f64) own per-plan / per-device staging buffers and take a
+ *     mutex for the whole call: concurrent callers on one plan are served one after the other.
  *   - sm_100a only.  There is no CPU fallback: without a CUDA device every compute
  *     entry point fails with ZB200_ENODEV.
  */
@@ -130,6 +134,17 @@ int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_img, int H, i
  * H2D -> kernel -> D2H pipeline; h_out is double [N,M] like the reference. Blocks. */
 int zb200_project_patches_host(const zb200_plan* plan, const float* h_patches, int64_t n_patches,
                                int precision, double* h_out);
+/* The reference's patch route end to end from HOST buffers, for a series of frames of one shape:
+ * KeyPoints(pts, frame, size).extract_patches() -> ZPs.transform(patches) [-> to_complex() / np.abs()]
+ * (_keypoint.py:60-78, _zps.py:146-157, _zmoments.py:300-316).  h_frames[f] is frame f (float [H,W]),
+ * h_counts[f] its number of peaks, h_pts_xy the peaks of all frames back to back as (x, y) doubles (already
+ * filtered by clear_border).  Only the frames and the coordinates cross the bus (16.8 MB per 2048^2 frame
+ * instead of 16 KB per patch); frames are pipelined over two streams (H2D of frame f+1 and the result
+ * download / widening of frame f-1 overlap the kernels of frame f).  out_kind REAL | COMPLEX | ABS;
+ * h_out is [sum(counts), M | 2Mc | Mc] of out_dtype (ZB200_F64: what the reference returns).  Blocks. */
+int zb200_project_peaks_host(const zb200_plan* plan, const float* const* h_frames, int n_frames, int H, int W,
+                             const double* h_pts_xy, const int64_t* h_counts, int precision, int out_kind,
+                             int out_dtype, void* h_out);
 
 /* ---- K4: dense map (replaces ZPs._transform_fft_convolve, _zps.py:159-193) --- */
 /* Moments at every pixel of rows [row0,row0+rows): d_out float [M,rows,W].

@@ -54,6 +54,7 @@ SIGNATURES = {
     "zb200_project_patches_scores_f32": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "zb200_project_peaks_f32": (_int, [_vp, _vp, _int, _int, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "zb200_project_patches_host": (_int, [_vp, _vp, _i64, _int, _vp]),
+    "zb200_project_peaks_host": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, _int, _int, _int, _vp]),
     "zb200_moment_map_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "zb200_symmetry_map_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "zb200_to_complex": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _i64, _vp]),

@@ -100,13 +100,7 @@ extern "C" void zb200_plan_destroy(zb200_plan* p) {
     free_operand(p->real);
     free_operand(p->cplx);
     free_map_half_operand(p);
-    for (int i = 0; i < 2; ++i) {
-        if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
-        if (p->pin_out[i]) cudaFreeHost(p->pin_out[i]);
-        cudaFree(p->dev_in[i]);
-        cudaFree(p->dev_out[i]);
-        if (p->io_stream[i]) cudaStreamDestroy(p->io_stream[i]);
-    }
+    free_host_pipe(p);
     delete p;
 }
 
@@ -227,9 +221,10 @@ extern "C" int zb200_plan_supports_map(const zb200_plan* p, int precision) {
 }
 
 // ---- K3 ---------------------------------------------------------------------------------------
-static int project_any(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind,
-                       void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds,
-                       int norm_kind, cudaStream_t s) {
+namespace zb200 {
+int project_any(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind,
+                void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds,
+                int norm_kind, cudaStream_t s) {
     if (precision == ZB200_PREC_FP32) {
         if (out_kind != ZB200_OUT_REAL || d_w) {
             set_error("the fp32 SIMT projection only produces real moments (out_kind REAL)");
@@ -243,6 +238,7 @@ static int project_any(const zb200_plan* p, const float* d_patches, int64_t n, i
     set_error("unknown precision %d", precision);
     return ZB200_EINVAL;
 }
+}  // namespace zb200
 
 extern "C" int zb200_project_patches_f32(const zb200_plan* p, const float* d_patches, int64_t n, int precision,
                                          int out_kind, void* d_out, void* d_out2, void* stream) {
@@ -263,6 +259,8 @@ extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float
     ZB_CHECK_ARG(norm_kind >= ZB200_NORM_NONE && norm_kind <= ZB200_NORM_INF, "project_scores: bad norm kind");
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG(d_patches && d_scores, "project_scores: null device pointer");
+    ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
+    ZB_CHECK_ARG(h_weights && h_select, "weights/select must not be null");
     cudaStream_t s = as_stream(stream);
     if (precision == ZB200_PREC_FP32) {
         // SIMT contraction into a temporary, then the score kernel (two launches, no fusion)
@@ -270,9 +268,9 @@ extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float
         ZB_CUDA(cudaMallocAsync(&tmp, sizeof(float) * (size_t)n * p->n_modes, s));
         int rc = project_simt(p, d_patches, n, tmp, s);
         if (!rc) {
-            std::vector<double> wd((size_t)n_folds * p->n_modes);
-            for (size_t i = 0; i < wd.size(); ++i) wd[i] = h_weights[i];
-            rc = zb200_rot_scores(ZB200_F32, tmp, n, p->n_modes, p->n_modes, 1, wd.data(), h_select, n_folds,
+            double wd[kMaxFolds * kMaxModes];          // bounded by the checks above: nothing throws across the C ABI
+            for (size_t i = 0; i < (size_t)n_folds * p->n_modes; ++i) wd[i] = h_weights[i];
+            rc = zb200_rot_scores(ZB200_F32, tmp, n, p->n_modes, p->n_modes, 1, wd, h_select, n_folds,
                                   norm_kind, d_scores, n_folds, 1, stream);
         }
         cudaFreeAsync(tmp, s);
@@ -285,69 +283,6 @@ extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float
     rc = project_any(p, d_patches, n, precision, ZB200_OUT_REAL, d_scores, nullptr, d_w, d_sel, n_folds, norm_kind, s);
     cudaFreeAsync(d_w, s);
     return rc;
-}
-
-// Host-buffer pipeline: chunks of patches flow  host -> (pinned) -> HBM -> kernel -> pinned -> host.
-static int ensure_host_pipeline(zb200_plan* p) {
-    if (p->host_chunk) return ZB200_OK;
-    const int64_t target = 64ll << 20;                        // 64 MiB of patches per chunk
-    int64_t chunk = target / ((int64_t)p->kk * sizeof(float));
-    if (chunk < 256) chunk = 256;
-    for (int i = 0; i < 2; ++i) {
-        ZB_CUDA(cudaMallocHost(&p->pin_in[i], sizeof(float) * chunk * p->kk));
-        ZB_CUDA(cudaMallocHost(&p->pin_out[i], sizeof(float) * chunk * p->n_modes));
-        ZB_CUDA(cudaMalloc(&p->dev_in[i], sizeof(float) * chunk * p->kk));
-        ZB_CUDA(cudaMalloc(&p->dev_out[i], sizeof(float) * chunk * p->n_modes));
-        ZB_CUDA(cudaStreamCreateWithFlags(&p->io_stream[i], cudaStreamNonBlocking));
-    }
-    p->host_chunk = chunk;
-    return ZB200_OK;
-}
-
-extern "C" int zb200_project_patches_host(const zb200_plan* plan, const float* h_patches, int64_t n, int precision,
-                                          double* h_out) {
-    ZB_CHECK_ARG(plan, "project_host: plan is null");
-    ZB_CHECK_ARG(n >= 0, "project_host: negative patch count");
-    if (n == 0) return ZB200_OK;
-    ZB_CHECK_ARG(h_patches && h_out, "project_host: null host pointer");
-    zb200_plan* p = const_cast<zb200_plan*>(plan);
-    int rc = ensure_host_pipeline(p);
-    if (rc) return rc;
-    cudaPointerAttributes attr;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&attr, h_patches) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    const int64_t chunk = p->host_chunk;
-    const int64_t n_chunks = ceil_div(n, chunk);
-    const int M = p->n_modes;
-    auto drain = [&](int64_t c) -> int {
-        const int b = (int)(c & 1);
-        const int64_t off = c * chunk, cnt = (n - off < chunk) ? n - off : chunk;
-        ZB_CUDA(cudaStreamSynchronize(p->io_stream[b]));
-        const float* src = static_cast<const float*>(p->pin_out[b]);
-        double* dst = h_out + off * M;
-        for (int64_t i = 0; i < cnt * M; ++i) dst[i] = (double)src[i];
-        return ZB200_OK;
-    };
-    for (int64_t c = 0; c < n_chunks; ++c) {
-        const int b = (int)(c & 1);
-        const int64_t off = c * chunk, cnt = (n - off < chunk) ? n - off : chunk;
-        if (c >= 2) { rc = drain(c - 2); if (rc) return rc; }
-        const size_t in_bytes = sizeof(float) * (size_t)cnt * p->kk;
-        const float* src = h_patches + off * p->kk;
-        if (!pinned) {
-            memcpy(p->pin_in[b], src, in_bytes);
-            src = static_cast<const float*>(p->pin_in[b]);
-        }
-        ZB_CUDA(cudaMemcpyAsync(p->dev_in[b], src, in_bytes, cudaMemcpyHostToDevice, p->io_stream[b]));
-        rc = project_any(p, static_cast<const float*>(p->dev_in[b]), cnt, precision, ZB200_OUT_REAL, p->dev_out[b],
-                         nullptr, nullptr, nullptr, 0, 0, p->io_stream[b]);
-        if (rc) return rc;
-        ZB_CUDA(cudaMemcpyAsync(p->pin_out[b], p->dev_out[b], sizeof(float) * (size_t)cnt * M, cudaMemcpyDeviceToHost,
-                                p->io_stream[b]));
-    }
-    for (int64_t c = (n_chunks >= 2 ? n_chunks - 2 : 0); c < n_chunks; ++c) { rc = drain(c); if (rc) return rc; }
-    return ZB200_OK;
 }
 
 // ---- K4 ---------------------------------------------------------------------------------------
@@ -395,72 +330,3 @@ extern "C" int zb200_symmetry_map_f32(const zb200_plan* p, const float* d_img, i
     return rc;
 }
 
-// ---- result download: float32 in HBM -> float64 host array (what the reference returns) -----------------
-// Chunked D2H into two pinned staging buffers on a private stream, widened to float64 by a few host threads
-// while the next chunk is in flight (the destination's first-touch page faults are spread over the threads).
-namespace {
-struct Downloader {
-    std::mutex mu;
-    float* pin[2] = {nullptr, nullptr};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ready = nullptr, done[2] = {nullptr, nullptr};
-    int device = -1;
-    static constexpr int64_t kChunk = 8ll << 20;      // floats per chunk (32 MiB)
-};
-constexpr int kMaxDevices = 64;
-Downloader g_downloaders[kMaxDevices];
-
-void widen_parallel(const float* src, double* dst, int64_t n, int n_threads) {
-    if (n < (1 << 16) || n_threads <= 1) {
-        for (int64_t i = 0; i < n; ++i) dst[i] = (double)src[i];
-        return;
-    }
-    std::vector<std::thread> pool;
-    const int64_t per = (n + n_threads - 1) / n_threads;
-    for (int t = 0; t < n_threads; ++t) {
-        const int64_t a = t * per, b = a + per < n ? a + per : n;
-        if (a >= b) break;
-        pool.emplace_back([=]() { for (int64_t i = a; i < b; ++i) dst[i] = (double)src[i]; });
-    }
-    for (auto& th : pool) th.join();
-}
-}  // namespace
-
-extern "C" int zb200_download_as_f64(const float* d_src, int64_t n, double* h_dst, void* stream) {
-    ZB_CHECK_ARG(n >= 0, "download: negative count");
-    if (n == 0) return ZB200_OK;
-    ZB_CHECK_ARG(d_src && h_dst, "download: null pointer");
-    int dev = 0;
-    ZB_CUDA(cudaGetDevice(&dev));
-    ZB_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "download: device ordinal %d out of range", dev);
-    Downloader& g_dl = g_downloaders[dev];           // one staging set per device (each lives in that device's context)
-    std::lock_guard<std::mutex> lock(g_dl.mu);
-    if (g_dl.device != dev) {
-        for (int i = 0; i < 2; ++i) {
-            ZB_CUDA(cudaMallocHost(&g_dl.pin[i], sizeof(float) * Downloader::kChunk));
-            ZB_CUDA(cudaEventCreateWithFlags(&g_dl.done[i], cudaEventDisableTiming));
-        }
-        ZB_CUDA(cudaEventCreateWithFlags(&g_dl.ready, cudaEventDisableTiming));
-        ZB_CUDA(cudaStreamCreateWithFlags(&g_dl.stream, cudaStreamNonBlocking));
-        g_dl.device = dev;
-    }
-    unsigned hw = std::thread::hardware_concurrency();
-    const int n_threads = hw >= 16 ? 12 : (hw >= 4 ? (int)hw - 2 : 1);
-    // the producing kernels run on the caller's stream
-    ZB_CUDA(cudaEventRecord(g_dl.ready, as_stream(stream)));
-    ZB_CUDA(cudaStreamWaitEvent(g_dl.stream, g_dl.ready, 0));
-    const int64_t n_chunks = ceil_div(n, Downloader::kChunk);
-    auto count_of = [&](int64_t c) { const int64_t off = c * Downloader::kChunk; return n - off < Downloader::kChunk ? n - off : Downloader::kChunk; };
-    for (int64_t c = 0; c <= n_chunks; ++c) {
-        if (c < n_chunks) {
-            ZB_CUDA(cudaMemcpyAsync(g_dl.pin[c & 1], d_src + c * Downloader::kChunk, sizeof(float) * count_of(c),
-                                    cudaMemcpyDeviceToHost, g_dl.stream));
-            ZB_CUDA(cudaEventRecord(g_dl.done[c & 1], g_dl.stream));
-        }
-        if (c >= 1) {
-            ZB_CUDA(cudaEventSynchronize(g_dl.done[(c - 1) & 1]));
-            widen_parallel(g_dl.pin[(c - 1) & 1], h_dst + (c - 1) * Downloader::kChunk, count_of(c - 1), n_threads);
-        }
-    }
-    return ZB200_OK;
-}

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 
 #include "zernike_b200.h"
 
@@ -93,6 +94,7 @@ struct MapHalf {
     CUtensorMap tmap_b2[2];
 };
 
+struct HostPipe;
 }  // namespace zb200
 
 struct zb200_plan {
@@ -117,12 +119,9 @@ struct zb200_plan {
     zb200::Operand cplx;          // complex-interleaved row order
     zb200::MapHalf map_half[4];   // fp16-split dense-map operands (real row order), <= 128 padded modes each
     int n_map_parts = 0;
-    void* pin_in[2] = {nullptr, nullptr};   // pinned staging for the host entry point
-    void* pin_out[2] = {nullptr, nullptr};
-    void* dev_in[2] = {nullptr, nullptr};
-    void* dev_out[2] = {nullptr, nullptr};
-    cudaStream_t io_stream[2] = {nullptr, nullptr};
-    int64_t host_chunk = 0;
+    // staging set of the host-buffer entry points (zb200_host.cu); calls on one plan take turns under host_mu
+    std::mutex host_mu;
+    zb200::HostPipe* host = nullptr;
 };
 
 namespace zb200 {
@@ -133,6 +132,11 @@ constexpr int kMaxModes = 1024;   // n_max <= 43
 int launch_basis(zb200_plan* plan, cudaStream_t s);
 int launch_pack(zb200_plan* plan, cudaStream_t s);
 int init_tensor_maps(zb200_plan* plan);
+
+void free_host_pipe(zb200_plan* plan);
+// precision / epilogue dispatch of the patch projection (zb200_api.cu)
+int project_any(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind, void* d_out,
+                void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind, cudaStream_t s);
 
 int project_simt(const zb200_plan* plan, const float* d_patches, int64_t n, float* d_out_real, cudaStream_t s);
 // frame + window corners for the fused gather -> projection path (K2 inside K3)

@@ -1,0 +1,413 @@
+// Host-buffer entry points: the calls a numpy user of the reference makes (host arrays in, float64 host
+// arrays out).  Everything here is plumbing around the kernels: a persistent host thread pool (staging copies
+// and float32 -> float64 widening are memory-bound loops that one core cannot feed at PCIe speed), two-slot
+// pipelines  host -> pinned -> HBM -> kernels -> pinned -> host  whose result side runs on a second host
+// thread, and the per-plan staging buffers, guarded by the plan's mutex (calls on one plan serialise).
+#include "zb200_common.cuh"
+
+#include <string.h>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace zb200 {
+
+// ---- persistent host pool -----------------------------------------------------------------------------
+namespace {
+class HostPool {
+public:
+    static HostPool& get() {
+        static HostPool* pool = new HostPool();      // leaked on purpose: no destructor order problems at exit
+        return *pool;
+    }
+    int width() const { return (int)workers_.size() + 1; }
+    // fn(begin, end) over [0, n) in contiguous slices; the caller works on the first slice itself
+    void parallel_for(int64_t n, int64_t grain, const std::function<void(int64_t, int64_t)>& fn) {
+        int parts = (int)((n + grain - 1) / grain);
+        if (parts > width()) parts = width();
+        if (parts <= 1) { fn(0, n); return; }
+        struct Latch { std::mutex m; std::condition_variable cv; int left; } latch;
+        latch.left = parts - 1;
+        const int64_t per = (n + parts - 1) / parts;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (int t = 1; t < parts; ++t) {
+                const int64_t a = t * per, b = a + per < n ? a + per : n;
+                q_.emplace_back([a, b, &fn, &latch]() {
+                    if (a < b) fn(a, b);
+                    std::lock_guard<std::mutex> lk2(latch.m);
+                    if (--latch.left == 0) latch.cv.notify_one();
+                });
+            }
+        }
+        cv_.notify_all();
+        fn(0, per < n ? per : n);
+        std::unique_lock<std::mutex> lk(latch.m);
+        latch.cv.wait(lk, [&] { return latch.left == 0; });
+    }
+
+private:
+    HostPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = hw >= 8 ? (int)hw / 2 : (hw >= 3 ? (int)hw - 2 : 0);
+        if (n > 16) n = 16;
+        if (const char* e = getenv("ZB200_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n = v - 1; }
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+        for (auto& w : workers_) w.detach();
+    }
+    void run() {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return !q_.empty(); });
+                job = std::move(q_.front());
+                q_.pop_front();
+            }
+            job();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+};
+
+void widen_parallel(const float* src, double* dst, int64_t n) {
+    HostPool::get().parallel_for(n, 1 << 16, [=](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) dst[i] = (double)src[i];
+    });
+}
+void copy_parallel(void* dst, const void* src, size_t bytes) {
+    HostPool::get().parallel_for((int64_t)bytes, 1 << 20, [=](int64_t a, int64_t b) {
+        memcpy(static_cast<char*>(dst) + a, static_cast<const char*>(src) + a, (size_t)(b - a));
+    });
+}
+bool is_pinned(const void* h) {
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;
+}
+
+// ---- two-slot pipeline: enqueue(c, slot) on the calling thread, drain(c, slot) on a second thread once the
+// event of the slot has fired.  Slot b is reused by item c only after item c-2 has been drained. ---------------
+struct PipeSync {
+    std::mutex m;
+    std::condition_variable cv;
+    int64_t enqueued = 0, drained = 0;
+    int rc = 0;
+    std::string msg;
+};
+
+template <class Enqueue, class Drain>
+int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drain drain) {
+    if (n_items <= 0) return ZB200_OK;
+    PipeSync ps;
+    std::thread drainer([&] {
+        cudaSetDevice(device);
+        for (int64_t c = 0; c < n_items; ++c) {
+            {
+                std::unique_lock<std::mutex> lk(ps.m);
+                ps.cv.wait(lk, [&] { return ps.enqueued > c || ps.rc; });
+                if (ps.rc) return;
+            }
+            int r = ZB200_OK;
+            cudaError_t e = cudaEventSynchronize(ev[c & 1]);
+            if (e != cudaSuccess) {
+                set_error("host pipeline: %s", cudaGetErrorString(e));
+                r = ZB200_ECUDA;
+            } else {
+                r = drain(c, (int)(c & 1));
+            }
+            std::lock_guard<std::mutex> lk(ps.m);
+            if (r) { ps.rc = r; ps.msg = zb200_last_error(); }
+            ps.drained = c + 1;
+            ps.cv.notify_all();
+            if (r) return;
+        }
+    });
+    for (int64_t c = 0; c < n_items; ++c) {
+        {
+            std::unique_lock<std::mutex> lk(ps.m);
+            ps.cv.wait(lk, [&] { return ps.drained >= c - 1 || ps.rc; });
+            if (ps.rc) break;
+        }
+        const int r = enq(c, (int)(c & 1));
+        std::lock_guard<std::mutex> lk(ps.m);
+        if (r) { ps.rc = r; ps.msg = zb200_last_error(); }
+        else ps.enqueued = c + 1;
+        ps.cv.notify_all();
+        if (r) break;
+    }
+    drainer.join();
+    if (ps.rc) {
+        set_error("%s", ps.msg.c_str());
+        cudaDeviceSynchronize();                     // nothing of this call is left in flight on the staging buffers
+        cudaGetLastError();
+    }
+    return ps.rc;
+}
+
+// growable buffers of the per-plan staging set
+enum BufKind { kPinned, kDevice };
+int ensure_buf(void** ptr, size_t* cap, size_t need, BufKind kind) {
+    if (*cap >= need && *ptr) return ZB200_OK;
+    if (*ptr) {
+        if (kind == kPinned) cudaFreeHost(*ptr); else cudaFree(*ptr);
+        *ptr = nullptr;
+        *cap = 0;
+    }
+    const size_t want = need + need / 4 + 4096;      // headroom: frames of a series differ a little in peak count
+    cudaError_t e = kind == kPinned ? cudaMallocHost(ptr, want) : cudaMalloc(ptr, want);
+    if (e != cudaSuccess) {
+        *ptr = nullptr;
+        cudaGetLastError();
+        set_error("host pipeline: cannot allocate %zu bytes of %s memory: %s", want, kind == kPinned ? "pinned" : "device",
+                  cudaGetErrorString(e));
+        return ZB200_ENOMEM;
+    }
+    *cap = want;
+    return ZB200_OK;
+}
+}  // namespace
+
+struct HostPipe {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // slots: input staging (pinned), result staging (pinned), device input, device patches, device points, device result
+    void* pin_in[2] = {nullptr, nullptr};   size_t pin_in_cap[2] = {0, 0};
+    void* pin_out[2] = {nullptr, nullptr};  size_t pin_out_cap[2] = {0, 0};
+    void* dev_in[2] = {nullptr, nullptr};   size_t dev_in_cap[2] = {0, 0};
+    void* dev_pat[2] = {nullptr, nullptr};  size_t dev_pat_cap[2] = {0, 0};
+    void* dev_pts[2] = {nullptr, nullptr};  size_t dev_pts_cap[2] = {0, 0};
+    void* dev_out[2] = {nullptr, nullptr};  size_t dev_out_cap[2] = {0, 0};
+};
+
+void free_host_pipe(zb200_plan* p) {
+    HostPipe* h = p->host;
+    if (!h) return;
+    for (int i = 0; i < 2; ++i) {
+        if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
+        if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
+        cudaFree(h->dev_in[i]);
+        cudaFree(h->dev_pat[i]);
+        cudaFree(h->dev_pts[i]);
+        cudaFree(h->dev_out[i]);
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+        if (h->st[i]) cudaStreamDestroy(h->st[i]);
+    }
+    delete h;
+    p->host = nullptr;
+}
+
+static int host_pipe(zb200_plan* p, HostPipe** out) {
+    if (!p->host) {
+        HostPipe* h = new (std::nothrow) HostPipe();
+        if (!h) { set_error("out of host memory"); return ZB200_ENOMEM; }
+        p->host = h;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaStreamCreateWithFlags(&h->st[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+                set_error("host pipeline: cannot create stream/event: %s", cudaGetErrorString(cudaGetLastError()));
+                free_host_pipe(p);                   // nothing half-built is kept
+                return ZB200_ECUDA;
+            }
+        }
+    }
+    *out = p->host;
+    return ZB200_OK;
+}
+
+static int row_len_of(const zb200_plan* p, int out_kind) {
+    return out_kind == ZB200_OUT_REAL ? p->n_modes : (out_kind == ZB200_OUT_COMPLEX ? 2 * p->n_complex : p->n_complex);
+}
+
+}  // namespace zb200
+
+using namespace zb200;
+
+// ---- patch stack from host memory (ZPs.transform(numpy), _zps.py:146-157) ------------------------------------
+extern "C" int zb200_project_patches_host(const zb200_plan* plan, const float* h_patches, int64_t n, int precision,
+                                          double* h_out) {
+    ZB_CHECK_ARG(plan, "project_host: plan is null");
+    ZB_CHECK_ARG(n >= 0, "project_host: negative patch count");
+    if (n == 0) return ZB200_OK;
+    ZB_CHECK_ARG(h_patches && h_out, "project_host: null host pointer");
+    zb200_plan* p = const_cast<zb200_plan*>(plan);
+    std::lock_guard<std::mutex> lock(p->host_mu);     // one host pipeline per plan: concurrent callers take turns
+    HostPipe* h = nullptr;
+    int rc = host_pipe(p, &h);
+    if (rc) return rc;
+    int64_t chunk = (64ll << 20) / ((int64_t)p->kk * (int64_t)sizeof(float));     // 64 MiB of patches per chunk
+    if (chunk < 256) chunk = 256;
+    if (chunk > n) chunk = n;
+    const int M = p->n_modes;
+    const bool pinned = is_pinned(h_patches);
+    for (int b = 0; b < 2; ++b) {
+        if (!pinned && (rc = ensure_buf(&h->pin_in[b], &h->pin_in_cap[b], sizeof(float) * chunk * p->kk, kPinned))) return rc;
+        if ((rc = ensure_buf(&h->pin_out[b], &h->pin_out_cap[b], sizeof(float) * chunk * M, kPinned))) return rc;
+        if ((rc = ensure_buf(&h->dev_in[b], &h->dev_in_cap[b], sizeof(float) * chunk * p->kk, kDevice))) return rc;
+        if ((rc = ensure_buf(&h->dev_out[b], &h->dev_out_cap[b], sizeof(float) * chunk * M, kDevice))) return rc;
+    }
+    const int64_t n_chunks = ceil_div(n, chunk);
+    auto count_of = [&](int64_t c) { return n - c * chunk < chunk ? n - c * chunk : chunk; };
+    auto enq = [&](int64_t c, int b) -> int {
+        const int64_t cnt = count_of(c);
+        const size_t in_bytes = sizeof(float) * (size_t)cnt * p->kk;
+        const float* src = h_patches + c * chunk * p->kk;
+        if (!pinned) {
+            copy_parallel(h->pin_in[b], src, in_bytes);
+            src = static_cast<const float*>(h->pin_in[b]);
+        }
+        ZB_CUDA(cudaMemcpyAsync(h->dev_in[b], src, in_bytes, cudaMemcpyHostToDevice, h->st[b]));
+        int r = project_any(p, static_cast<const float*>(h->dev_in[b]), cnt, precision, ZB200_OUT_REAL, h->dev_out[b],
+                            nullptr, nullptr, nullptr, 0, 0, h->st[b]);
+        if (r) return r;
+        ZB_CUDA(cudaMemcpyAsync(h->pin_out[b], h->dev_out[b], sizeof(float) * (size_t)cnt * M, cudaMemcpyDeviceToHost, h->st[b]));
+        ZB_CUDA(cudaEventRecord(h->ev[b], h->st[b]));
+        return ZB200_OK;
+    };
+    auto drain = [&](int64_t c, int b) -> int {
+        widen_parallel(static_cast<const float*>(h->pin_out[b]), h_out + c * chunk * M, count_of(c) * M);
+        return ZB200_OK;
+    };
+    return run_pipeline(p->device, n_chunks, h->ev, enq, drain);
+}
+
+// ---- the reference pipeline from host memory: frames + peak coordinates in, features out ---------------------
+// KeyPoints(pts, img, size).extract_patches() -> ZPs.transform -> (to_complex / np.abs), _keypoint.py:60-78,
+// _zps.py:146-157, _zmoments.py:300-316; 16.8 MB per 2048^2 frame cross the bus instead of 16 KB per patch.
+extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* const* h_frames, int n_frames, int H, int W,
+                                        const double* h_pts_xy, const int64_t* h_counts, int precision, int out_kind,
+                                        int out_dtype, void* h_out) {
+    ZB_CHECK_ARG(plan, "project_peaks_host: plan is null");
+    ZB_CHECK_ARG(n_frames >= 0 && H > 0 && W > 0, "project_peaks_host: bad shape");
+    ZB_CHECK_ARG(out_kind >= ZB200_OUT_REAL && out_kind <= ZB200_OUT_ABS, "project_peaks_host: out_kind %d not supported here",
+                 out_kind);
+    ZB_CHECK_ARG(out_dtype == ZB200_F32 || out_dtype == ZB200_F64, "project_peaks_host: bad out_dtype %d", out_dtype);
+    if (n_frames == 0) return ZB200_OK;
+    ZB_CHECK_ARG(h_frames && h_counts, "project_peaks_host: null host pointer");
+    int64_t max_count = 0, total = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        ZB_CHECK_ARG(h_counts[f] >= 0 && h_frames[f], "project_peaks_host: bad frame %d", f);
+        if (h_counts[f] > max_count) max_count = h_counts[f];
+        total += h_counts[f];
+    }
+    if (total == 0) return ZB200_OK;
+    ZB_CHECK_ARG(h_pts_xy && h_out, "project_peaks_host: null host pointer");
+    if (precision != ZB200_PREC_FP32 && !zb200_plan_supports(plan, precision, out_kind)) {
+        set_error("project_peaks_host: precision %d with out_kind %d is not available for this plan", precision, out_kind);
+        return ZB200_EUNSUP;
+    }
+    zb200_plan* p = const_cast<zb200_plan*>(plan);
+    std::lock_guard<std::mutex> lock(p->host_mu);
+    HostPipe* h = nullptr;
+    int rc = host_pipe(p, &h);
+    if (rc) return rc;
+    const int L = row_len_of(p, out_kind);
+    const size_t frame_bytes = sizeof(float) * (size_t)H * W;
+    bool all_pinned = true;
+    for (int f = 0; f < n_frames && all_pinned; ++f) all_pinned = is_pinned(h_frames[f]);
+    for (int b = 0; b < 2 && b < n_frames; ++b) {
+        if (!all_pinned && (rc = ensure_buf(&h->pin_in[b], &h->pin_in_cap[b], frame_bytes, kPinned))) return rc;
+        if ((rc = ensure_buf(&h->pin_out[b], &h->pin_out_cap[b], sizeof(float) * max_count * L, kPinned))) return rc;
+        if ((rc = ensure_buf(&h->dev_in[b], &h->dev_in_cap[b], frame_bytes, kDevice))) return rc;
+        if ((rc = ensure_buf(&h->dev_pts[b], &h->dev_pts_cap[b], sizeof(double) * 2 * max_count, kDevice))) return rc;
+        if ((rc = ensure_buf(&h->dev_pat[b], &h->dev_pat_cap[b], sizeof(float) * max_count * p->kk, kDevice))) return rc;
+        if ((rc = ensure_buf(&h->dev_out[b], &h->dev_out_cap[b], sizeof(float) * max_count * L, kDevice))) return rc;
+    }
+    std::vector<int64_t> first((size_t)n_frames + 1, 0);
+    for (int f = 0; f < n_frames; ++f) first[f + 1] = first[f] + h_counts[f];
+    auto enq = [&](int64_t f, int b) -> int {
+        const int64_t cnt = h_counts[f];
+        const float* src = h_frames[f];
+        if (!all_pinned) {
+            copy_parallel(h->pin_in[b], src, frame_bytes);
+            src = static_cast<const float*>(h->pin_in[b]);
+        }
+        ZB_CUDA(cudaMemcpyAsync(h->dev_in[b], src, frame_bytes, cudaMemcpyHostToDevice, h->st[b]));
+        if (cnt > 0) {
+            ZB_CUDA(cudaMemcpyAsync(h->dev_pts[b], h_pts_xy + 2 * first[f], sizeof(double) * 2 * (size_t)cnt,
+                                    cudaMemcpyHostToDevice, h->st[b]));
+            int r = zb200_gather_patches_f32(static_cast<const float*>(h->dev_in[b]), H, W,
+                                             static_cast<const double*>(h->dev_pts[b]), cnt, p->size,
+                                             static_cast<float*>(h->dev_pat[b]), h->st[b]);
+            if (r) return r;
+            r = project_any(p, static_cast<const float*>(h->dev_pat[b]), cnt, precision, out_kind, h->dev_out[b], nullptr,
+                            nullptr, nullptr, 0, 0, h->st[b]);
+            if (r) return r;
+            ZB_CUDA(cudaMemcpyAsync(h->pin_out[b], h->dev_out[b], sizeof(float) * (size_t)cnt * L, cudaMemcpyDeviceToHost,
+                                    h->st[b]));
+        }
+        ZB_CUDA(cudaEventRecord(h->ev[b], h->st[b]));
+        return ZB200_OK;
+    };
+    auto drain = [&](int64_t f, int b) -> int {
+        const int64_t cnt = h_counts[f] * L;
+        if (out_dtype == ZB200_F64)
+            widen_parallel(static_cast<const float*>(h->pin_out[b]), static_cast<double*>(h_out) + first[f] * L, cnt);
+        else
+            copy_parallel(static_cast<float*>(h_out) + first[f] * L, h->pin_out[b], sizeof(float) * (size_t)cnt);
+        return ZB200_OK;
+    };
+    return run_pipeline(p->device, n_frames, h->ev, enq, drain);
+}
+
+// ---- result download: float32 in HBM -> float64 host array (what the reference returns) -----------------
+// Chunked D2H into two pinned staging buffers on a private stream, widened to float64 by the host pool
+// while the next chunk is in flight (the destination's first-touch page faults are spread over the threads).
+namespace {
+struct Downloader {
+    std::mutex mu;
+    float* pin[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr, done[2] = {nullptr, nullptr};
+    int device = -1;
+    static constexpr int64_t kChunk = 8ll << 20;      // floats per chunk (32 MiB)
+};
+constexpr int kMaxDevices = 64;
+Downloader g_downloaders[kMaxDevices];
+}  // namespace
+
+extern "C" int zb200_download_as_f64(const float* d_src, int64_t n, double* h_dst, void* stream) {
+    ZB_CHECK_ARG(n >= 0, "download: negative count");
+    if (n == 0) return ZB200_OK;
+    ZB_CHECK_ARG(d_src && h_dst, "download: null pointer");
+    int dev = 0;
+    ZB_CUDA(cudaGetDevice(&dev));
+    ZB_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "download: device ordinal %d out of range", dev);
+    Downloader& g_dl = g_downloaders[dev];           // one staging set per device (each lives in that device's context)
+    std::lock_guard<std::mutex> lock(g_dl.mu);
+    if (g_dl.device != dev) {
+        for (int i = 0; i < 2; ++i) {
+            ZB_CUDA(cudaMallocHost(&g_dl.pin[i], sizeof(float) * Downloader::kChunk));
+            ZB_CUDA(cudaEventCreateWithFlags(&g_dl.done[i], cudaEventDisableTiming));
+        }
+        ZB_CUDA(cudaEventCreateWithFlags(&g_dl.ready, cudaEventDisableTiming));
+        ZB_CUDA(cudaStreamCreateWithFlags(&g_dl.stream, cudaStreamNonBlocking));
+        g_dl.device = dev;
+    }
+    // the producing kernels run on the caller's stream
+    ZB_CUDA(cudaEventRecord(g_dl.ready, as_stream(stream)));
+    ZB_CUDA(cudaStreamWaitEvent(g_dl.stream, g_dl.ready, 0));
+    const int64_t n_chunks = ceil_div(n, Downloader::kChunk);
+    auto count_of = [&](int64_t c) { const int64_t off = c * Downloader::kChunk; return n - off < Downloader::kChunk ? n - off : Downloader::kChunk; };
+    for (int64_t c = 0; c <= n_chunks; ++c) {
+        if (c < n_chunks) {
+            ZB_CUDA(cudaMemcpyAsync(g_dl.pin[c & 1], d_src + c * Downloader::kChunk, sizeof(float) * count_of(c),
+                                    cudaMemcpyDeviceToHost, g_dl.stream));
+            ZB_CUDA(cudaEventRecord(g_dl.done[c & 1], g_dl.stream));
+        }
+        if (c >= 1) {
+            ZB_CUDA(cudaEventSynchronize(g_dl.done[(c - 1) & 1]));
+            widen_parallel(g_dl.pin[(c - 1) & 1], h_dst + (c - 1) * Downloader::kChunk, count_of(c - 1));
+        }
+    }
+    return ZB200_OK;
+}

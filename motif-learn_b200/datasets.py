@@ -130,3 +130,32 @@ def render_atoms_gpu(shape, pts, amps, sigma: float, r_factor: float = 3.0, out=
                                           int(h), int(w), int(img.data_ptr()), 0 if out is None else 1,
                                           C.c_void_p(_lib.current_stream_ptr())), "render_atoms")
     return img
+
+
+def honeycomb_frame_gpu(size, bond: float = 12.0, seed: int | None = 0, angle: float = 0.0,
+                        sigma: float | None = None, amp_a: float = 1.0, amp_b: float = 0.5, jitter: float = 0.0,
+                        vacancy_frac: float = 0.0, dopant_frac: float = 0.0, noise: float = 0.0):
+    """``honeycomb_image`` with the drawing done on the GPU (row f1 renderer): the lattice sites come from the
+    same host routine (integer / trigonometric bookkeeping, milliseconds), the tapered Gaussians are drawn by
+    ``zb200_render_atoms_f32`` and the optional Gaussian noise by the device RNG (seeded).  Returns
+    (frame CUDA float32 (H, W), pts float64 numpy (P, 2)) -- a 2048^2 frame takes a few ms instead of seconds,
+    which is what makes BASELINE configs 4 and 5 (a 4096^2 frame, a 256-frame series) practical to generate."""
+    from . import _lib
+    torch = _lib.require_cuda()
+    shape = (size, size) if np.isscalar(size) else tuple(size)
+    sigma = bond / 4.0 if sigma is None else sigma
+    pts, sub = honeycomb_points(shape, bond, angle, seed, jitter, margin=3.0 * sigma + 1)
+    amps = np.where(sub == 0, amp_a, amp_b).astype(np.float64)
+    rng = np.random.default_rng(None if seed is None else seed + 7919)
+    if vacancy_frac > 0:
+        amps[rng.random(len(amps)) < vacancy_frac] = 0.0
+    if dopant_frac > 0:
+        amps[rng.random(len(amps)) < dopant_frac] *= 0.8
+    img = render_atoms_gpu(shape, pts, amps, sigma)
+    if noise > 0:
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(0 if seed is None else int(seed) + 104729)
+        img.add_(torch.randn(img.shape, generator=gen, device="cuda", dtype=torch.float32), alpha=float(noise))
+    h, w = shape
+    inside = (pts[:, 0] >= 0) & (pts[:, 0] < w) & (pts[:, 1] >= 0) & (pts[:, 1] < h)
+    return img, pts[inside]

@@ -223,6 +223,15 @@ class ZPs(BaseEstimator, TransformerMixin):
         data = _host_f64(out) if self._want_host(images) else out
         return zmoments(data=data, n=self.n, m=self.m, patch_size=self.size)
 
+    def _project_device(self, dev):
+        """Real moments (N, M) float32 of a CUDA patch stack, always a CUDA tensor (internal)."""
+        torch = _lib.require_cuda()
+        out = torch.empty((int(dev.shape[0]), len(self.n)), dtype=torch.float32, device=dev.device)
+        _lib.check(_lib.load().zb200_project_patches_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]),
+                                                         self._precision_code(), _lib.OUT_REAL, int(out.data_ptr()), None,
+                                                         self._stream()), "project_patches")
+        return zmoments(data=out, n=self.n, m=self.m, patch_size=self.size)
+
     def transform_features(self, images, kind: str = "abs"):
         """Fused projection epilogues on a CUDA patch stack (tensor-core path only).
 
@@ -237,7 +246,8 @@ class ZPs(BaseEstimator, TransformerMixin):
             # the fused epilogue is not available for this shape/precision: real moments from the
             # projection kernel, then the packing kernel (two launches, still all on the GPU)
             dev_in = images if is_torch(images) else torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
-            zc = self._transform_patches(dev_in.to(device="cuda")).to_complex().data.contiguous()
+            dev_in = dev_in.to(device="cuda", dtype=torch.float32).contiguous()
+            zc = self._project_device(dev_in).to_complex().data.contiguous()
             if kind == "complex":
                 return zc
             real_t = torch.float32 if zc.dtype == torch.complex64 else torch.float64
@@ -285,8 +295,8 @@ class ZPs(BaseEstimator, TransformerMixin):
         kind = norm_code(p)
         fusable = n_f <= 8 and (prec == _lib.PREC_FP32 or len(self.n) <= (128 if prec == _lib.PREC_TF32X3 else 256))
         if not fusable:
-            out = self._transform_patches(dev).rot_maps(n_folds, p=p, m_unselect=m_unselect)
-            return out.double().cpu().numpy() if host_in and self._want_host(images) else out
+            out = self._project_device(dev).rot_maps(n_folds, p=p, m_unselect=m_unselect)
+            return _host_f64(out) if self._want_host(images) else out
         out = torch.empty((int(dev.shape[0]), n_f), dtype=torch.float32, device=dev.device)
         w32 = np.ascontiguousarray(wts, dtype=np.float32)
         _lib.check(lib.zb200_project_patches_scores_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]), prec,
@@ -297,12 +307,16 @@ class ZPs(BaseEstimator, TransformerMixin):
     def transform_peaks(self, image, pts, kind: str = "real", fused=None):
         """Moments of the ``size x size`` windows centred at ``pts`` (rows of (x, y), as kept by
         ``clear_border``) of one frame -- ``KeyPoints(pts, image, size).extract_patches()`` followed by
-        ``transform`` in ONE kernel: windows are gathered from the L2-resident frame straight into the
-        tensor-core operand, the patch stack never exists in HBM (BASELINE config 5).
+        ``transform`` (BASELINE config 5), without the patch stack ever crossing the bus.
 
         kind='real' -> ``zmoments`` (N, M); 'complex' | 'abs' | 'abs_phase' as ``transform_features``.
-        ``fused=None`` picks the fused kernel when the intermediate patch stack would exceed 8 GiB
-        (it is the memory-lean path; at round 1 the two-kernel path is the faster one), ``True``/``False`` force it."""
+        Where the result lives is decided once, from ``image`` and ``self.output``: a numpy frame gives
+        float64 / complex128 numpy results like the reference (through ``zb200_project_peaks_host``: frame and
+        coordinates up, features down), a CUDA frame float32 / complex64 CUDA tensors.
+        ``fused=True`` runs gather and projection as ONE kernel (windows go from the L2-resident frame straight
+        into the tensor-core operand; the memory-lean path), ``False`` the gather kernel followed by the
+        projection (the faster one); ``None`` picks the fused kernel when the intermediate patch stack would
+        exceed 8 GiB."""
         if image.ndim != 2:
             raise ValueError("Images must be 2D or 3D array.")
         torch = _lib.require_cuda()
@@ -310,40 +324,91 @@ class ZPs(BaseEstimator, TransformerMixin):
         codes = {"real": _lib.OUT_REAL, "complex": _lib.OUT_COMPLEX, "abs": _lib.OUT_ABS, "abs_phase": _lib.OUT_ABS_PHASE}
         code = codes[kind]
         prec = self._precision_code()
-        dev = self._image_on_device(image)
+        to_host = self._want_host(image)
         pts_np = np.ascontiguousarray(np.asarray(pts, dtype=np.float64).reshape(-1, 2))
         can_fuse = (prec == _lib.PREC_TF32X3 and self.size >= 32 and lib.zb200_plan_supports(self._plan, prec, code))
         if fused is None:
             fused = can_fuse and pts_np.shape[0] * self.size * self.size * 4 > (8 << 30)
         if fused and not can_fuse:
             raise ValueError("fused gather+projection needs precision 'tf32x3' (or 'auto' on a supported shape) and size >= 32")
+        if (to_host and not is_torch(image) and not fused and kind != "abs_phase"
+                and (prec == _lib.PREC_FP32 and kind == "real" or lib.zb200_plan_supports(self._plan, prec, code))):
+            return self.transform_peaks_batch([image], [pts_np], kind)[0]
+        dev = self._image_on_device(image)
         if not fused:
             # two kernels: gather to HBM, then the projection at the requested precision
             from ._keypoint import KeyPoints
             kp = KeyPoints.__new__(KeyPoints)
             kp.shape, kp.size, kp.img, kp.pts, kp.patches = tuple(dev.shape), self.size, dev, pts_np, None
             patches = kp.extract_patches()
-            return self._transform_patches(patches) if kind == "real" else self.transform_features(patches, kind)
-        dpts = torch.from_numpy(pts_np).to(dev.device)
-        count = int(dpts.shape[0])
-        n_c = lib.zb200_num_complex_modes(self.n_max)
-        out2 = None
-        if kind == "real":
-            out = torch.empty((count, len(self.n)), dtype=torch.float32, device=dev.device)
-        elif kind == "complex":
-            out = torch.empty((count, n_c), dtype=torch.complex64, device=dev.device)
+            res = self._project_device(patches) if kind == "real" else self.transform_features(patches, kind)
         else:
-            out = torch.empty((count, n_c), dtype=torch.float32, device=dev.device)
-            if kind == "abs_phase":
-                out2 = torch.empty_like(out)
-        _lib.check(lib.zb200_project_peaks_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]), int(dev.shape[1]),
-                                               int(dpts.data_ptr()), count, prec, code, int(out.data_ptr()),
-                                               None if out2 is None else int(out2.data_ptr()), self._stream()),
-                   "project_peaks")
+            dpts = torch.from_numpy(pts_np).to(dev.device)
+            count = int(dpts.shape[0])
+            n_c = lib.zb200_num_complex_modes(self.n_max)
+            out2 = None
+            if kind == "real":
+                out = torch.empty((count, len(self.n)), dtype=torch.float32, device=dev.device)
+            elif kind == "complex":
+                out = torch.empty((count, n_c), dtype=torch.complex64, device=dev.device)
+            else:
+                out = torch.empty((count, n_c), dtype=torch.float32, device=dev.device)
+                if kind == "abs_phase":
+                    out2 = torch.empty_like(out)
+            _lib.check(lib.zb200_project_peaks_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]), int(dev.shape[1]),
+                                                   int(dpts.data_ptr()), count, prec, code, int(out.data_ptr()),
+                                                   None if out2 is None else int(out2.data_ptr()), self._stream()),
+                       "project_peaks")
+            res = zmoments(data=out, n=self.n, m=self.m, patch_size=self.size) if kind == "real" else (
+                out if out2 is None else (out, out2))
+        if not to_host:
+            return res
         if kind == "real":
-            data = _host_f64(out) if self._want_host(image) else out
-            return zmoments(data=data, n=self.n, m=self.m, patch_size=self.size)
-        return out if out2 is None else (out, out2)
+            return zmoments(data=_host_f64(res.data), n=self.n, m=self.m, patch_size=self.size)
+        if kind == "complex":
+            return res.cpu().numpy().astype(np.complex128)
+        if kind == "abs":
+            return _host_f64(res)
+        return tuple(_host_f64(t) for t in res)
+
+    def transform_peaks_batch(self, frames, pts_list, kind: str = "real"):
+        """``transform_peaks`` for a series of equally shaped HOST frames (an in-situ series, BASELINE config 5):
+        one call of ``zb200_project_peaks_host``, which pipelines the frames over two streams (upload of frame
+        f+1 and download + float64 widening of frame f-1 overlap the kernels of frame f).  ``frames`` is a
+        sequence of (H, W) numpy arrays (or one (F, H, W) array), ``pts_list`` one (P_f, 2) array of (x, y) per
+        frame.  Returns a list with one entry per frame: ``zmoments`` for kind='real', complex128 (P_f, Mc) for
+        'complex', float64 (P_f, Mc) for 'abs'."""
+        _lib.require_cuda()
+        lib = _lib.load()
+        code = {"real": _lib.OUT_REAL, "complex": _lib.OUT_COMPLEX, "abs": _lib.OUT_ABS}[kind]
+        frames = [np.ascontiguousarray(f, dtype=np.float32) for f in frames]
+        if len(frames) != len(pts_list):
+            raise ValueError("one array of peak coordinates per frame is required")
+        if not frames:
+            return []
+        h, w = frames[0].shape
+        for f in frames:
+            if f.ndim != 2 or f.shape != (h, w):
+                raise ValueError("all frames of a batch must be 2D arrays of one shape")
+        pts = [np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(-1, 2)) for q in pts_list]
+        counts = np.array([len(q) for q in pts], dtype=np.int64)
+        flat = np.ascontiguousarray(np.concatenate(pts)) if counts.sum() else np.zeros((0, 2))
+        n_c = lib.zb200_num_complex_modes(self.n_max)
+        if kind == "real":
+            out = np.empty((int(counts.sum()), len(self.n)), dtype=np.float64)
+        elif kind == "complex":
+            out = np.empty((int(counts.sum()), n_c), dtype=np.complex128)
+        else:
+            out = np.empty((int(counts.sum()), n_c), dtype=np.float64)
+        ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+        prec = self._precision_code()
+        _lib.check(lib.zb200_project_peaks_host(self._plan, ptrs, len(frames), int(h), int(w), np_ptr(flat), np_ptr(counts),
+                                                prec, code, _lib.F64, np_ptr(out)), "project_peaks_host")
+        edges = np.concatenate([[0], np.cumsum(counts)])
+        parts = [out[a:b] for a, b in zip(edges[:-1], edges[1:])]
+        if kind == "real":
+            return [zmoments(data=q, n=self.n, m=self.m, patch_size=self.size) for q in parts]
+        return parts
 
     # ------------------------------------------------------------ K4: dense map
     def _image_on_device(self, image):

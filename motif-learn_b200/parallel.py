@@ -66,6 +66,43 @@ def gather_ragged(local, dim: int = 0, sizes: Sequence[int] | None = None, group
     return out.movedim(0, dim)
 
 
+def gather_rows(local, out=None, sizes: Sequence[int] | None = None, group=None):
+    """All-gather of row blocks ``(n_r, ...)`` into ``out`` ``(sum n_r, ...)`` (allocated when None), in rank
+    order, on every rank -- the final feature gather of the path.  Equal blocks move with ONE
+    ``all_gather_into_tensor`` straight into ``out`` (no padding, no concatenation); ragged blocks are padded
+    to the largest one in a scratch buffer first."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist_info()
+    if world == 1:
+        if out is None:
+            return local
+        out.copy_(local)
+        return out
+    if sizes is None:
+        mine = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        every = torch.empty(world, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        sizes = [int(v) for v in every.tolist()]
+    total = int(sum(sizes))
+    if out is None:
+        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    local = local.contiguous()
+    if len(set(sizes)) == 1:
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    biggest = max(sizes)
+    padded = torch.zeros((biggest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    scratch = torch.empty((world * biggest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(scratch, padded, group=group)
+    at = 0
+    for r, s in enumerate(sizes):
+        out[at:at + s] = scratch[r * biggest:r * biggest + s]
+        at += s
+    return out
+
+
 def transform_patches_sharded(transform: Callable, patches, gather: bool = True):
     """Project this rank's contiguous shard of a replicated patch stack and (optionally) gather the
     feature rows of all ranks.  ``transform`` maps a patch tensor (n, k, k) to a tensor (n, F) --

@@ -57,7 +57,13 @@ def _worker(rank, world, port, n_patches, height, out_dir):
 
         smap = par.symmetry_map_sharded(fake_band, height)
         ragged = par.gather_ragged(torch.full((rank + 1, 2), float(rank)), dim=0)
-        torch.save({"feats": feats, "smap": smap, "ragged": ragged}, os.path.join(out_dir, f"r{rank}.pt"))
+        # gather_rows: equal blocks land straight in a preallocated buffer, ragged blocks via padding
+        even_out = torch.full((2 * 3, 4), -1.0)
+        got = par.gather_rows(torch.full((3, 4), float(rank + 10)), out=even_out, sizes=[3, 3])
+        assert got is even_out
+        rows = par.gather_rows(torch.arange((rank + 2) * 5, dtype=torch.float64).reshape(rank + 2, 5) + 100 * rank)
+        torch.save({"feats": feats, "smap": smap, "ragged": ragged, "even": even_out, "rows": rows},
+                   os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -76,3 +82,7 @@ def test_world2_gloo_gathers(tmp_path, n_patches, height):
         assert torch.equal(got["feats"], want_feats)
         assert torch.equal(got["smap"], want_map)
         assert torch.equal(got["ragged"], torch.tensor([[0.0, 0.0], [1.0, 1.0], [1.0, 1.0]]))
+        assert torch.equal(got["even"], torch.cat([torch.full((3, 4), 10.0), torch.full((3, 4), 11.0)]))
+        want_rows = torch.cat([torch.arange(10, dtype=torch.float64).reshape(2, 5),
+                               torch.arange(15, dtype=torch.float64).reshape(3, 5) + 100])
+        assert torch.equal(got["rows"], want_rows)
