@@ -423,12 +423,18 @@ def make_patch_batch(ctx, n: int, seed: int):
     return out
 
 
-def gather_report(ctx, ms_full, ms_nogather, steps, units_per_step, nbytes_in):
-    """What the K5 gather cost: both figures, whole job."""
-    return {"collective": "all_gather_into_tensor (NCCL over NVLink)", "in_timed_step": True,
-            "ms_per_step_with_gather": ms_full / steps, "ms_per_step_no_gather": ms_nogather / steps,
-            "ms_gather": (ms_full - ms_nogather) / steps, "value_no_gather": units_per_step * steps / (ms_nogather / 1e3),
-            "bytes_received_per_rank_per_step": nbytes_in}
+def gather_report(ctx, how, ms_full, ms_nogather, ms_nccl, steps, units_per_step, nbytes_in):
+    """What the K5 gather cost, whole job: the timed step (`value`) uses `how`; beside it the same step without any
+    gather and with a plain NCCL all-gather after the kernel (the baseline the fused push is measured against)."""
+    out = {"how": how, "in_timed_step": True,
+           "ms_per_step_with_gather": ms_full / steps, "ms_per_step_no_gather": ms_nogather / steps,
+           "ms_gather": (ms_full - ms_nogather) / steps, "value_no_gather": units_per_step * steps / (ms_nogather / 1e3),
+           "bytes_received_per_rank_per_step": nbytes_in,
+           "receive_gbs_per_rank": nbytes_in * steps / (ms_full / 1e3) / 1e9}
+    if ms_nccl is not None:
+        out["nccl_after_kernel"] = {"ms_per_step": ms_nccl / steps, "value": units_per_step * steps / (ms_nccl / 1e3),
+                                    "what": "same kernel, then all_gather_into_tensor (NCCL) on the same stream"}
+    return out
 
 
 # --------------------------------------------------------------------------- patches (metric shape)
@@ -436,7 +442,7 @@ def bench_patches(ctx):
     import numpy as np
     torch, args, pk, world = ctx.torch, ctx.args, ctx.pk, ctx.world
     from motif_learn_b200.features import ZPs
-    from motif_learn_b200.parallel import gather_rows
+    from motif_learn_b200.parallel import PeerArray, gather_rows
     zo = _oracle()
     zp = ZPs(N_MAX, PATCH, precision=args.precision)
     prec = PREC_NAMES[zp._precision_code()]
@@ -444,15 +450,23 @@ def bench_patches(ctx):
     batch = args.batch
     patches = make_patch_batch(ctx, batch, seed=ctx.rank)          # batch * 16 KiB >> 126 MB L2
     gathered = torch.empty((world * batch, n_modes), dtype=torch.float32, device="cuda") if world > 1 else None
+    push = world > 1 and args.gather == "push" and prec in ("tf32", "tf32x3")
+    peers = PeerArray(world * batch, n_modes) if push else None
     hold = {}
 
     def compute():
         hold["z"] = zp.transform(patches).data
 
-    def step():
+    def step_nccl():
         compute()
-        if world > 1:
-            gather_rows(hold["z"], out=gathered, sizes=[batch] * world)
+        gather_rows(hold["z"], out=gathered, sizes=[batch] * world)
+
+    def step_push():
+        peers.begin()                                   # nobody still reads the previous round's rows
+        hold["z"] = zp.transform_allgather(patches, peers, ctx.rank * batch)
+        peers.fence()                                   # every rank's rows have landed in every copy
+
+    step = compute if world == 1 else (step_push if push else step_nccl)
 
     # parity of the timed batch itself: a 4096-patch sample against the oracle (float64 numpy.dot)
     compute()
@@ -474,7 +488,15 @@ def bench_patches(ctx):
     gather = None
     if world > 1:
         ms_ng, _, _ = timed(ctx, compute, args.steps, 1)
-        gather = gather_report(ctx, ms, ms_ng, args.steps, total, (world - 1) * batch * n_modes * 4)
+        ms_nccl, _, _ = timed(ctx, step_nccl, args.steps, 1)
+        if push:                                       # the pushed copies equal the NCCL gather bit for bit, on every rank
+            step_push()
+            torch.cuda.synchronize()
+            assert torch.equal(peers.local, gathered), "peer-pushed rows differ from the NCCL all-gather"
+        gather = gather_report(ctx, "fused: P2P stores over NVLink from a warp of the projection kernel" if push
+                               else "all_gather_into_tensor (NCCL) after the kernel", ms, ms_ng, ms_nccl if push else None,
+                               args.steps, total, (world - 1) * batch * n_modes * 4)
+        compute()
         assert torch.equal(gathered[ctx.rank * batch:(ctx.rank + 1) * batch], hold["z"]), "gathered rows differ from the local shard"
     else:
         ms_ng = ms
@@ -495,6 +517,8 @@ def bench_patches(ctx):
                          "value": total * sus_steps / (ms_s / 1e3), "achieved": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9,
                          "frac": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9 / pk["hbm_gbs"], "clocks": clocks_s}
 
+    if peers is not None:
+        peers.close()
     e2e = e2e_patches(ctx, zp, n_modes)
     cfg = workload_config("patches", world)
     cfg["batch_per_gpu"] = batch
@@ -533,18 +557,24 @@ def e2e_patches(ctx, zp, n_modes):
     ref = zo.project_patches(zo.extract_patches(frames[1], pts_list[1][:512], PATCH).astype(np.float64), zp.polynomials)
     fp32_close(res[1].data[:512], ref, "e2e frame route")
     steps = max(2, min(args.steps, 5))
-    if world > 1:
-        ctx.dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        res = zp_host.transform_peaks_batch(frames, pts_list)
-    dt = ctx.max_over_ranks(time.perf_counter() - t0)
     n_patches = sum(len(q) for q in pts_list)
-    assert sum(r.data.shape[0] for r in res) == n_patches and res[0].data.dtype == np.float64
-    out = {"value": ctx.sum_over_ranks(n_patches) * steps / dt, "unit": "patches/s",
+    result = np.zeros((n_patches, n_modes))                                 # a frame loop keeps ONE result buffer (out=)
+    rates = {}
+    for label, kw in (("reused_out", {"out": result}), ("fresh_out", {})):
+        if world > 1:
+            ctx.dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = zp_host.transform_peaks_batch(frames, pts_list, **kw)
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        assert sum(r.data.shape[0] for r in res) == n_patches and res[0].data.dtype == np.float64
+        rates[label] = ctx.sum_over_ranks(n_patches) * steps / dt
+    out = {"value": rates["reused_out"], "unit": "patches/s",
            "h2d_bytes_per_step": n_frames * 2048 * 2048 * 4 + n_patches * 16, "d2h_bytes_per_step": n_patches * n_modes * 4,
            "steps": steps, "patches_per_step": n_patches,
-           "api": "ZPs.transform_peaks_batch(8 pinned numpy frames, peak lists) -> zb200_project_peaks_host -> float64 numpy"}
+           "api": "ZPs.transform_peaks_batch(8 pinned numpy frames, peak lists, out=buffer) -> zb200_project_peaks_host -> float64 numpy",
+           "fresh_result_array_per_call": {"value": rates["fresh_out"], "unit": "patches/s",
+                                           "what": "same call without out=: a new 120 MB float64 array per call pays its page faults"}}
     # --- patch-stack route, pageable (what a reference user holds) and pinned
     n_e2e = min(args.batch, args.e2e_batch)
     base = zo.extract_patches(frames[0], pts_list[0][:8192], PATCH)
@@ -598,7 +628,7 @@ def bench_map(ctx, tiled=False):
     torch, args, pk, world, rank = ctx.torch, ctx.args, ctx.pk, ctx.world, ctx.rank
     from motif_learn_b200.datasets import honeycomb_frame_gpu
     from motif_learn_b200.features import ZPs
-    from motif_learn_b200.parallel import gather_rows, row_band, shard_sizes
+    from motif_learn_b200.parallel import PeerArray, gather_rows, push_score_bands, row_band, shard_sizes
     name = "map4k" if tiled else "map"
     size, window = (4096, 64) if tiled else (2048, 48)
     zp = ZPs(N_MAX, window, precision=args.precision)
@@ -615,13 +645,23 @@ def bench_map(ctx, tiled=False):
     # the band is (F, rows, W); gathering along rows = all-gather of (rows, F, W) blocks in rank order
     full = torch.empty((size, len(FOLDS), size), dtype=torch.float32, device="cuda") if do_gather else None
 
+    push = do_gather and args.gather == "push"
+    peers = PeerArray(len(FOLDS) * size, size) if push else None       # every rank's copy of the (F, H, W) score map
+
     def compute():
         hold["s"] = zp.symmetry_map(dimg, FOLDS, row0=row0, rows=rows)
 
-    def step():
+    def step_nccl():
         compute()
-        if do_gather:
-            gather_rows(hold["s"].permute(1, 0, 2), out=full, sizes=shard_sizes(size, world))
+        gather_rows(hold["s"].permute(1, 0, 2), out=full, sizes=shard_sizes(size, world))
+
+    def step_push():
+        peers.begin()
+        compute()
+        push_score_bands(peers, hold["s"], row0, size)                 # copy engines: F row bands per peer in one 2-D copy
+        peers.fence()
+
+    step = step_push if push else (step_nccl if do_gather else compute)
 
     compute()
     err, n_px = parity_map_sample(zp, dimg, hold["s"], row0, rows)
@@ -639,8 +679,17 @@ def bench_map(ctx, tiled=False):
     ms_ng = ms
     if do_gather:
         ms_ng, _, _ = timed(ctx, compute, steps, 1, between=flush)
-        gather = gather_report(ctx, ms, ms_ng, steps, units, (size - rows) * len(FOLDS) * size * 4)
+        ms_nccl, _, _ = timed(ctx, step_nccl, steps, 1, between=flush)
+        if push:
+            step_push()
+            torch.cuda.synchronize()
+            assert torch.equal(peers.local.view(len(FOLDS), size, size), full.permute(1, 0, 2)), "pushed score map differs from the NCCL gather"
+        gather = gather_report(ctx, "row bands forwarded to every peer by the copy engines (cudaMemcpy2DAsync over NVLink)" if push
+                               else "all_gather_into_tensor (NCCL) after the kernel", ms, ms_ng, ms_nccl if push else None,
+                               steps, units, (size - rows) * len(FOLDS) * size * 4)
         assert torch.equal(full[row0:row0 + rows].permute(1, 0, 2), hold["s"]), "gathered band differs from the local one"
+    if peers is not None:
+        peers.close()
     flops = 2.0 * rows * size * window * window * len(zp.n)
     ach = flops * steps / (ms_ng / 1e3) / 1e12
     # denominator: the measured dense bf16 rate for the kind::f16 kernels (same tensor-pipe rate), the tf32 rate for
@@ -690,7 +739,7 @@ def bench_c3(ctx):
     import numpy as np
     torch, args, pk, world, rank = ctx.torch, ctx.args, ctx.pk, ctx.world, ctx.rank
     from motif_learn_b200.features import ZPs
-    from motif_learn_b200.parallel import gather_rows, shard_range, shard_sizes
+    from motif_learn_b200.parallel import PeerArray, gather_rows, shard_range, shard_sizes
     zo = _oracle()
     total = args.c3_total
     lo, hi = shard_range(total, rank, world)
@@ -702,14 +751,23 @@ def bench_c3(ctx):
     gathered = torch.empty((total, n_c), dtype=torch.complex64, device="cuda") if world > 1 else None
     hold = {}
 
+    push = world > 1 and args.gather == "push" and prec in ("tf32", "tf32x3")
+    peers = PeerArray(total, 2 * n_c) if push else None
+
     def compute(kind="complex"):
         hold["z"] = zp.transform_features(patches, kind)
 
-    def step():
+    def step_nccl():
         compute()
-        if world > 1:
-            gather_rows(torch.view_as_real(hold["z"]).reshape(n, 2 * n_c), out=torch.view_as_real(gathered).reshape(total, 2 * n_c),
-                        sizes=shard_sizes(total, world))
+        gather_rows(torch.view_as_real(hold["z"]).reshape(n, 2 * n_c), out=torch.view_as_real(gathered).reshape(total, 2 * n_c),
+                    sizes=shard_sizes(total, world))
+
+    def step_push():
+        peers.begin()
+        hold["z"] = torch.view_as_complex(zp.transform_allgather(patches, peers, lo, "complex").view(n, n_c, 2))
+        peers.fence()
+
+    step = compute if world == 1 else (step_push if push else step_nccl)
 
     compute()
     rows = sample_rows(n)
@@ -734,8 +792,18 @@ def bench_c3(ctx):
     ms_ng = ms
     if world > 1:
         ms_ng, _, _ = timed(ctx, compute, steps, 1)
-        gather = gather_report(ctx, ms, ms_ng, steps, total, (total - n) * n_c * 8)
+        ms_nccl, _, _ = timed(ctx, step_nccl, steps, 1)
+        if push:
+            step_push()
+            torch.cuda.synchronize()
+            assert torch.equal(peers.local, torch.view_as_real(gathered).reshape(total, 2 * n_c)), "pushed rows differ from the NCCL gather"
+        gather = gather_report(ctx, "fused: P2P stores over NVLink from a warp of the projection kernel" if push
+                               else "all_gather_into_tensor (NCCL) after the kernel", ms, ms_ng, ms_nccl if push else None,
+                               steps, total, (total - n) * n_c * 8)
+        compute()
         assert torch.equal(gathered[lo:hi], hold["z"]), "gathered rows differ from the local shard"
+    if peers is not None:
+        peers.close()
     ms_abs, _, _ = timed(ctx, lambda: compute("abs"), steps, 1)
     alg_bytes = n * (PATCH * PATCH * 4 + n_c * 8)
     flops = 2.0 * n * PATCH * PATCH * 231
@@ -815,7 +883,8 @@ def bench_c5(ctx):
     if world > 1:
         ms_ng, _, _ = timed(ctx, compute, steps, 1)
         mine = float(sum(hold["counts"]))
-        gather = gather_report(ctx, ms, ms_ng, steps, n_patches, int((n_patches - mine) * n_c * 4))
+        gather = gather_report(ctx, "ragged all_gather_into_tensor (NCCL) of the per-rank feature blocks, sizes exchanged first",
+                               ms, ms_ng, None, steps, n_patches, int((n_patches - mine) * n_c * 4))
         assert hold["all"].shape[0] == int(n_patches)
     cfg = workload_config("c5", world)
     details = {"frames_total": n_frames_total, "frames_per_gpu": hi - lo, "patches_total": int(n_patches),
@@ -850,6 +919,8 @@ def main():
     ap.add_argument("--also", default="all", help="comma list of the other workloads to carry under 'also' (all | none | names)")
     ap.add_argument("--no-also", action="store_true", help="same as --also none")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--gather", default="push", choices=["push", "nccl"],
+                    help="N>1: how the timed step gathers the features (push = fused P2P stores / copy engines; nccl = all_gather after the kernel)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)                                   # timing rule: at least 3 warm-up steps
 

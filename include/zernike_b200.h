@@ -27,6 +27,7 @@
 #ifndef ZERNIKE_B200_H_
 #define ZERNIKE_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -145,6 +146,26 @@ int zb200_project_patches_host(const zb200_plan* plan, const float* h_patches, i
 int zb200_project_peaks_host(const zb200_plan* plan, const float* const* h_frames, int n_frames, int H, int W,
                              const double* h_pts_xy, const int64_t* h_counts, int precision, int out_kind,
                              int out_dtype, void* h_out);
+
+/* ---- K5: final feature gather over NVLink peer memory (the reference is single-process) ------ */
+/* One process per GPU.  Every rank allocates its copy of the gathered array with zb200_peer_buffer_alloc, hands the
+ * 64-byte handle to the other ranks (any transport), which map it with zb200_peer_buffer_open (CUDA IPC, peer
+ * access enabled lazily).  zb200_project_patches_push_f32 is zb200_project_patches_f32 whose kernel ALSO writes
+ * every finished tile of output rows to the same rows of the peers' copies (P2P stores over NVLink from a warp of
+ * the projection kernel, overlapped with the computation of the next tiles): d_out = this rank's rows inside its
+ * own copy, d_out_peers[g] = the same rows inside peer g's copy (equal modulo 16 bytes).  The rows are complete on
+ * every rank once all ranks' kernels have finished (order that with a barrier / collective on the stream).
+ * Tensor-core precisions only; out_kind REAL | COMPLEX | ABS. */
+#define ZB200_IPC_HANDLE_BYTES 64
+int zb200_peer_buffer_alloc(size_t bytes, void** d_ptr, unsigned char* handle /* [64] */);
+int zb200_peer_buffer_free(void* d_ptr);
+int zb200_peer_buffer_open(const unsigned char* handle /* [64] */, void** d_ptr);
+int zb200_peer_buffer_close(void* d_ptr);
+int zb200_project_patches_push_f32(const zb200_plan* plan, const float* d_patches, int64_t n_patches, int precision,
+                                   int out_kind, void* d_out, void* const* d_out_peers, int n_peers, void* stream);
+/* Copy-engine forwarding of a 2-D block (e.g. the F row bands of a score map) into a peer's array. */
+int zb200_peer_copy_2d(void* d_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t width_bytes,
+                       size_t height, void* stream);
 
 /* ---- K4: dense map (replaces ZPs._transform_fft_convolve, _zps.py:159-193) --- */
 /* Moments at every pixel of rows [row0,row0+rows): d_out float [M,rows,W].

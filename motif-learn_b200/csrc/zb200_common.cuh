@@ -148,9 +148,15 @@ struct GatherSource {
     const float* planes = nullptr;
     int Wp = 0, L = 0;
 };
+// K5 fused into K3: the same output rows inside up to 7 peer GPUs' result arrays (device pointers valid on this
+// device: CUDA IPC mappings with peer access, zb200_peer.cu)
+struct PeerTargets {
+    int n = 0;
+    float* out[7] = {};
+};
 int project_tc(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind,
                void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
-               cudaStream_t s, const GatherSource* gather = nullptr);
+               cudaStream_t s, const GatherSource* gather = nullptr, const PeerTargets* peers = nullptr);
 bool tc_supported(const zb200_plan* plan, int precision, bool complex_order);
 
 int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,

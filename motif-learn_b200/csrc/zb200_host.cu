@@ -5,7 +5,9 @@
 // thread, and the per-plan staging buffers, guarded by the plan's mutex (calls on one plan serialise).
 #include "zb200_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -95,8 +97,11 @@ bool is_pinned(const void* h) {
     return pinned;
 }
 
-// ---- two-slot pipeline: enqueue(c, slot) on the calling thread, drain(c, slot) on a second thread once the
-// event of the slot has fired.  Slot b is reused by item c only after item c-2 has been drained. ---------------
+// ---- kSlots-deep pipeline: enqueue(c, slot) on the calling thread, drain(c, slot) on a second thread once the
+// event of the slot has fired.  Slot c % kSlots is reused by item c only after item c - kSlots has been drained.
+// Three slots: the chain upload -> gather -> projection -> download -> widening of one frame is ~1 ms long while
+// its longest stage (the upload) is 0.3 ms; two slots ran at 0.56 ms per 2048^2 frame, three reach the bus rate.
+constexpr int kSlots = 3;
 struct PipeSync {
     std::mutex m;
     std::condition_variable cv;
@@ -105,10 +110,21 @@ struct PipeSync {
     std::string msg;
 };
 
+static bool host_trace() {
+    static const bool on = getenv("ZB200_HOST_TRACE") != nullptr;      // read once; diagnostics on stderr
+    return on;
+}
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 template <class Enqueue, class Drain>
 int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drain drain) {
     if (n_items <= 0) return ZB200_OK;
     PipeSync ps;
+    const bool trace = host_trace();
+    double t_enq = 0, t_slot = 0, t_evsync = 0, t_drain = 0;
+    const double t_begin = now_ms();
     std::thread drainer([&] {
         cudaSetDevice(device);
         for (int64_t c = 0; c < n_items; ++c) {
@@ -118,13 +134,16 @@ int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drai
                 if (ps.rc) return;
             }
             int r = ZB200_OK;
-            cudaError_t e = cudaEventSynchronize(ev[c & 1]);
+            const double t0 = trace ? now_ms() : 0;
+            cudaError_t e = cudaEventSynchronize(ev[c % kSlots]);
+            const double t1 = trace ? now_ms() : 0;
             if (e != cudaSuccess) {
                 set_error("host pipeline: %s", cudaGetErrorString(e));
                 r = ZB200_ECUDA;
             } else {
-                r = drain(c, (int)(c & 1));
+                r = drain(c, (int)(c % kSlots));
             }
+            if (trace) { t_evsync += t1 - t0; t_drain += now_ms() - t1; }
             std::lock_guard<std::mutex> lk(ps.m);
             if (r) { ps.rc = r; ps.msg = zb200_last_error(); }
             ps.drained = c + 1;
@@ -133,12 +152,15 @@ int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drai
         }
     });
     for (int64_t c = 0; c < n_items; ++c) {
+        const double t0 = trace ? now_ms() : 0;
         {
             std::unique_lock<std::mutex> lk(ps.m);
-            ps.cv.wait(lk, [&] { return ps.drained >= c - 1 || ps.rc; });
+            ps.cv.wait(lk, [&] { return ps.drained >= c - (kSlots - 1) || ps.rc; });
             if (ps.rc) break;
         }
-        const int r = enq(c, (int)(c & 1));
+        const double t1 = trace ? now_ms() : 0;
+        const int r = enq(c, (int)(c % kSlots));
+        if (trace) { t_slot += t1 - t0; t_enq += now_ms() - t1; }
         std::lock_guard<std::mutex> lk(ps.m);
         if (r) { ps.rc = r; ps.msg = zb200_last_error(); }
         else ps.enqueued = c + 1;
@@ -146,6 +168,9 @@ int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drai
         if (r) break;
     }
     drainer.join();
+    if (trace)
+        fprintf(stderr, "[zb200 host pipeline] items %lld total %.2f ms | main: enqueue %.2f, waiting for a slot %.2f | drainer: "
+                "event wait %.2f, drain %.2f\n", (long long)n_items, now_ms() - t_begin, t_enq, t_slot, t_evsync, t_drain);
     if (ps.rc) {
         set_error("%s", ps.msg.c_str());
         cudaDeviceSynchronize();                     // nothing of this call is left in flight on the staging buffers
@@ -178,21 +203,21 @@ int ensure_buf(void** ptr, size_t* cap, size_t need, BufKind kind) {
 }  // namespace
 
 struct HostPipe {
-    cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    // slots: input staging (pinned), result staging (pinned), device input, device patches, device points, device result
-    void* pin_in[2] = {nullptr, nullptr};   size_t pin_in_cap[2] = {0, 0};
-    void* pin_out[2] = {nullptr, nullptr};  size_t pin_out_cap[2] = {0, 0};
-    void* dev_in[2] = {nullptr, nullptr};   size_t dev_in_cap[2] = {0, 0};
-    void* dev_pat[2] = {nullptr, nullptr};  size_t dev_pat_cap[2] = {0, 0};
-    void* dev_pts[2] = {nullptr, nullptr};  size_t dev_pts_cap[2] = {0, 0};
-    void* dev_out[2] = {nullptr, nullptr};  size_t dev_out_cap[2] = {0, 0};
+    cudaStream_t st[kSlots] = {};
+    cudaEvent_t ev[kSlots] = {};
+    // per slot: input staging (pinned), result staging (pinned), device input, device patches, device points, device result
+    void* pin_in[kSlots] = {};   size_t pin_in_cap[kSlots] = {};
+    void* pin_out[kSlots] = {};  size_t pin_out_cap[kSlots] = {};
+    void* dev_in[kSlots] = {};   size_t dev_in_cap[kSlots] = {};
+    void* dev_pat[kSlots] = {};  size_t dev_pat_cap[kSlots] = {};
+    void* dev_pts[kSlots] = {};  size_t dev_pts_cap[kSlots] = {};
+    void* dev_out[kSlots] = {};  size_t dev_out_cap[kSlots] = {};
 };
 
 void free_host_pipe(zb200_plan* p) {
     HostPipe* h = p->host;
     if (!h) return;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
         if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
         cudaFree(h->dev_in[i]);
@@ -211,7 +236,7 @@ static int host_pipe(zb200_plan* p, HostPipe** out) {
         HostPipe* h = new (std::nothrow) HostPipe();
         if (!h) { set_error("out of host memory"); return ZB200_ENOMEM; }
         p->host = h;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSlots; ++i) {
             if (cudaStreamCreateWithFlags(&h->st[i], cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) {
                 set_error("host pipeline: cannot create stream/event: %s", cudaGetErrorString(cudaGetLastError()));
@@ -249,7 +274,7 @@ extern "C" int zb200_project_patches_host(const zb200_plan* plan, const float* h
     if (chunk > n) chunk = n;
     const int M = p->n_modes;
     const bool pinned = is_pinned(h_patches);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kSlots && b < ceil_div(n, chunk); ++b) {
         if (!pinned && (rc = ensure_buf(&h->pin_in[b], &h->pin_in_cap[b], sizeof(float) * chunk * p->kk, kPinned))) return rc;
         if ((rc = ensure_buf(&h->pin_out[b], &h->pin_out_cap[b], sizeof(float) * chunk * M, kPinned))) return rc;
         if ((rc = ensure_buf(&h->dev_in[b], &h->dev_in_cap[b], sizeof(float) * chunk * p->kk, kDevice))) return rc;
@@ -314,7 +339,7 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
     const size_t frame_bytes = sizeof(float) * (size_t)H * W;
     bool all_pinned = true;
     for (int f = 0; f < n_frames && all_pinned; ++f) all_pinned = is_pinned(h_frames[f]);
-    for (int b = 0; b < 2 && b < n_frames; ++b) {
+    for (int b = 0; b < kSlots && b < n_frames; ++b) {
         if (!all_pinned && (rc = ensure_buf(&h->pin_in[b], &h->pin_in_cap[b], frame_bytes, kPinned))) return rc;
         if ((rc = ensure_buf(&h->pin_out[b], &h->pin_out_cap[b], sizeof(float) * max_count * L, kPinned))) return rc;
         if ((rc = ensure_buf(&h->dev_in[b], &h->dev_in_cap[b], frame_bytes, kDevice))) return rc;

@@ -33,11 +33,14 @@ project_simt_kernel(const float* __restrict__ A, long long n_patches, int kk,
     const int b_k = tid >> 4;            // 0..15
     const int b_c = (tid & 15) * 4;      // 0..60
 
-    float acc[8][4];
+    // two-level sum: `acc` runs over 16 slabs (256 taps), then is folded into `tot`.  One 4096-term fp32 chain
+    // left 2.4e-6 * max|Z| on the antisymmetric low modes (|Z| small, partial sums large) -- right AT the parity
+    // gate atol = 1e-6 * max; with 256-term chains the error is a quarter of that.
+    float acc[8][4], tot[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = tot[i][j] = 0.f;
 
     float4 ra[2], rb;
     auto load_tile = [&](int k0) {
@@ -92,11 +95,21 @@ project_simt_kernel(const float* __restrict__ A, long long n_patches, int kk,
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
+        if ((s & 15) == 15) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+        }
         if (s + 1 < n_slabs) {
             store_tile(buf ^ 1);
             __syncthreads();
         }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tot[i][j] += acc[i][j];
 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -105,7 +118,7 @@ project_simt_kernel(const float* __restrict__ A, long long n_patches, int kk,
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = n0 + 4 * tn + j;
-            if (c < n_modes) C[r * n_modes + c] = acc[i][j];
+            if (c < n_modes) C[r * n_modes + c] = tot[i][j];
         }
     }
 }

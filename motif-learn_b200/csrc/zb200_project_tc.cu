@@ -50,6 +50,8 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsi
 
 
 
+constexpr int kMaxPeers = 7;
+
 struct Params {
     long long n_patches;
     int n_tiles;          // ceil(n_patches / (128*subtiles))
@@ -84,6 +86,10 @@ struct Params {
     int g_H, g_W, g_k;
     const int2* g_xy;     // top-left corner (x0, y0) of every patch window
     int dbg;              // ZB200_TC_DEBUG bitmask: experiments only (results are wrong when set)
+    // K5 fused into K3: copies of the output rows go to the same rows of up to 7 peer GPUs' result arrays over
+    // NVLink (P2P stores from an otherwise idle warp, tile by tile while the next tiles are being computed)
+    int n_peers;
+    float* peer_out[kMaxPeers];
 };
 
 // ---- epilogue: 16 accumulator columns of one patch -----------------------------------------------
@@ -149,6 +155,59 @@ __device__ __forceinline__ void finish_scores(const Params& p, long long row, co
         if (f < p.n_folds) p.out[row * p.n_folds + f] = sc.num[f] / den;
 }
 
+// ---- K5 inside K3: one warp forwards finished output tiles to the peer GPUs ----------------------------------
+// The epilogue warps store a tile's rows to the local result array, fence, and bump `done` (shared memory, one
+// count per storing warp; a monotonic counter, not an mbarrier: the epilogue never waits for the pusher, so phases
+// could wrap).  The pusher warp then reads the tile's rows back through L2 (ld.cg: a line that straddles two tiles
+// must not be served from a stale L1 copy) and writes them to the same offsets of every peer's array with 16-byte
+// stores -- fully coalesced 512-B warp stores, the packet size NVLink moves efficiently, where the epilogue's own
+// 4-byte stores at a 364-byte stride would not.
+__device__ __forceinline__ void push_tile(const Params& p, long long r0, int n_rows, int lane) {
+    const size_t nf = (size_t)n_rows * p.row_len;
+    const float* src = p.out + (size_t)r0 * p.row_len;
+    size_t head = ((16u - (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 2;
+    if (head > nf) head = nf;
+    const size_t nv = (nf - head) >> 2, tail0 = head + (nv << 2);
+    const size_t off = (size_t)r0 * p.row_len;
+    // at most 3 leading and 3 trailing floats around the 16-byte aligned body
+    if ((size_t)lane < head) {
+        const float v = __ldcg(src + lane);
+        for (int g = 0; g < p.n_peers; ++g) p.peer_out[g][off + lane] = v;
+    }
+    if (tail0 + lane < nf) {
+        const float v = __ldcg(src + tail0 + lane);
+        for (int g = 0; g < p.n_peers; ++g) p.peer_out[g][off + tail0 + lane] = v;
+    }
+    // two 16-byte loads in flight per lane: the pusher lives in the control warpgroup (48 registers per thread after
+    // setmaxnreg.dec), so the loop is kept small; its latency is hidden behind a whole tile of computation
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    for (size_t i = lane; i < nv; i += 64) {
+        const bool two = i + 32 < nv;
+        const uint4 a = __ldcg(s4 + i);
+        uint4 b = a;
+        if (two) b = __ldcg(s4 + i + 32);
+        for (int g = 0; g < p.n_peers; ++g) {
+            uint4* d4 = reinterpret_cast<uint4*>(p.peer_out[g] + off + head);
+            d4[i] = a;
+            if (two) d4[i + 32] = b;
+        }
+    }
+}
+
+__device__ __forceinline__ void pusher_loop(const Params& p, volatile unsigned* done, int warps_per_tile, int my_tiles, int lane) {
+    const int tile_rows = p.subtiles * kTileRows;
+    for (int t = 0; t < my_tiles; ++t) {
+        const long long r0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * tile_rows;
+        if (r0 >= p.n_patches) break;
+        const unsigned want = (unsigned)(t + 1) * (unsigned)warps_per_tile;
+        while (*done < want) __nanosleep(256);
+        __syncwarp();
+        const long long left = p.n_patches - r0;
+        push_tile(p, r0, (int)(left < tile_rows ? left : tile_rows), lane);
+    }
+    __threadfence_system();
+}
+
 // ================================================================================================
 // 1 x TF32: raw fp32 operands, the tensor core truncates them to tf32 (stated bound 1e-3 * max|Z|)
 // ================================================================================================
@@ -168,12 +227,14 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t* acc_full = bars + 2 * p.n_stages;   // accumulator complete      [2]
     uint64_t* acc_empty = acc_full + 2;           // accumulator drained       [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    unsigned* out_done = reinterpret_cast<unsigned*>(tmem_slot + 1);     // epilogue warps that finished storing a tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_x);
         prefetch_tmap(&map_b);
+        *out_done = 0;
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
@@ -290,7 +351,14 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (p.n_peers) {
+                __threadfence();                              // this tile's rows are in L2 before the pusher is told
+                __syncwarp();
+                if (lane == 0) atomicAdd(out_done, 1u);
+            }
         }
+    } else if (warp == 3 && p.n_peers) {
+        pusher_loop(p, out_done, 4, my_tiles, lane);
     }
 
     tc_fence_before();
@@ -341,6 +409,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint64_t* acc_empty = acc_full + 2;           // chunk drained by the epilogue            [2]
     uint64_t* bpeer = acc_empty + 2;              // pair mode: the peer CTA's half of a B k-block landed [4]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bpeer + 4);
+    unsigned* out_done = reinterpret_cast<unsigned*>(tmem_slot + 1);     // epilogue warps that finished storing a tile
 
     // Warp-role layout.  The SM's issue arbiter prefers the highest warp id of a sub-partition, and
     // every sub-partition hosts one busy splitter warp, so the latency-critical single-thread roles
@@ -358,6 +427,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         prefetch_tmap(&map_x);
         prefetch_tmap(&map_bhi);
         prefetch_tmap(&map_blo);
+        *out_done = 0;
     }
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
@@ -569,6 +639,9 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 }
             }
             __syncwarp();
+        } else if (warp == kWarpAlloc && p.n_peers) {
+            // ===================== K5: forward finished tiles to the peer GPUs =====================
+            pusher_loop(p, out_done, p.epi_solo ? 4 : 8, my_tiles, lane);
         }
     } else if (wg == 0) {
         // ===================== splitter =====================
@@ -788,6 +861,11 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 }
                 if constexpr (kOut == kOutScores) finish_scores(p, row, sc);   // host guarantees subtiles == 2
             }
+            if (p.n_peers) {
+                __threadfence();                              // this tile's rows are in L2 before the pusher is told
+                __syncwarp();
+                if (lane == 0) atomicAdd(out_done, 1u);
+            }
         }
     }
 
@@ -845,11 +923,12 @@ static int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t
 
 }  // namespace tc
 
-// 1xTF32 needs one UMMA N (<= 256 operand rows); tf32x3 additionally keeps two accumulator sets
-// plus the Xlo staging in the 512 TMEM columns: 2*n_pad + 32 <= 512  ->  n_pad <= 240.
+// Both kernels need one UMMA N (<= 256 operand rows).  tf32x3 keeps two accumulator sets plus the operand staging
+// in the 512 TMEM columns while 2*n_pad + 32 <= 512; wider operands (n_max = 20: 231 real rows -> 240, 242
+// complex-interleaved rows -> 256) run with ONE set and four staging buffers (256 + 4*32 columns).
 static bool operand_ok(const Operand& op, int precision) {
-    if (!op.has_tmap) return false;
-    return precision == ZB200_PREC_TF32X3 ? op.rows_pad <= 240 : op.rows_pad <= 256;
+    (void)precision;
+    return op.has_tmap && op.rows_pad <= 256;
 }
 
 bool tc_supported(const zb200_plan* p, int precision, bool complex_order) {
@@ -884,7 +963,7 @@ int init_tensor_maps(zb200_plan* p) {
 
 int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind, void* d_out,
                void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind, cudaStream_t s,
-               const GatherSource* gsrc) {
+               const GatherSource* gsrc, const PeerTargets* peers) {
     using namespace tc;
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG(gsrc || (reinterpret_cast<uintptr_t>(d_patches) & 15) == 0,
@@ -900,7 +979,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     if (!tc_supported(p, precision, cplx)) {
         set_error("tcgen05 projection (precision %d, %s order) unsupported for n_max=%d size=%d: needs sm_100, even "
                   "size and <= %d operand rows (have %d)", precision, cplx ? "complex" : "real", p->n_max, p->size,
-                  x3 ? 240 : 256, op.rows_pad);
+                  256, op.rows_pad);
         return ZB200_EUNSUP;
     }
 
@@ -936,6 +1015,14 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
         prm.g_W = gsrc->W;
         prm.g_k = p->size;
         prm.g_xy = gsrc->xy0;
+    }
+    if (peers && peers->n > 0) {
+        if (peers->n > kMaxPeers || out_kind == ZB200_OUT_ABS_PHASE) {
+            set_error("project: peer push supports at most %d peers and one output array", kMaxPeers);
+            return ZB200_EUNSUP;
+        }
+        prm.n_peers = peers->n;
+        for (int g = 0; g < peers->n; ++g) prm.peer_out[g] = peers->out[g];
     }
     if (const char* e = getenv("ZB200_TC_DEBUG")) prm.dbg = atoi(e);
     if (prm.dbg & 4) prm.chunk_kb = prm.k_blocks;

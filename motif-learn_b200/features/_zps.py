@@ -273,6 +273,35 @@ class ZPs(BaseEstimator, TransformerMixin):
                                                  self._stream()), "project_patches")
         return out if out2 is None else (out, out2)
 
+    def transform_allgather(self, images, peers, row0: int, kind: str = "real"):
+        """Multi-GPU ``transform`` whose final feature gather is part of the projection kernel:
+        this rank's CUDA patch stack ``images`` (n, k, k) is projected and the rows land at ``[row0, row0 + n)`` of
+        ``peers`` (a ``motif_learn_b200.parallel.PeerArray`` of ``(total, cols)`` float32, cols = M | 2*Mc | Mc for
+        kind 'real' | 'complex' | 'abs') ON EVERY RANK: finished tiles are forwarded to the other GPUs over NVLink by
+        a warp of the kernel while the next tiles are computed.  Call ``peers.fence()`` afterwards; then
+        ``peers.local`` holds all ranks' rows.  Tensor-core precisions only."""
+        self._validate_size(images)
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        code = {"real": _lib.OUT_REAL, "complex": _lib.OUT_COMPLEX, "abs": _lib.OUT_ABS}[kind]
+        cols = {"real": len(self.n), "complex": 2 * lib.zb200_num_complex_modes(self.n_max),
+                "abs": lib.zb200_num_complex_modes(self.n_max)}[kind]
+        if peers.cols != cols:
+            raise ValueError(f"peer array has {peers.cols} columns, kind={kind!r} needs {cols}")
+        dev = images.to(device="cuda", dtype=torch.float32).contiguous()
+        n = int(dev.shape[0])
+        if row0 < 0 or row0 + n > peers.rows:
+            raise ValueError("rows [row0, row0 + n) fall outside the peer array")
+        prec = self._precision_code()
+        if prec not in (_lib.PREC_TF32, _lib.PREC_TF32X3) or not lib.zb200_plan_supports(self._plan, prec, code):
+            raise ValueError("transform_allgather needs a tensor-core precision supported for this shape")
+        others = [r for r in range(peers.world) if r != peers.rank]
+        ptrs = (C.c_void_p * max(1, len(others)))(*[peers.row_ptr(r, row0) for r in others])
+        _lib.check(lib.zb200_project_patches_push_f32(self._plan, int(dev.data_ptr()), n, prec, code,
+                                                      C.c_void_p(peers.row_ptr(peers.rank, row0)), ptrs, len(others),
+                                                      self._stream()), "project_patches_push")
+        return peers.local[row0:row0 + n]
+
     def symmetry_scores(self, images, n_folds, p=2, m_unselect=None):
         """Fused ``transform(patches).rot_maps(n_folds, p, m_unselect)`` -> (N, F): the n-fold scores of a
         patch stack computed in the projection kernel's epilogue (the moments never leave the SM).
@@ -371,13 +400,15 @@ class ZPs(BaseEstimator, TransformerMixin):
             return _host_f64(res)
         return tuple(_host_f64(t) for t in res)
 
-    def transform_peaks_batch(self, frames, pts_list, kind: str = "real"):
+    def transform_peaks_batch(self, frames, pts_list, kind: str = "real", out=None):
         """``transform_peaks`` for a series of equally shaped HOST frames (an in-situ series, BASELINE config 5):
         one call of ``zb200_project_peaks_host``, which pipelines the frames over two streams (upload of frame
         f+1 and download + float64 widening of frame f-1 overlap the kernels of frame f).  ``frames`` is a
         sequence of (H, W) numpy arrays (or one (F, H, W) array), ``pts_list`` one (P_f, 2) array of (x, y) per
         frame.  Returns a list with one entry per frame: ``zmoments`` for kind='real', complex128 (P_f, Mc) for
-        'complex', float64 (P_f, Mc) for 'abs'."""
+        'complex', float64 (P_f, Mc) for 'abs'.  ``out`` (optional) is a C-contiguous array of the result dtype with
+        at least sum(P_f) rows that receives the features -- a frame loop that reuses one buffer does not pay the
+        page faults of a fresh 100 MB allocation per call; the returned entries are views of it."""
         _lib.require_cuda()
         lib = _lib.load()
         code = {"real": _lib.OUT_REAL, "complex": _lib.OUT_COMPLEX, "abs": _lib.OUT_ABS}[kind]
@@ -394,12 +425,15 @@ class ZPs(BaseEstimator, TransformerMixin):
         counts = np.array([len(q) for q in pts], dtype=np.int64)
         flat = np.ascontiguousarray(np.concatenate(pts)) if counts.sum() else np.zeros((0, 2))
         n_c = lib.zb200_num_complex_modes(self.n_max)
-        if kind == "real":
-            out = np.empty((int(counts.sum()), len(self.n)), dtype=np.float64)
-        elif kind == "complex":
-            out = np.empty((int(counts.sum()), n_c), dtype=np.complex128)
+        shape = (int(counts.sum()), len(self.n) if kind == "real" else n_c)
+        dtype = np.complex128 if kind == "complex" else np.float64
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
         else:
-            out = np.empty((int(counts.sum()), n_c), dtype=np.float64)
+            if (not isinstance(out, np.ndarray) or out.dtype != dtype or out.ndim != 2 or out.shape[1] != shape[1]
+                    or out.shape[0] < shape[0] or not out.flags.c_contiguous):
+                raise ValueError(f"out must be a C-contiguous {np.dtype(dtype).name} array of shape (>= {shape[0]}, {shape[1]})")
+            out = out[:shape[0]]
         ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
         prec = self._precision_code()
         _lib.check(lib.zb200_project_peaks_host(self._plan, ptrs, len(frames), int(h), int(w), np_ptr(flat), np_ptr(counts),

@@ -125,3 +125,117 @@ def symmetry_map_sharded(band_fn: Callable, height: int, gather: bool = True):
     if not gather or world == 1:
         return band
     return gather_ragged(band, dim=1, sizes=shard_sizes(height, world))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K5 fused into the projection kernel: peer-memory result arrays
+# ---------------------------------------------------------------------------------------------------------------
+class _CudaBlock:
+    """A library-owned device allocation seen by torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerArray:
+    """A ``(rows, cols)`` float32 array that exists once per rank and is writable by EVERY rank of the node: each
+    process allocates its copy through the C ABI (``zb200_peer_buffer_alloc``), the CUDA IPC handles travel over
+    ``torch.distributed`` (plumbing), and every process maps the others' copies (``zb200_peer_buffer_open``).
+    ``ZPs.transform_allgather`` then lets the projection kernel write its output rows into all copies over NVLink
+    while it is still computing -- the final feature gather of SURVEY.md 8e without a separate collective.
+
+    ``local`` is this rank's copy as a CUDA tensor; ``fence()`` orders the copies: after it (on the current
+    stream) every rank's rows are complete in ``local``; call it once more before the NEXT round of writes if a
+    consumer on another rank may still be reading (``begin()``)."""
+
+    def __init__(self, rows: int, cols: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.rows, self.cols, self.group = int(rows), int(cols), group
+        self.rank, self.world = dist_info()
+        lib = _lib.load()
+        nbytes = max(16, self.rows * self.cols * 4)
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        _lib.check(lib.zb200_peer_buffer_alloc(nbytes, C.byref(ptr), handle), "peer_buffer_alloc")
+        self._lib, self._own = lib, ptr
+        self.local = torch.as_tensor(_CudaBlock(ptr.value, (self.rows, self.cols), "<f4"), device="cuda")
+        self.ptrs = [None] * self.world
+        self.ptrs[self.rank] = int(ptr.value)
+        self._opened = []
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    continue
+                other = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(hb)
+                _lib.check(lib.zb200_peer_buffer_open(buf, C.byref(other)), f"peer_buffer_open(rank {r})")
+                self.ptrs[r] = int(other.value)
+                self._opened.append(other)
+            self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def row_ptr(self, rank: int, row0: int) -> int:
+        return self.ptrs[rank] + int(row0) * self.cols * 4
+
+    def fence(self):
+        """Stream-ordered: returns (on the stream) when every rank's kernels queued before it have finished."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag, group=self.group)
+
+    begin = fence
+
+    def close(self):
+        """Unmap the peers' copies and free the own one (collective: every rank must call it)."""
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        torch.cuda.synchronize()
+        for p in self._opened:
+            _lib.check(self._lib.zb200_peer_buffer_close(p), "peer_buffer_close")
+        self._opened = []
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)            # nobody still maps the allocation that is freed next
+        self.local = None
+        if self._own is not None:
+            _lib.check(self._lib.zb200_peer_buffer_free(self._own), "peer_buffer_free")
+            self._own = None
+
+
+def push_band(arr: PeerArray, band, row0: int, stream=None):
+    """Forward ``band`` (rows, cols) -- already stored at rows [row0, row0+rows) of ``arr.local`` or any other
+    CUDA tensor -- into the same rows of every peer's copy with the copy engines (no SM work; used for the score
+    bands of the tiled dense map, whose kernel stores 4-byte words at a 16-byte stride -- a poor NVLink pattern)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    band = band.contiguous()
+    rows = int(band.shape[0])
+    st = C.c_void_p(_lib.current_stream_ptr() if stream is None else int(stream))
+    for r in range(arr.world):
+        if r == arr.rank:
+            if band.data_ptr() != arr.row_ptr(r, row0):
+                arr.local[row0:row0 + rows].copy_(band.reshape(rows, arr.cols))
+            continue
+        _lib.check(lib.zb200_peer_copy_2d(arr.row_ptr(r, row0), arr.cols * 4, int(band.data_ptr()), arr.cols * 4,
+                                          arr.cols * 4, rows, st), "peer_copy_2d")
+
+
+def push_score_bands(arr: PeerArray, band, row0: int, height: int, stream=None):
+    """Image-tile sharding of ONE frame (BASELINE config 4): ``arr`` is every rank's copy of the full ``(F, H, W)``
+    score map (a PeerArray of ``F*H`` rows), ``band`` this rank's ``(F, rows, W)`` result for rows ``[row0, row0+rows)``.
+    One 2-D copy per peer moves all F planes (source pitch rows*W, destination pitch H*W), driven by the copy
+    engines; the local copy is filled the same way."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    band = band.contiguous()
+    n_f, rows, width = (int(v) for v in band.shape)
+    st = C.c_void_p(_lib.current_stream_ptr() if stream is None else int(stream))
+    for r in range(arr.world):
+        _lib.check(lib.zb200_peer_copy_2d(arr.row_ptr(r, row0), height * width * 4, int(band.data_ptr()), rows * width * 4,
+                                          rows * width * 4, n_f, st), "peer_copy_2d")

@@ -168,7 +168,7 @@ def test_projection_shapes_vs_oracle(api, n_max, size, count):
             if prec == "tf32":
                 assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max()
             else:
-                fp32_close(got, ref, rtol=2e-4, scale=2e-6)
+                fp32_close(got, ref)                      # the stated gate: rtol 1e-4, atol 1e-6 * max|ref|
 
 
 def test_projection_edge_cases(api, torch):
@@ -463,7 +463,9 @@ def test_fused_gather_projection(api, torch):
     dense = z.transform(dimg).data
     c = np.rint(edge).astype(int)
     want = dense[:, torch.from_numpy(c[:, 1]).cuda(), torch.from_numpy(c[:, 0]).cuda()].cpu().numpy().T
-    fp32_close(got, want, rtol=2e-4, scale=3e-6)
+    # two fp32-grade KERNELS against each other (tf32x3 projection vs f16x3 dense map), each within the gate of
+    # the oracle: the difference may reach twice the atol term
+    fp32_close(got, want, rtol=1e-4, scale=2e-6)
     assert z.transform_peaks(dimg, np.zeros((0, 2))).data.shape == (0, 91)
 
 
@@ -796,6 +798,31 @@ def _nccl_worker(rank, world, port, out_dir):
         full = z.symmetry_map(img, [2, 3])
         whole = z.transform(patches).data
         ok = bool(torch.equal(feats, whole) and torch.equal(rows, whole) and torch.equal(smap, full))
+        # K5 fused into K3: the projection kernel writes its rows into every rank's copy (CUDA IPC peer memory)
+        big = torch.from_numpy(np.random.default_rng(5).random((70001, 32, 32), dtype=np.float32)).cuda()
+        lo, hi = par.shard_range(70001, rank, world)
+        for kind, cols in (("real", 66), ("abs", 36), ("complex", 72)):
+            arr = par.PeerArray(70001, cols)
+            arr.begin()
+            z.transform_allgather(big[lo:hi], arr, lo, kind)
+            arr.fence()
+            torch.cuda.synchronize()
+            if kind == "real":
+                want = z.transform(big).data
+            else:
+                want = z.transform_features(big, kind)
+                want = torch.view_as_real(want).reshape(70001, cols) if kind == "complex" else want
+            ok = ok and bool(torch.equal(arr.local, want))
+            arr.close()
+        # score bands of one frame through the copy engines
+        arr = par.PeerArray(2 * 200, 160)
+        r0, rr = par.row_band(200, rank, world)
+        arr.begin()
+        par.push_score_bands(arr, z.symmetry_map(img, [2, 3], row0=r0, rows=rr), r0, 200)
+        arr.fence()
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(arr.local.view(2, 200, 160), full))
+        arr.close()
         torch.save({"ok": ok, "n": int(feats.shape[0])}, os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
