@@ -511,7 +511,7 @@ def bench_patches(ctx):
             "tflops": flops * args.steps / (ms_ng / 1e3) / 1e12, "timed": "projection kernel only (the no-gather loop when N>1)"}
 
     # sustained leg: >= 2.5 s of back-to-back launches with the 2 ms clock sampler -- what a long job sees
-    sus_steps = max(args.steps, int(2500.0 / max(ms_ng / args.steps, 1e-3)))
+    sus_steps = args.steps if args.no_sustained else max(args.steps, int(2500.0 / max(ms_ng / args.steps, 1e-3)))
     ms_s, clocks_s, _ = timed(ctx, compute, sus_steps, 1)
     roof["sustained"] = {"steps": sus_steps, "seconds": ms_s / 1e3, "ms_per_step": ms_s / sus_steps,
                          "value": total * sus_steps / (ms_s / 1e3), "achieved": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9,
@@ -538,8 +538,8 @@ def e2e_patches(ctx, zp, n_modes):
     from motif_learn_b200.features import ZPs, clear_border
     zo = _oracle()
     zp_host = ZPs(N_MAX, PATCH, precision=args.precision, output="numpy")
-    # --- frame route: 8 pinned 2048^2 frames per step (a short in-situ series), ~21 k peaks each
-    n_frames = 8
+    # --- frame route: 16 pinned 2048^2 frames per step (a short in-situ series), ~21 k peaks each
+    n_frames = 16
     img, pts = honeycomb_image(1024, bond=12.0, seed=100 + ctx.rank)
     tile = np.tile(img, (2, 2))                                             # 2048^2 without the slow host renderer
     kept = np.concatenate([clear_border(pts + np.array([dx, dy]), tile.shape, PATCH) for dx in (0, 1024) for dy in (0, 1024)])
@@ -553,12 +553,16 @@ def e2e_patches(ctx, zp, n_modes):
         q = kept.copy()
         q[:, 0] = (q[:, 0] + 7 * f) % 2048
         pts_list.append(clear_border(q, tile.shape, PATCH))
-    res = zp_host.transform_peaks_batch(frames[:2], pts_list[:2])           # warm-up: staging buffers, pool threads
+    res = zp_host.transform_peaks_batch(frames[:4], pts_list[:4])           # warm-up: every staging slot, pool threads
     ref = zo.project_patches(zo.extract_patches(frames[1], pts_list[1][:512], PATCH).astype(np.float64), zp.polynomials)
     fp32_close(res[1].data[:512], ref, "e2e frame route")
     steps = max(2, min(args.steps, 5))
     n_patches = sum(len(q) for q in pts_list)
     result = np.zeros((n_patches, n_modes))                                 # a frame loop keeps ONE result buffer (out=)
+    zp_host.transform_peaks_batch(frames, pts_list, out=result)             # full warm-up: the buffer's pages exist
+    # the oracle check above ran numpy.dot: OpenBLAS' worker threads keep spinning for ~0.1 s after a call and steal
+    # the cores of the library's own host threads (measured: 8 ms -> 18 ms per call) -- let the CHECKER go idle first
+    time.sleep(1.0)
     rates = {}
     for label, kw in (("reused_out", {"out": result}), ("fresh_out", {})):
         if world > 1:
@@ -572,9 +576,9 @@ def e2e_patches(ctx, zp, n_modes):
     out = {"value": rates["reused_out"], "unit": "patches/s",
            "h2d_bytes_per_step": n_frames * 2048 * 2048 * 4 + n_patches * 16, "d2h_bytes_per_step": n_patches * n_modes * 4,
            "steps": steps, "patches_per_step": n_patches,
-           "api": "ZPs.transform_peaks_batch(8 pinned numpy frames, peak lists, out=buffer) -> zb200_project_peaks_host -> float64 numpy",
+           "api": "ZPs.transform_peaks_batch(16 pinned numpy frames, peak lists, out=buffer) -> zb200_project_peaks_host -> float64 numpy",
            "fresh_result_array_per_call": {"value": rates["fresh_out"], "unit": "patches/s",
-                                           "what": "same call without out=: a new 120 MB float64 array per call pays its page faults"}}
+                                           "what": "same call without out=: a new 240 MB float64 array per call pays its page faults"}}
     # --- patch-stack route, pageable (what a reference user holds) and pinned
     n_e2e = min(args.batch, args.e2e_batch)
     base = zo.extract_patches(frames[0], pts_list[0][:8192], PATCH)
@@ -582,6 +586,7 @@ def e2e_patches(ctx, zp, n_modes):
     pin = torch.empty((n_e2e, PATCH, PATCH), dtype=torch.float32, pin_memory=True)
     pin.copy_(torch.from_numpy(pageable))
     zp_host.transform(pageable[:1024])
+    time.sleep(0.5)
     for label, arr in (("pageable", pageable), ("pinned", pin.numpy())):
         if world > 1:
             ctx.dist.barrier()
@@ -831,7 +836,7 @@ def bench_c5(ctx):
     import numpy as np
     torch, args, pk, world, rank = ctx.torch, ctx.args, ctx.pk, ctx.world, ctx.rank
     from motif_learn_b200.datasets import honeycomb_frame_gpu
-    from motif_learn_b200.features import ZPs, KeyPoints, clear_border, local_max
+    from motif_learn_b200.features import ZPs, clear_border, local_max, series_features
     from motif_learn_b200.parallel import gather_rows, shard_range
     zo = _oracle()
     n_frames_total = args.c5_frames
@@ -848,13 +853,10 @@ def bench_c5(ctx):
     hold = {}
 
     def compute():
-        feats, counts = [], []
-        for f in range(hi - lo):
-            pts = local_max(frames[f], PEAK_MIN_DISTANCE, PEAK_THRESHOLD)            # (P,2) host int64, brightest first
-            kept = clear_border(pts, (C5_SIZE, C5_SIZE), PATCH)
-            feats.append(zp.transform_peaks(frames[f], kept, "abs"))                 # gather kernel + |Zc| epilogue
-            counts.append(len(kept))
-        hold["feats"], hold["counts"] = feats, counts
+        # per frame: local_max -> clear_border -> gather kernel -> projection with the |Zc| epilogue; the frames are
+        # spread over `workers` host threads with one CUDA stream each so their small kernels interleave
+        feats, pts = series_features(zp, frames, PEAK_MIN_DISTANCE, PEAK_THRESHOLD, kind="abs", workers=args.c5_workers)
+        hold["feats"], hold["counts"] = feats, [len(q) for q in pts]
 
     def step():
         compute()
@@ -888,7 +890,8 @@ def bench_c5(ctx):
         assert hold["all"].shape[0] == int(n_patches)
     cfg = workload_config("c5", world)
     details = {"frames_total": n_frames_total, "frames_per_gpu": hi - lo, "patches_total": int(n_patches),
-               "peaks": f"local_max(min_distance={PEAK_MIN_DISTANCE}, threshold={PEAK_THRESHOLD}) on the GPU"}
+               "peaks": f"local_max(min_distance={PEAK_MIN_DISTANCE}, threshold={PEAK_THRESHOLD}) on the GPU",
+               "pipeline": f"features.series_features, {args.c5_workers} worker threads / streams"}
     per_frame_bytes = C5_SIZE * C5_SIZE * 4
     return {"metric": "zernike_patches_per_sec", "value": value, "unit": "patches/s", "ms_per_step": ms / steps, "steps": steps,
             "frames_per_sec": n_frames_total * steps / (ms / 1e3), "dtype": DTYPES[prec], "precision": prec, "scaling": "strong",
@@ -912,13 +915,15 @@ def main():
     ap.add_argument("--workload", default="patches", choices=WORKLOADS)
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "tf32x3", "f16", "f16x3"])
     ap.add_argument("--batch", type=int, default=262144, help="patches per GPU per step (metric shape)")
-    ap.add_argument("--e2e-batch", type=int, default=65536)
+    ap.add_argument("--e2e-batch", type=int, default=32768)
     ap.add_argument("--map-steps", type=int, default=20)
     ap.add_argument("--c3-total", type=int, default=C3_TOTAL)
     ap.add_argument("--c5-frames", type=int, default=C5_FRAMES)
+    ap.add_argument("--c5-workers", type=int, default=6, help="host threads / CUDA streams of the frame-series pipeline")
     ap.add_argument("--also", default="all", help="comma list of the other workloads to carry under 'also' (all | none | names)")
     ap.add_argument("--no-also", action="store_true", help="same as --also none")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2.5 s sustained leg of the patch workload")
     ap.add_argument("--gather", default="push", choices=["push", "nccl"],
                     help="N>1: how the timed step gathers the features (push = fused P2P stores / copy engines; nccl = all_gather after the kernel)")
     args = ap.parse_args()

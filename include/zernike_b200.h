@@ -226,7 +226,8 @@ int zb200_render_atoms_f32(const double* d_pts_xy, const double* d_amps, double 
 /* d_xy_out int32 [capacity,2] receives the kept peaks as (x, y), brightest first (equal intensities in
  * raster order).  has_threshold=0 means threshold=None (= image.min()).  *h_count = number of kept peaks,
  * *h_candidates (may be NULL) = local maxima before suppression.  capacity=0 with d_xy_out=NULL only counts;
- * a too small capacity fails with ZB200_EINVAL after setting *h_count.  Blocks until the result is ready. */
+ * a too small capacity fails with ZB200_EINVAL after setting *h_count.  Blocks until *h_count is known; the coordinates
+ * in d_xy_out are ordered on `stream` like any kernel output. */
 int zb200_local_max_f32(const float* d_img, int H, int W, double min_distance, int has_threshold, double threshold,
                         int32_t* d_xy_out, int64_t capacity, int64_t* h_count, int64_t* h_candidates, void* stream);
 /* ---- "next" row f4: PCA of the feature matrix (replaces pca, mtflearn/features/_dimension_reduction.py:3-6 =

@@ -99,9 +99,9 @@ bool is_pinned(const void* h) {
 
 // ---- kSlots-deep pipeline: enqueue(c, slot) on the calling thread, drain(c, slot) on a second thread once the
 // event of the slot has fired.  Slot c % kSlots is reused by item c only after item c - kSlots has been drained.
-// Three slots: the chain upload -> gather -> projection -> download -> widening of one frame is ~1 ms long while
-// its longest stage (the upload) is 0.3 ms; two slots ran at 0.56 ms per 2048^2 frame, three reach the bus rate.
-constexpr int kSlots = 3;
+// Four slots: the chain upload -> gather -> projection -> download -> widening of one 2048^2 frame is ~1.1 ms long
+// while its longest stage (the upload) is 0.32 ms; two slots ran at 0.56 ms per frame, three at 0.50 ms.
+constexpr int kSlots = 4;
 struct PipeSync {
     std::mutex m;
     std::condition_variable cv;

@@ -165,8 +165,8 @@ extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_
     {
         uint32_t* mm = reinterpret_cast<uint32_t*>(pool);                       // [0] min, [1] max
         unsigned long long* count = reinterpret_cast<unsigned long long*>(pool + 16);
-        unsigned int* undecided = reinterpret_cast<unsigned int*>(pool + 32);
-        unsigned long long* n_sel = reinterpret_cast<unsigned long long*>(pool + 48);
+        unsigned int* undecided = reinterpret_cast<unsigned int*>(pool + 32);     // [4]: one per sweep of a batch
+        unsigned long long* n_sel = reinterpret_cast<unsigned long long*>(pool + 64);
         unsigned long long* keys0 = reinterpret_cast<unsigned long long*>(pool + off_keys0);
         unsigned long long* keys1 = reinterpret_cast<unsigned long long*>(pool + off_keys1);
         int* rank_map = reinterpret_cast<int*>(pool + off_rank);
@@ -205,14 +205,26 @@ extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_
         {
             const int R = (int)floor(min_distance);
             const double r2 = min_distance * min_distance;
-            for (int sweep = 0; sweep < 4096; ++sweep) {
-                unsigned int left = 0;
-                ZB_PEAKS_CUDA(cudaMemsetAsync(undecided, 0, sizeof(unsigned int), s));
-                peaks_nms_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(keys1, n, rank_map, H, W, R, r2, state, undecided);
-                g_launches.fetch_add(1, std::memory_order_relaxed);
-                ZB_PEAKS_CUDA(cudaMemcpyAsync(&left, undecided, sizeof(left), cudaMemcpyDeviceToHost, s));
+            // Sweeps run in batches of 4 between host checks (a lattice frame settles in 2-4 sweeps; a sweep over
+            // an already settled list is a few microseconds, a host round trip costs more).  counters[j] = peaks
+            // still undecided after sweep j of the batch.
+            unsigned int left = 1;
+            constexpr int kBatch = 4, kMaxSweeps = 8192;
+            for (int sweep = 0; sweep < kMaxSweeps && left != 0; sweep += kBatch) {
+                ZB_PEAKS_CUDA(cudaMemsetAsync(undecided, 0, sizeof(unsigned int) * kBatch, s));
+                for (int j = 0; j < kBatch; ++j) {
+                    peaks_nms_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(keys1, n, rank_map, H, W, R, r2, state, undecided + j);
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                }
+                ZB_PEAKS_CUDA(cudaMemcpyAsync(&left, undecided + (kBatch - 1), sizeof(left), cudaMemcpyDeviceToHost, s));
                 ZB_PEAKS_CUDA(cudaStreamSynchronize(s));
-                if (left == 0) break;
+            }
+            if (left != 0) {
+                // a dependency chain longer than the sweep cap (e.g. a huge plateau of equal maxima): report it
+                // rather than silently dropping the undecided peaks
+                set_error("local_max: suppression did not settle within %d sweeps (%u peaks undecided)", kMaxSweeps, left);
+                rc = ZB200_EUNSUP;
+                goto done;
             }
         }
         peaks_flags_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(state, n, flags);
@@ -239,8 +251,7 @@ extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_
         }
         if (kept) {
             peaks_emit_kernel<<<(unsigned)ceil_div((long long)kept, 256), 256, 0, s>>>(keys0, (long long)kept, W, d_xy_out);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            ZB_PEAKS_CUDA(cudaStreamSynchronize(s));
+            g_launches.fetch_add(1, std::memory_order_relaxed);   // stream-ordered: no host wait for the coordinates
         }
     }
 done:

@@ -7,6 +7,7 @@ from ._indexing import (construct_complex_matrix, construct_real_matrix, constru
 from ._keypoint import KeyPoints, clear_border
 from ._local_max import local_max
 from ._dimension_reduction import pca
+from ._series import series_features
 
 __all__ = ["ZPs", "zmoments", "construct_rot_maps_matrix", "construct_complex_matrix", "construct_real_matrix",
-           "KeyPoints", "clear_border", "local_max", "pca", "nm2j", "nm2j_complex"]
+           "KeyPoints", "clear_border", "local_max", "pca", "series_features", "nm2j", "nm2j_complex"]

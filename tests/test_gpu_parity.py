@@ -841,3 +841,29 @@ def test_feature_gather_on_nccl(torch, tmp_path):
     for r in range(2):
         got = torch.load(str(tmp_path / f"r{r}.pt"))
         assert got["ok"] and got["n"] == 1001
+
+
+def test_series_features_threads_and_streams(api, torch):
+    """BASELINE config 5 pipeline: frames spread over worker threads / streams give exactly the per-frame results."""
+    from motif_learn_b200.datasets import honeycomb_image
+    frames = []
+    for seed in range(7):
+        img, _ = honeycomb_image((384, 448), bond=12.0, seed=seed, angle=7.0 * seed, jitter=0.3, noise=0.01)
+        frames.append(img)
+    dev = torch.from_numpy(np.stack(frames)).cuda()
+    z = api.ZPs(12, 48)
+    n, m, v = zo.zernike_basis(12, 48)
+    feats, pts = api.series_features(z, dev, 5.0, 0.3, kind="abs", workers=3)
+    torch.cuda.synchronize()
+    assert len(feats) == len(pts) == 7
+    for f in range(7):
+        want_pts = zo.clear_border(zo.local_max(frames[f], 5.0, 0.3), frames[f].shape, 48)
+        np.testing.assert_array_equal(pts[f], want_pts)
+        ref = np.abs(zo.to_complex(zo.project_patches(zo.extract_patches(frames[f], want_pts, 48).astype(np.float64), v), n, m)[0])
+        assert feats[f].is_cuda and np.abs(feats[f].cpu().numpy() - ref).max() <= 3e-6 * ref.max()
+    one, pts1 = api.series_features(z, frames, 5.0, 0.3, kind="real", workers=1)      # numpy frames, single worker
+    torch.cuda.synchronize()
+    for f in range(7):
+        np.testing.assert_array_equal(pts1[f], pts[f])
+        assert one[f].data.shape == (len(pts[f]), 91)
+    assert api.series_features(z, [], 5.0) == ([], [])
