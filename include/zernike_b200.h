@@ -221,6 +221,19 @@ int zb200_complex_abs_phase(int dtype, const void* d_in, int64_t n, void* d_abs,
  * from a zero frame, 1 adds to the existing one (second sub-lattice). */
 int zb200_render_atoms_f32(const double* d_pts_xy, const double* d_amps, double amp_scalar, int64_t n_atoms,
                            double sigma, double r_factor, int H, int W, float* d_img, int accumulate, void* stream);
+/* Honeycomb lattice sites on the device (replaces HoneyCombLattice._generate_coordinates,
+ * mtflearn/datasets/_honeycomb_lattice.py:103-140): sites (n1, n2) in [-n_index, n_index]^2, n1-major, sub-lattices
+ * A and B -> d_coords_a / d_coords_b, double [(2 n_index + 1)^2, 2] as (x, y).  h_* are host 2-vectors; the optional
+ * d_jitter_* (same shape as the outputs, host-drawn with the reference's RNG stream) are added last. */
+int zb200_lattice_coords_f64(int n_index, const double* h_a1, const double* h_a2, const double* h_dA, const double* h_dB,
+                             const double* h_offset, double angle_rad, double centre, const double* d_jitter_a,
+                             const double* d_jitter_b, double* d_coords_a, double* d_coords_b, void* stream);
+/* Delta placement + Gaussian blur of one species (replaces TMDImageSimulator.place_atoms_delta + the fftconvolve
+ * with gaussian_kernel in simulate, mtflearn/datasets/_tmd_simulator.py:151-186): atoms rounded to pixels (half to
+ * even), dropped outside the frame, each stamps scale * amplitude * exp(-(dx^2+dy^2)/(2 sigma^2)) on the
+ * kernel_size^2 pixels around it (kernel_size odd).  accumulate=1: img = float32(img + blurred). */
+int zb200_render_stamps_f32(const double* d_pts_xy, const float* d_scales, int64_t n_atoms, double amplitude, double sigma,
+                            int kernel_size, int H, int W, float* d_img, int accumulate, void* stream);
 /* ---- "next" row f2: peak detection (replaces local_max, mtflearn/features/_local_max_v2.py:6-66 =
  * skimage peak_local_max(min_distance=1, threshold_abs) + intensity-ordered radius suppression) ---------- */
 /* d_xy_out int32 [capacity,2] receives the kept peaks as (x, y), brightest first (equal intensities in
@@ -238,6 +251,32 @@ int zb200_gram_f32(const float* d_x, int64_t n, int m, double* d_gram, double* d
 /* d_out double [n, n_comp]: (x_i - mean) . components[c]  with host tables mean[m], components[n_comp, m]. */
 int zb200_pca_scores_f32(const float* d_x, int64_t n, int m, const double* h_mean, const double* h_components,
                          int n_comp, double* d_out, void* stream);
+/* ---- "next" row f4: cluster labels of the feature matrix (replaces the passes over X inside kmeans_lbs / gmm_lbs,
+ * mtflearn/clustering/_clustering_functions.py:8-34 = scikit-learn KMeans / GaussianMixture('full')).  All arithmetic
+ * in float64 on the float32 row-major matrix d_x (n, d), centred by h_mean on the fly; deterministic reductions. ---- */
+/* k-means++ seeding step: d_out[j][i] = min(d_closest[i], |x_i - mean - cand_j|^2) (no min when d_closest is NULL),
+ * h_pot[j] = sum_i d_out[j][i]; h_cand (t, d) in centred coordinates.  Blocks. */
+int zb200_kmeans_mindist_f32(const float* d_x, int64_t n, int d, const double* h_mean, const double* h_cand, int t,
+                             const double* d_closest, double* d_out, double* h_pot, void* stream);
+/* One Lloyd iteration: labels = argmin_c |x - mean - centre_c|^2 (first minimum), *h_changed = labels that changed;
+ * update=1 also returns the per-cluster sums of the centred samples (k, d) and the counts (k).  Blocks. */
+int zb200_kmeans_step_f32(const float* d_x, int64_t n, int d, const double* h_mean, const double* h_centres, int k,
+                          int32_t* d_labels, int update, double* h_sums, double* h_counts, int64_t* h_changed, void* stream);
+/* E-step of a full-covariance Gaussian mixture: h_prec_chol (k, d, d) upper-triangular factors (precision = P P^T),
+ * h_means (k, d) absolute.  d_log_resp (n, k) and / or d_labels (argmax) may be NULL; *h_mean_log_norm (may be NULL) =
+ * mean over the samples of the log-sum-exp (the lower bound scikit-learn monitors).  Blocks when it is requested. */
+int zb200_gmm_estep_f32(const float* d_x, int64_t n, int d, const double* h_log_weights, const double* h_log_dets,
+                        const double* h_means, const double* h_prec_chol, int k, double* d_log_resp, int32_t* d_labels,
+                        double* h_mean_log_norm, void* stream);
+/* M-step accumulators with r = exp(d_log_resp) (or the one-hot of d_labels when d_log_resp is NULL), x centred by
+ * h_mean: h_nk (k), h_sx (k, d) = sum r x, h_sxx (k, d, d) = sum r x x^T.  d <= 90.  Blocks. */
+int zb200_gmm_mstep_f32(const float* d_x, int64_t n, int d, const double* h_mean, const double* d_log_resp,
+                        const int32_t* d_labels, int k, double* h_nk, double* h_sx, double* h_sxx, void* stream);
+/* Overlap-add of the patch-SVD denoiser (replaces reconstruct_patches, mtflearn/denoise/_denoise_svd.py:51-70):
+ * d_patches double [ny*nx, kh, kw] laid back at start rows d_ys[ny] x start columns d_xs[nx] (row-major grid), summed
+ * in that order and divided by the overlap count -> d_img double [H, W]. */
+int zb200_overlap_add_f64(const double* d_patches, const int32_t* d_ys, int ny, const int32_t* d_xs, int nx, int kh, int kw,
+                          int H, int W, double* d_img, void* stream);
 /* Result download: n floats in HBM -> float64 host array (the dtype the reference returns), chunked D2H through
  * pinned staging overlapped with multi-threaded widening.  Ordered after the work queued on `stream`; blocks. */
 int zb200_download_as_f64(const float* d_src, int64_t n, double* h_dst, void* stream);

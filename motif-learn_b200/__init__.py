@@ -8,6 +8,8 @@ written CUDA kernels behind a C ABI (include/zernike_b200.h); no CPU fallback.
 __version__ = "0.1.0"
 
 from . import features            # noqa: F401
+from . import clustering          # noqa: F401
+from . import denoise             # noqa: F401
 from .features import ZPs, zmoments, KeyPoints  # noqa: F401
 
-__all__ = ["features", "ZPs", "zmoments", "KeyPoints", "__version__"]
+__all__ = ["features", "clustering", "denoise", "ZPs", "zmoments", "KeyPoints", "__version__"]

@@ -72,10 +72,17 @@ SIGNATURES = {
     "zb200_mirror_scores": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, _vp, _int, _vp, _vp]),
     "zb200_complex_abs_phase": (_int, [_int, _vp, _i64, _vp, _vp, _vp]),
     "zb200_render_atoms_f32": (_int, [_vp, _vp, C.c_double, _i64, C.c_double, C.c_double, _int, _int, _vp, _int, _vp]),
+    "zb200_lattice_coords_f64": (_int, [_int, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "zb200_render_stamps_f32": (_int, [_vp, _vp, _i64, C.c_double, C.c_double, _int, _int, _int, _vp, _int, _vp]),
     "zb200_local_max_f32": (_int, [_vp, _int, _int, C.c_double, _int, C.c_double, _vp, _i64, C.POINTER(_i64),
                                    C.POINTER(_i64), _vp]),
     "zb200_gram_f32": (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
     "zb200_pca_scores_f32": (_int, [_vp, _i64, _int, _vp, _vp, _int, _vp, _vp]),
+    "zb200_kmeans_mindist_f32": (_int, [_vp, _i64, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "zb200_kmeans_step_f32": (_int, [_vp, _i64, _int, _vp, _vp, _int, _vp, _int, _vp, _vp, C.POINTER(_i64), _vp]),
+    "zb200_gmm_estep_f32": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, C.POINTER(C.c_double), _vp]),
+    "zb200_gmm_mstep_f32": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "zb200_overlap_add_f64": (_int, [_vp, _vp, _int, _vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "zb200_download_as_f64": (_int, [_vp, _i64, _vp, _vp]),
     "zb200_cast": (_int, [_int, _vp, _int, _vp, _i64, _vp]),
 }

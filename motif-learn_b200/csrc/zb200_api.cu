@@ -3,6 +3,7 @@
 #include "zb200_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <new>
@@ -19,6 +20,44 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+static int knob(const char* name, int lo, int hi, int fallback) {
+    const char* e = getenv(name);
+    if (!e || !*e) return fallback;
+    char* end = nullptr;
+    const long v = strtol(e, &end, 10);
+    if (end == e || *end != '\0' || v < lo || v > hi) {
+        fprintf(stderr, "[zb200] ignoring %s=%s (allowed range %d..%d)\n", name, e, lo, hi);
+        return fallback;
+    }
+    return (int)v;
+}
+
+const Knobs& knobs() {
+    static const Knobs k = [] {
+        Knobs v;
+        const char* on = getenv("ZB200_EXPERIMENT");
+        if (!on || strcmp(on, "1") != 0) return v;
+        v.tc_kskip = knob("ZB200_TC_KSKIP", 0, 1, -1);
+        v.tc_chunk = knob("ZB200_TC_CHUNK", 1, 64, 0);
+        v.tc_cluster = knob("ZB200_TC_CLUSTER", 1, 4, 0);
+        if (v.tc_cluster == 3) v.tc_cluster = 0;
+        v.tc_pair = knob("ZB200_TC_PAIR", 0, 1, -1);
+        v.tc_bstages = knob("ZB200_TC_BSTAGES", 1, 4, 0);
+        v.tc_stages = knob("ZB200_TC_STAGES", 1, 8, 0);
+        v.tc_accbufs = knob("ZB200_TC_ACCBUFS", 1, 2, 0);
+        v.map_gskip = knob("ZB200_MAP_GSKIP", 0, 1, -1);
+        v.map_bstages = knob("ZB200_MAP_BSTAGES", 2, 8, 0);
+        v.map_slots = knob("ZB200_MAP_SLOTS", 2, 16, 0);
+        v.gather_4b = knob("ZB200_GATHER_4B", 0, 1, 0);
+#if ZB200_DEBUG_HOOKS
+        v.tc_debug = knob("ZB200_TC_DEBUG", 0, 255, 0);
+        v.map_debug = knob("ZB200_MAP_DEBUG", 0, 255, 0);
+#endif
+        return v;
+    }();
+    return k;
 }
 
 static int check_device(int* sms, int* major, int* minor) {

@@ -43,6 +43,29 @@ extern std::atomic<int64_t> g_launches;
         ZB_CUDA(cudaGetLastError());                                                   \
     } while (0)
 
+// Experiment knobs (A/B measurements of DESIGN.md).  They exist ONLY when the process is started with
+// ZB200_EXPERIMENT=1; then each ZB200_* variable below is read ONCE (first use), range-checked, and out-of-range
+// values are ignored.  Without the switch the library never looks at the environment on a launch path.
+struct Knobs {
+    int tc_kskip = -1;     // ZB200_TC_KSKIP   0|1   issue every K step / skip the all-zero ones
+    int tc_chunk = 0;      // ZB200_TC_CHUNK   1..64 k-blocks per accumulation chunk
+    int tc_cluster = 0;    // ZB200_TC_CLUSTER 1|2|4 CTAs sharing the basis stream
+    int tc_pair = -1;      // ZB200_TC_PAIR    0|1   cta_group::2 pairs
+    int tc_bstages = 0;    // ZB200_TC_BSTAGES 1..4
+    int tc_stages = 0;     // ZB200_TC_STAGES  1..8
+    int tc_accbufs = 0;    // ZB200_TC_ACCBUFS 1|2
+    int tc_debug = 0;      // ZB200_TC_DEBUG   bit mask, needs a -DZB200_DEBUG_HOOKS=1 build (results are wrong when set)
+    int map_gskip = -1;    // ZB200_MAP_GSKIP  0|1
+    int map_bstages = 0;   // ZB200_MAP_BSTAGES 2..8
+    int map_slots = 0;     // ZB200_MAP_SLOTS  2..16 (checked against shared memory by the launcher)
+    int map_debug = 0;     // ZB200_MAP_DEBUG  bit mask, debug-hook builds only
+    int gather_4b = 0;     // ZB200_GATHER_4B  1: 4-byte gathers in the fused gather->projection path
+};
+const Knobs& knobs();
+#ifndef ZB200_DEBUG_HOOKS
+#define ZB200_DEBUG_HOOKS 0      // ablation bits / blocked-cycle counters inside the hot kernels: compiled out of releases
+#endif
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

@@ -85,7 +85,7 @@ extern "C" int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_im
     g_launches.fetch_add(1, std::memory_order_relaxed);
     GatherSource src{d_img, H, W, xy0};
     float* planes = nullptr;
-    if (plan->size % 4 == 0 && !getenv("ZB200_GATHER_4B")) {
+    if (plan->size % 4 == 0 && !knobs().gather_4b) {
         // windows start at arbitrary columns; four copies shifted by 0..3 pixels make every window row 16-byte aligned
         const int L = plan->size, Wp = round_up(W + 2 * L, 4);
         if (cudaMallocAsync(&planes, sizeof(float) * 4 * (size_t)H * Wp, s) == cudaSuccess) {
@@ -119,6 +119,41 @@ extern "C" int zb200_gather_patches_f32(const float* d_img, int H, int W, const 
     const long long want = (long long)sms * 8;          // 8 resident CTAs of 256 threads per SM
     const unsigned grid = (unsigned)(n_pts < want ? n_pts : want);
     gather_kernel<256><<<grid, 256, 0, as_stream(stream)>>>(d_img, H, W, d_pts_xy, (long long)n_pts, k, d_out);
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
+// ---- "next" row f4: overlap-add of the patch-SVD denoiser -----------------------------------------------------------
+// Replaces reconstruct_patches (mtflearn/denoise/_denoise_svd.py:51-70): patches laid back at their start indices
+// (ys x xs grid, row-major), summed, divided by the overlap count.  One thread per pixel walks the patches that
+// cover it in the reference's accumulation order (increasing start row, then start column): float64, deterministic.
+namespace zb200 {
+__global__ void overlap_add_kernel(const double* __restrict__ patches, const int* __restrict__ ys, int ny,
+                                   const int* __restrict__ xs, int nx, int kh, int kw, int H, int W, double* __restrict__ img) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    double acc = 0.0, cnt = 0.0;
+    for (int a = 0; a < ny; ++a) {
+        const int dy = y - ys[a];
+        if (dy < 0 || dy >= kh) continue;
+        for (int b = 0; b < nx; ++b) {
+            const int dx = x - xs[b];
+            if (dx < 0 || dx >= kw) continue;
+            acc += patches[((size_t)(a * nx + b) * kh + dy) * kw + dx];
+            cnt += 1.0;
+        }
+    }
+    img[(size_t)y * W + x] = acc / cnt;                       // the start grids cover every pixel: cnt >= 1
+}
+}  // namespace zb200
+
+extern "C" int zb200_overlap_add_f64(const double* d_patches, const int32_t* d_ys, int ny, const int32_t* d_xs, int nx,
+                                     int kh, int kw, int H, int W, double* d_img, void* stream) {
+    using namespace zb200;
+    ZB_CHECK_ARG(d_patches && d_ys && d_xs && d_img, "overlap_add: null pointer");
+    ZB_CHECK_ARG(ny >= 1 && nx >= 1 && kh >= 1 && kw >= 1 && H >= kh && W >= kw, "overlap_add: bad shape");
+    dim3 grid((unsigned)ceil_div(W, 128), (unsigned)H);
+    overlap_add_kernel<<<grid, 128, 0, as_stream(stream)>>>(d_patches, d_ys, ny, d_xs, nx, kh, kw, H, W, d_img);
     ZB_LAUNCHED();
     return ZB200_OK;
 }

@@ -57,6 +57,8 @@ private:
         unsigned hw = std::thread::hardware_concurrency();
         int n = hw >= 8 ? (int)hw / 2 : (hw >= 3 ? (int)hw - 2 : 0);
         if (n > 16) n = 16;
+        // the only environment variable a release build honours besides ZB200_EXPERIMENT: the pool width (1..64),
+        // read once when the pool is created
         if (const char* e = getenv("ZB200_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n = v - 1; }
         for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
         for (auto& w : workers_) w.detach();

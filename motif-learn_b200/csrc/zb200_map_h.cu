@@ -382,7 +382,7 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
                     const int c0 = span * kSpan - p.half + p.pad;            // = 4 q0 (4-byte words of a plane row)
                     for (int st = 0; st <= p.n_rows; ++st) {
                         mbar_wait(&img_empty[s], ph ^ 1);
-                        if (p.dbg & 1) {
+                        if (ZB200_DEBUG_HOOKS && (p.dbg & 1)) {
                             mbar_arrive(&img_full[s]);
                             if (++s == p.img_slots) { s = 0; ph ^= 1; }
                             continue;
@@ -412,7 +412,7 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
                 for (long long t = 0; t < my_tiles; ++t) {
                     for (int i = 0; i < p.n_rows; ++i) {
                         mbar_wait(&b_empty[s], ph ^ 1);
-                        if (p.dbg & 16) {
+                        if (ZB200_DEBUG_HOOKS && (p.dbg & 16)) {
                             mbar_arrive(&b_full[s]);
                             if (++s == p.b_slots) { s = 0; ph ^= 1; }
                             continue;
@@ -489,7 +489,7 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + g) * p.n_pad);
 #pragma unroll
                 for (int cc = 0; cc < kMaxColChunks; ++cc) {
-                    if (cc < n_cc && !(p.dbg & 8)) {
+                    if (cc < n_cc && !(ZB200_DEBUG_HOOKS && (p.dbg & 8))) {
                         uint32_t v[16];
                         tmem_ld16(taddr + cc * 16, v);
                         tmem_ld_wait();
@@ -504,7 +504,7 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
             const int x = span * kSpan + 4 * (q * 32 + lane) + r;
             const int yl = y0 + (g == 0 ? 1 : 0) - p.row0;                 // local output row of this warpgroup's half
             const bool live = tile < p.n_tiles && x < p.W && yl >= 0 && yl < p.rows;
-            if (p.dbg & 4) {
+            if (ZB200_DEBUG_HOOKS && (p.dbg & 4)) {
                 if (live) p.out_scores[(size_t)yl * p.W + x] = sum[0][0] + sum[5][15];
             } else if (live) {
                 if (kScores) {
@@ -731,8 +731,7 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
     prm.kb_per_row = (mh.n_groups + 3) / 4;
     prm.a_first = mh.a_first; prm.n_rows = mh.a_end - mh.a_first;
     {
-        const char* e = getenv("ZB200_MAP_GSKIP");
-        const bool skip = !(e && atoi(e) == 0);
+        const bool skip = knobs().map_gskip != 0;
         for (int st = 0; st <= prm.n_rows; ++st) {
             const unsigned up = st < prm.n_rows ? mh.act[mh.a_first + st] : 0u;
             const unsigned lo = st >= 1 ? mh.act[mh.a_first + st - 1] : 0u;
@@ -755,7 +754,7 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
         for (int f = 0; f < n_folds; ++f)
             for (int c = 0; c < p->n_modes; ++c) prm.wts[f][c] = h_sel[c] ? h_w[(size_t)f * p->n_modes + c] : 0.f;
     }
-    if (const char* e = getenv("ZB200_MAP_DEBUG")) prm.dbg = atoi(e);
+    prm.dbg = knobs().map_debug;
 
     // operand planes of the frame: (x1 | x2) x 4 pixel phases, overlapped 16-byte units
     const int n_parts = x3 ? 2 : 1;
@@ -800,8 +799,7 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
     }
 
     int cluster = 2;
-    if (const char* e = getenv("ZB200_TC_CLUSTER")) cluster = atoi(e);
-    if (cluster != 1 && cluster != 2) cluster = 2;
+    if (knobs().tc_cluster == 1) cluster = 1;
     while (cluster > 1 && (cluster > mh.max_cluster || prm.n_tiles < 2 * cluster)) cluster >>= 1;
     prm.cluster = cluster;
     const int lg = cluster == 2 ? 1 : 0;
@@ -810,8 +808,8 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
     const int slot_bytes = n_parts * prm.copy_q * 16;
     prm.img_slots = 8;
     prm.b_slots = prm.kb_per_row == 1 ? 4 : 2;
-    if (const char* e = getenv("ZB200_MAP_BSTAGES")) prm.b_slots = atoi(e) > 1 ? atoi(e) : prm.b_slots;
-    if (const char* e = getenv("ZB200_MAP_SLOTS")) prm.img_slots = atoi(e) > 0 ? atoi(e) : 8;
+    if (knobs().map_bstages) prm.b_slots = knobs().map_bstages;
+    if (knobs().map_slots) prm.img_slots = knobs().map_slots;
     auto smem_need = [&]() {
         return 1024 + (size_t)n_rings * (prm.b_slots + 1) * prm.n_pad * 128 + (((size_t)prm.img_slots * slot_bytes + 15) & ~(size_t)15) +
                8 * (2 * prm.img_slots + 2 * prm.b_slots + 4) + 16;

@@ -192,7 +192,7 @@ map_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant
                     const int xs = span * kSpan - p.half + 4;                 // plane column of copy element 0 (multiple of 4)
                     for (int a = 0; a < k; ++a) {
                         mbar_wait(&img_empty[s], ph ^ 1);
-                        if (p.dbg & 1) {
+                        if (ZB200_DEBUG_HOOKS && (p.dbg & 1)) {
                             mbar_arrive(&img_full[s]);
                             if (++s == p.img_slots) { s = 0; ph ^= 1; }
                             continue;
@@ -276,7 +276,7 @@ map_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant
                                 const uint32_t ao = 2u * (uint32_t)b8;                      // 8 taps = 32 B
                                 const uint32_t bo = 2u * k4;
                                 const uint32_t acc = (a > a_begin || b8 > 0) ? 1u : 0u;
-                                if (!(p.dbg & 2)) {
+                                if (!(ZB200_DEBUG_HOOKS && (p.dbg & 2))) {
                                 umma_tf32(d0, desc_toeplitz(a00 + ao), desc_from_lo(bhl + bo), idesc, acc);
                                 if (x3) {
                                     umma_tf32(d0, desc_toeplitz(a00 + copy_step + ao), desc_from_lo(bhl + bo), idesc, 1u);
@@ -449,7 +449,7 @@ int map_tc(const zb200_plan* p, const float* d_img, int H, int W, int row0, int 
     prm.chunk_rows = 32 / (prm.k / 8) > 0 ? 32 / (prm.k / 8) : 1;     // drain after ~32 accumulation steps
     prm.out_moments = d_moments; prm.out_scores = d_scores; prm.w = d_w; prm.sel = d_sel;
     prm.n_folds = n_folds; prm.norm_kind = norm_kind;
-    if (const char* e = getenv("ZB200_MAP_DEBUG")) prm.dbg = atoi(e);
+    prm.dbg = knobs().map_debug;
 
     // operand planes of the frame: (hi | lo) x 4 pixel-phase shifts, pitch padded to 16 B
     const int Wp = round_up(W + 4, 4);
@@ -481,8 +481,7 @@ int map_tc(const zb200_plan* p, const float* d_img, int H, int W, int row0, int 
     }
 
     int cluster = 2;
-    if (const char* e = getenv("ZB200_TC_CLUSTER")) cluster = atoi(e);
-    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
+    if (knobs().tc_cluster) cluster = knobs().tc_cluster;
     while (cluster > 1 && (cluster > op.max_cluster || prm.n_tiles < 2 * cluster)) cluster >>= 1;
     prm.cluster = cluster;
     const int lg = cluster == 4 ? 2 : (cluster == 2 ? 1 : 0);

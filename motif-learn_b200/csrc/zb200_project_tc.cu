@@ -39,8 +39,10 @@ namespace zb200 {
 
 namespace tc {
 
-// experiment support: cycles spent blocked per wait site, summed over CTAs (ZB200_TC_DEBUG & 16)
+// experiment support (debug-hook builds only): cycles spent blocked per wait site, summed over CTAs (ZB200_TC_DEBUG & 16)
+#if ZB200_DEBUG_HOOKS
 __device__ unsigned long long g_wait_cycles[16];
+#endif
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
     if (!on) { mbar_wait(bar, parity); return; }
     const long long t0 = clock64();
@@ -110,6 +112,32 @@ struct ScoreAcc {
     }
 };
 
+// |z| and angle(z) for the fused epilogues, written for register count: the libm versions carry slow paths
+// (denormal fix-ups behind a call) that made ptxas spill up to 228 bytes around them while 128 running sums are
+// live.  sqrt.approx.ftz is within 1 ulp; the arctangent is the classic two-step range reduction
+// (tan(pi/8), tan(3pi/8)) with a degree-4 polynomial in z = t^2: max error 1.2e-7 rad over the plane.
+__device__ __forceinline__ float fast_abs2(float re, float im) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(re, re, im * im)));
+    return r;
+}
+__device__ __forceinline__ float compact_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = mx > 0.f ? __fdividef(mn, mx) : 0.f;           // in [0, 1]
+    float base = 0.f;
+    if (t > 0.4142135623730950f) {                            // tan(pi/8)
+        t = __fdividef(t - 1.f, t + 1.f);
+        base = 0.7853981633974483f;
+    }
+    const float z = t * t;
+    float r = fmaf(fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f) * z, t, t);
+    r += base;
+    if (ay > ax) r = 1.5707963267948966f - r;
+    if (x < 0.f) r = 3.141592653589793f - r;
+    return copysignf(r, y);
+}
+
 template <int kOut>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, long long row, int c0, const uint32_t (&v)[16],
                                                ScoreAcc& sc) {
@@ -124,8 +152,8 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, long long row, i
         for (int i = 0; i < 8; ++i) {
             if (m0 + i < p.row_len) {
                 const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
-                p.out[row * (long long)p.row_len + m0 + i] = sqrtf(re * re + im * im);
-                if constexpr (kOut == kOutAbsPhase) p.out2[row * (long long)p.row_len + m0 + i] = atan2f(im, re);
+                p.out[row * (long long)p.row_len + m0 + i] = fast_abs2(re, im);
+                if constexpr (kOut == kOutAbsPhase) p.out2[row * (long long)p.row_len + m0 + i] = compact_atan2(im, re);
             }
         }
     } else {   // fused n-fold scores over real-order columns
@@ -377,7 +405,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 //   warpgroup 3  splitter: Xlo = x - trunc_tf32(x) for its 128 rows, tcgen05.st into TMEM
 // ================================================================================================
 #ifndef ZB200_TC3_PROF
-#define ZB200_TC3_PROF 0
+#define ZB200_TC3_PROF ZB200_DEBUG_HOOKS
 #endif
 constexpr int kRegsCtl = 48, kRegsEpi = 176, kRegsSplit = 112;     // (48 + 2*176 + 112) * 128 = 64 Ki
 constexpr int kMaxColChunks = 8;     // 8 x 16 = 128 running sums per epilogue thread
@@ -869,6 +897,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
     }
 
+#if ZB200_DEBUG_HOOKS
     if (prof && lane == 0 && (warp == kWarpTma || warp == kWarpMma || warp == 4 || warp == 0)) {
         const int base = warp == kWarpTma ? 0 : (warp == kWarpMma ? 1 : (warp == 4 ? 5 : 8));
         atomicAdd(&g_wait_cycles[base], w0);        // 0 producer.empty | 1 mma.acc_empty | 5 epi.acc_full | 8 split.full
@@ -876,6 +905,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         atomicAdd(&g_wait_cycles[base + 2], w2);    // 3 mma.issue   | 10 split.st_wait
         if (warp == kWarpMma) atomicAdd(&g_wait_cycles[4], w3);   // 4 mma.commit
     }
+#endif
     tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();        // no CTA leaves while a peer may still write into it
@@ -988,9 +1018,8 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.n_pad = op.rows_pad;
     prm.n_cols = op.rows;
     prm.kmask = p->d_kmask;
-    if (const char* e = getenv("ZB200_TC_KSKIP")) {
-        if (atoi(e) == 0) prm.kmask = p->d_kmask + p->k_pad / 32;      // every K step issued
-    }
+    const Knobs& kn = knobs();
+    if (kn.tc_kskip == 0) prm.kmask = p->d_kmask + p->k_pad / 32;      // experiment: every K step issued
     prm.kb0 = p->kb_first;                                  // leading / trailing k-blocks with an all-zero basis
     prm.k_blocks = p->kb_last - p->kb_first;                //   (window rows outside the unit disk) are never loaded
     prm.out = static_cast<float*>(d_out);
@@ -1004,7 +1033,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                          : (out_kind == ZB200_OUT_REAL ? p->n_modes
                                                        : (out_kind == ZB200_OUT_COMPLEX ? 2 * p->n_complex : p->n_complex));
     prm.chunk_kb = 8;
-    if (const char* e = getenv("ZB200_TC_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) prm.chunk_kb = v; }
+    if (kn.tc_chunk) prm.chunk_kb = kn.tc_chunk;
     if (gsrc) {
         prm.gather = 1;
         prm.g_img = gsrc->img;
@@ -1024,7 +1053,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
         prm.n_peers = peers->n;
         for (int g = 0; g < peers->n; ++g) prm.peer_out[g] = peers->out[g];
     }
-    if (const char* e = getenv("ZB200_TC_DEBUG")) prm.dbg = atoi(e);
+    prm.dbg = kn.tc_debug;                                  // 0 unless a debug-hook build runs with ZB200_EXPERIMENT=1
     if (prm.dbg & 4) prm.chunk_kb = prm.k_blocks;
 
     // tile shape: two 128-patch accumulators per tile when TMEM/smem allow and there is enough work
@@ -1054,24 +1083,23 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.n_tiles = (int)ceil_div(n, (int64_t)sub * kTileRows);
     // cluster of C CTAs shares each B k-block through TMA multicast (L2 -> SM traffic of B / C)
     int cluster = 2;
-    if (const char* e = getenv("ZB200_TC_CLUSTER")) cluster = atoi(e);
-    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
+    if (kn.tc_cluster) cluster = kn.tc_cluster;
     while (cluster > 1 && (cluster > op.max_cluster || prm.n_tiles < 2 * cluster)) cluster >>= 1;
     prm.cluster = cluster;
     const int lg = cluster == 4 ? 2 : (cluster == 2 ? 1 : 0);
     // CTA pairs (cta_group::2) for the fp32-grade kernel: needs the 2-CTA cluster and the TMA-fed X ring
     prm.pair = (x3 && cluster == 2 && !gsrc && op.rows_pad % 16 == 0) ? 1 : 0;
-    if (const char* e = getenv("ZB200_TC_PAIR")) prm.pair = (prm.pair && atoi(e) != 0) ? 1 : 0;
+    if (kn.tc_pair == 0) prm.pair = 0;
 
     prm.b_stages = 3;
-    if (const char* e = getenv("ZB200_TC_BSTAGES")) { int v = atoi(e); if (v >= 1 && v <= 4) prm.b_stages = v; }
+    if (kn.tc_bstages) prm.b_stages = kn.tc_bstages;
     if (x3) {
         const int bst = (prm.pair ? 1 : 2) * prm.n_pad * 128, xb = sub * kTileRows * 128;
         prm.n_stages = (kSmemLimit - bar_bytes - prm.b_stages * bst) / xb;
     } else
     prm.n_stages = (kSmemLimit - bar_bytes) / stage_bytes(sub);
     if (prm.n_stages > 8) prm.n_stages = 8;
-    if (const char* e = getenv("ZB200_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < prm.n_stages) prm.n_stages = v; }
+    if (kn.tc_stages && kn.tc_stages < prm.n_stages) prm.n_stages = kn.tc_stages;
     if (prm.n_stages < 1) {
         set_error("project_tc: operand of %d rows does not fit shared memory", prm.n_pad);
         return ZB200_EUNSUP;
@@ -1086,8 +1114,8 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
             prm.acc_bufs = 1;
             room = ((int)kTmemCols - sub * prm.n_pad) / per_buf;
         }
-        if (const char* e = getenv("ZB200_TC_ACCBUFS")) {
-            const int v = atoi(e);
+        if (kn.tc_accbufs) {
+            const int v = kn.tc_accbufs;
             if (x3 && (v == 1 || (v == 2 && 2 * sub * prm.n_pad + per_buf <= (int)kTmemCols))) {
                 prm.acc_bufs = v;
                 room = ((int)kTmemCols - v * sub * prm.n_pad) / per_buf;
@@ -1145,6 +1173,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     ZB_TC_LAUNCH(kOutScores)
 #undef ZB_TC_LAUNCH
     ZB_LAUNCHED();
+#if ZB200_DEBUG_HOOKS
     if (prm.dbg & 16) {
         unsigned long long h[16];
         cudaDeviceSynchronize();
@@ -1156,6 +1185,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(g_wait_cycles, z, sizeof(z));
     }
+#endif
     return ZB200_OK;
 }
 

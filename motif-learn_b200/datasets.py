@@ -159,3 +159,273 @@ def honeycomb_frame_gpu(size, bond: float = 12.0, seed: int | None = 0, angle: f
     h, w = shape
     inside = (pts[:, 0] >= 0) & (pts[:, 0] < w) & (pts[:, 1] >= 0) & (pts[:, 1] < h)
     return img, pts[inside]
+
+
+# =================================================================================================================
+# GPU mirrors of the reference's synthetic-data classes ("next" row f1 of SURVEY.md section 8)
+# =================================================================================================================
+class HoneyCombLattice:
+    """``mtflearn.datasets.HoneyCombLattice`` (mtflearn/datasets/_honeycomb_lattice.py:6-226) with the coordinate
+    generation and the drawing on the GPU: same constructor, same attributes, ``get_points()`` and ``to_image()``
+    with the reference's arguments.  The reference builds the sites with a Python double loop and draws them with a
+    per-atom numpy loop (3.5 s per 2048^2 frame); here ``zb200_lattice_coords_f64`` and ``zb200_render_atoms_f32`` do
+    both in a few milliseconds.  Randomness (origin shift, jitter) is drawn on the host from the same
+    ``numpy.random.default_rng(seed)`` stream in the same order, so a seeded lattice is the reference's lattice."""
+
+    def __init__(self, size: int = 512, l: float = 12.0, a=None, angle: float = 0.0, random_shift: bool = True,
+                 seed=None, jitter: float = 0.0):
+        self.size = int(size)
+        self.l = float(l)
+        inferred_a = self.l * np.sqrt(3.0)
+        if a is not None:
+            a = float(a)
+            if not np.isclose(a, inferred_a, rtol=1e-5, atol=1e-6):
+                raise ValueError(
+                    f"Inconsistent 'a' and 'l': got a={a}, l={self.l}, "
+                    f"but for ideal graphene expect a≈sqrt(3)*l≈{inferred_a:.6f}."
+                )
+            self.a = a
+        else:
+            self.a = inferred_a
+        self.angle_deg = float(angle)
+        self.angle = np.deg2rad(self.angle_deg)
+        self.a1 = np.array([1.5 * self.l, np.sqrt(3.0) * self.l / 2.0], dtype=np.float64)
+        self.a2 = np.array([1.5 * self.l, -np.sqrt(3.0) * self.l / 2.0], dtype=np.float64)
+        self.dA = np.array([0.0, 0.0], dtype=np.float64)
+        self.dB = np.array([self.l, 0.0], dtype=np.float64)
+        self.rng = np.random.default_rng(seed)
+        self.random_shift = random_shift
+        if random_shift:
+            self.shift_u1, self.shift_u2 = self.rng.random(2)
+        else:
+            self.shift_u1 = 0.0
+            self.shift_u2 = 0.0
+        self.jitter = float(jitter)
+        self.N = int(np.ceil(self.size / self.l)) + 3
+        self._coords_A = None          # CUDA float64 tensors ((2N+1)^2, 2)
+        self._coords_B = None
+
+    def set_angle(self, angle: float) -> None:
+        self.angle_deg = float(angle)
+        self.angle = np.deg2rad(self.angle_deg)
+        self._coords_A = None
+        self._coords_B = None
+
+    def _generate_coordinates(self) -> None:
+        import ctypes as C
+        from . import _lib
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        count = (2 * self.N + 1) ** 2
+        offset = self.shift_u1 * self.a1 + self.shift_u2 * self.a2
+        ja = jb = None
+        if self.jitter > 0.0:                         # the reference draws A first, then B, from the same generator
+            ja = torch.from_numpy(self.rng.normal(0.0, self.jitter, (count, 2))).cuda()
+            jb = torch.from_numpy(self.rng.normal(0.0, self.jitter, (count, 2))).cuda()
+        ca = torch.empty((count, 2), dtype=torch.float64, device="cuda")
+        cb = torch.empty_like(ca)
+        vec = lambda v: np.ascontiguousarray(v, dtype=np.float64).ctypes.data_as(C.c_void_p)      # noqa: E731
+        a1, a2, dA, dB, off = (np.ascontiguousarray(v, dtype=np.float64) for v in (self.a1, self.a2, self.dA, self.dB, offset))
+        _lib.check(lib.zb200_lattice_coords_f64(self.N, vec(a1), vec(a2), vec(dA), vec(dB), vec(off), float(self.angle),
+                                                self.size / 2.0, None if ja is None else int(ja.data_ptr()),
+                                                None if jb is None else int(jb.data_ptr()), int(ca.data_ptr()),
+                                                int(cb.data_ptr()), C.c_void_p(_lib.current_stream_ptr())), "lattice_coords")
+        self._coords_A, self._coords_B = ca, cb
+
+    def _ensure(self):
+        if self._coords_A is None or self._coords_B is None:
+            self._generate_coordinates()
+
+    def coordinates(self):
+        """All generated sites (A, B) as host arrays -- the reference's ``_coords_A`` / ``_coords_B``."""
+        self._ensure()
+        return self._coords_A.cpu().numpy(), self._coords_B.cpu().numpy()
+
+    def get_points(self):
+        """A and B sublattice coordinates clipped to [0, size) (host arrays, like the reference)."""
+        ca, cb = self.coordinates()
+        size = self.size
+        keep = lambda c: c[(c[:, 0] >= 0.0) & (c[:, 0] < size) & (c[:, 1] >= 0.0) & (c[:, 1] < size)]      # noqa: E731
+        return keep(ca), keep(cb)
+
+    def to_image(self, sigma=None, intensity_A: float = 1.0, intensity_B: float = 0.5, normalize: bool = False,
+                 as_tensor: bool = False):
+        """Rasterise the lattice (tapered Gaussians, cut-off 3 sigma) into a (size, size) float32 frame.
+        ``as_tensor=True`` keeps the frame in HBM."""
+        import ctypes as C
+        from . import _lib
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        self._ensure()
+        if sigma is None:
+            sigma = self.l / 4.0
+        img = torch.empty((self.size, self.size), dtype=torch.float32, device="cuda")
+        stream = C.c_void_p(_lib.current_stream_ptr())
+        # sites whose support misses the frame contribute nothing; the kernel bins atoms per tile, so the whole
+        # over-generated list can be passed (the reference filters it first for its per-atom Python loop)
+        for coords, amp, acc in ((self._coords_A, intensity_A, 0), (self._coords_B, intensity_B, 1)):
+            _lib.check(lib.zb200_render_atoms_f32(int(coords.data_ptr()), None, float(amp), int(coords.shape[0]), float(sigma),
+                                                  3.0, self.size, self.size, int(img.data_ptr()), acc, stream), "render_atoms")
+        if normalize:
+            vmax = float(img.max())
+            if vmax > 0.0:
+                img /= vmax
+        return img if as_tensor else img.cpu().numpy()
+
+
+class TMDImageSimulator:
+    """``mtflearn.datasets.TMDImageSimulator`` (mtflearn/datasets/_tmd_simulator.py:7-210): hexagonal TMD lattice with
+    vacancies and dopants, rendered as delta functions blurred by a per-species Gaussian.  Same constructor, defect
+    API (``add_single_vacancy, add_double_vacancy, add_random_vacancies, add_random_dopants``), attributes
+    (``pts, pts_all, labels, lbs, filtered_indices``) and ``simulate(return_masks=False)``.  The lattice bookkeeping
+    is vectorised integer / float64 numpy on the host (the reference's pure-Python loops and its O(n^2) visibility
+    test take about a minute at 4096^2); placement and blur run on the GPU (``zb200_render_stamps_f32``: every atom
+    stamps its kernel directly, which is what the reference's ``fftconvolve(delta, kernel, 'same')`` evaluates up to
+    FFT round-off).  Quirks kept: defect indices are GLOBAL atom indices but are applied to the per-species arrays
+    (``_tmd_simulator.py:167-174``); species are drawn in sorted label order (the reference iterates a ``set``)."""
+
+    def __init__(self, size=(512, 512), a=30, theta=0.0, species_params=None, basis=None, use_fft=True):
+        self.size = size
+        self.a = a
+        self.theta = theta
+        self.use_fft = use_fft
+        self.species_params = species_params or {'TM': {'sigma': 2.0, 'A': 1.0}, 'X': {'sigma': 1.5, 'A': 0.6}}
+        self.basis = basis or [(0.0, 0.0, 'TM'), (1 / 3, 1 / 3, 'X')]
+        self.vacancies = []
+        self.dopants = []
+        self._cached_coords = None
+        self.pts_all = None
+        self.pts = None
+        self.labels = None
+        self.lbs = None
+        self.filtered_indices = {}
+
+    def rotation_matrix(self):
+        theta = np.deg2rad(self.theta)
+        return np.array([[np.cos(theta), -np.sin(theta)], [np.sin(theta), np.cos(theta)]])
+
+    def generate_lattice(self):
+        a1 = self.a * np.array([1, 0])
+        a2 = self.a * np.array([0.5, np.sqrt(3) / 2])
+        R = self.rotation_matrix()
+        height, width = self.size
+        nx = int(width // self.a * 2) + 4
+        ny = int(height // (self.a * np.sqrt(3) / 2) * 2) + 4
+        i = np.arange(-nx, nx, dtype=np.float64)[:, None, None]
+        j = np.arange(-ny, ny, dtype=np.float64)[None, :, None]
+        base = i * a1 + j * a2                                        # (2nx, 2ny, 2), the reference's loop order
+        per_basis = []
+        for dx, dy, label in self.basis:
+            pos = base + dx * a1 + dy * a2
+            rot = np.stack([R[0, 0] * pos[..., 0] + R[0, 1] * pos[..., 1],
+                            R[1, 0] * pos[..., 0] + R[1, 1] * pos[..., 1]], axis=-1)
+            per_basis.append(rot.reshape(-1, 2))
+        n_cells, n_basis = per_basis[0].shape[0], len(self.basis)
+        labels_basis = [b[2] for b in self.basis]
+        self.pts_all = np.stack(per_basis, axis=1).reshape(-1, 2)      # cell-major, basis atom innermost
+        all_labels = np.tile(np.array(labels_basis), n_cells)
+        coords = {}
+        for label in sorted(set(labels_basis)):
+            coords[label] = np.concatenate([per_basis[b].reshape(n_cells, 1, 2) for b in range(n_basis) if labels_basis[b] == label],
+                                           axis=1).reshape(-1, 2)
+        self._cached_coords = coords
+        mask = ((self.pts_all[:, 0] >= 0) & (self.pts_all[:, 0] < width) & (self.pts_all[:, 1] >= 0) & (self.pts_all[:, 1] < height))
+        self.pts = self.pts_all[mask]
+        defect_labels = all_labels.astype(object)
+        for _, vac_idx, scale in self.vacancies:
+            if scale == 0.5:
+                defect_labels[vac_idx] = 'v1'
+            elif scale == 0.0:
+                defect_labels[vac_idx] = 'v2'
+        for _, dop_idx, _ in self.dopants:
+            defect_labels[dop_idx] = 'D'
+        self.labels = np.array([str(v) for v in defect_labels[mask]])
+        label_to_int = {lbl: k for k, lbl in enumerate(sorted(set(str(v) for v in defect_labels)))}
+        self.lbs = np.array([label_to_int[lbl] for lbl in self.labels], dtype=int)
+        visible = np.where(mask)[0]
+        for label in coords:
+            idx = np.where(all_labels == label)[0]
+            self.filtered_indices[label] = [int(v) for v in idx[np.isin(idx, visible)]]
+        return coords
+
+    def add_single_vacancy(self, label='X', index=None):
+        if index is not None:
+            self.vacancies.append((label, index, 0.5))
+
+    def add_double_vacancy(self, label='X', indices=None):
+        if indices is not None and len(indices) >= 1:
+            self.vacancies.append((label, indices[0], 0.0))
+
+    def add_random_vacancies(self, label='X', num_single=0, num_double=0, seed=None):
+        if self._cached_coords is None:
+            self.generate_lattice()
+        indices = self.filtered_indices.get(label, [])
+        if len(indices) == 0:
+            return
+        rng = np.random.default_rng(seed)
+        rng.shuffle(indices)                                          # a Python list, like the reference
+        selected = 0
+        for _ in range(num_single):
+            if selected >= len(indices):
+                break
+            self.add_single_vacancy(label, indices[selected])
+            selected += 1
+        for _ in range(num_double):
+            if selected >= len(indices):
+                break
+            self.add_double_vacancy(label, [indices[selected]])
+            selected += 1
+
+    def add_random_dopants(self, label='TM', num_dopants=0, dopant_intensity=0.8, seed=None):
+        if self._cached_coords is None:
+            self.generate_lattice()
+        indices = self.filtered_indices.get(label, [])
+        if len(indices) == 0:
+            return
+        rng = np.random.default_rng(seed)
+        for idx in rng.choice(indices, size=min(num_dopants, len(indices)), replace=False):
+            self.dopants.append((label, idx, dopant_intensity))
+
+    def _scales(self, label, count):
+        scales = np.ones(count, dtype=np.float32)
+        for vac_label, vac_idx, scale in self.vacancies:
+            if vac_label == label and 0 <= vac_idx < count:
+                scales[vac_idx] = scale
+        for dop_label, dop_idx, dop_scale in self.dopants:
+            if dop_label == label and 0 <= dop_idx < count:
+                scales[dop_idx] = dop_scale
+        return scales
+
+    def simulate(self, return_masks: bool = False, as_tensor: bool = False):
+        import ctypes as C
+        from . import _lib
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        coords = self.generate_lattice()
+        height, width = self.size
+        total = torch.zeros((height, width), dtype=torch.float32, device="cuda")
+        stream = C.c_void_p(_lib.current_stream_ptr())
+        masks = {}
+        for label, atoms in coords.items():
+            d_pts = torch.from_numpy(np.ascontiguousarray(atoms, dtype=np.float64)).cuda()
+            d_sc = torch.from_numpy(self._scales(label, len(atoms))).cuda()
+            p = self.species_params.get(label, {'sigma': 2.0, 'A': 1.0})
+            if not self.use_fft:
+                raise NotImplementedError("use_fft=False (scipy.ndimage.gaussian_filter) is not provided on the GPU")
+            ksize = int(6 * p['sigma']) | 1
+            _lib.check(lib.zb200_render_stamps_f32(int(d_pts.data_ptr()), int(d_sc.data_ptr()), len(atoms), float(p['A']),
+                                                   float(p['sigma']), ksize, height, width, int(total.data_ptr()), 1, stream),
+                       "render_stamps")
+            if return_masks:
+                delta = torch.empty_like(total)
+                _lib.check(lib.zb200_render_stamps_f32(int(d_pts.data_ptr()), int(d_sc.data_ptr()), len(atoms), 1.0, 1.0, 1,
+                                                       height, width, int(delta.data_ptr()), 0, stream), "render_stamps")
+                masks[label] = delta if as_tensor else delta.cpu().numpy()
+        img = total if as_tensor else total.cpu().numpy()
+        return (img, masks) if return_masks else img
+
+    def get_defect_counts(self):
+        if self.labels is None:
+            raise ValueError("Run simulate() first to generate labels.")
+        unique, counts = np.unique(self.labels, return_counts=True)
+        return dict(zip(unique, counts))

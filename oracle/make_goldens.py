@@ -220,6 +220,75 @@ def golden_pca():
     save("pca.npz", feats=feats, pca2=pca(feats.astype(np.float64), 2), pca5=pca(feats.astype(np.float64), 5))
 
 
+def golden_datasets():
+    """Lattice coordinates and TMD frames ("next" row f1, second part) straight from the reference classes."""
+    from mtflearn.datasets import TMDImageSimulator
+    arrays = {}
+    for tag, kw in (("a", dict(size=160, l=12, seed=3, angle=17.0, jitter=0.2)),
+                    ("b", dict(size=200, l=10, seed=1, angle=-33.0, random_shift=False))):
+        lat = HoneyCombLattice(**kw)
+        img = lat.to_image(normalize=(tag == "b"))
+        pa, pb = lat.get_points()
+        arrays[f"lat_{tag}_A"], arrays[f"lat_{tag}_B"] = lat._coords_A, lat._coords_B
+        arrays[f"lat_{tag}_ptsA"], arrays[f"lat_{tag}_ptsB"] = pa, pb
+        arrays[f"lat_{tag}_img"] = img
+    for tag, kw, basis in (("a", dict(size=(96, 128), a=20, theta=7.0), None),
+                           ("b", dict(size=(80, 80), a=16, theta=30.0), [(0.0, 0.0, 'TM'), (1 / 3, 1 / 3, 'X'), (2 / 3, 2 / 3, 'X')])):
+        sim = TMDImageSimulator(basis=basis, **kw)
+        sim.add_random_vacancies('X', 3, 2, seed=0)
+        sim.add_random_dopants('TM', 4, seed=1)
+        img, masks = sim.simulate(return_masks=True)
+        arrays[f"tmd_{tag}_img"] = img
+        for label, m in masks.items():
+            arrays[f"tmd_{tag}_mask_{label}"] = m
+        arrays[f"tmd_{tag}_lbs"] = sim.lbs
+        arrays[f"tmd_{tag}_pts"] = sim.pts
+        arrays[f"tmd_{tag}_labels"] = np.array([str(v) for v in sim.labels])
+    save("datasets.npz", **arrays)
+
+
+def golden_clustering():
+    """Cluster labels ("next" row f4): the reference's own kmeans_lbs / gmm_lbs (scikit-learn underneath,
+    random_state=0) on rotation-invariant features of three patch families of unequal size; plus what the
+    reference's rot_maps returns when it is called on COMPLEX moments (it squares the complex numbers)."""
+    from mtflearn.clustering import kmeans_lbs, gmm_lbs
+    rng = np.random.default_rng(21)
+    fam = [get_zps_test_patches(size=32, n_fold=3, num_patches=500),
+           get_zps_test_patches(size=32, n_fold=4, num_patches=300),
+           get_zps_test_patches(size=32, n_fold=6, num_patches=200, include_center=False)]
+    patches = np.concatenate(fam).astype(np.float32)
+    patches += rng.normal(0, 0.02, patches.shape).astype(np.float32)
+    perm = rng.permutation(len(patches))
+    patches = patches[perm]
+    truth = np.concatenate([np.full(500, 0), np.full(300, 1), np.full(200, 2)])[perm]
+    o = ZPs(10, 32).fit_transform(patches)
+    feats = np.abs(o.to_complex().data)
+    oc = o.to_complex()
+    save("clustering.npz", feats=feats.astype(np.float32), truth=truth,
+         kmeans3=kmeans_lbs(feats, 3), kmeans5=kmeans_lbs(feats, 5), gmm3=gmm_lbs(feats, 3),
+         rot_on_complex=oc.rot_maps([2, 3, 4, 6])[:32], rot_on_real=o.rot_maps([2, 3, 4, 6])[:32],
+         cdata=oc.data[:32], cn=oc.n, cm=oc.m)
+
+
+def golden_denoise():
+    """Patch-SVD denoiser ("next" row f4): the reference's extract_patches / reconstruct_patches / denoise_svd on a
+    noisy lattice frame.  denoise_svd uses random_state=None: the stored frame is ONE draw of its randomized SVD, the
+    exact rank-r projection is stored beside it (the yardstick both implementations approximate)."""
+    from mtflearn.denoise._denoise_svd import extract_patches, reconstruct_patches, denoise_svd
+    rng = np.random.default_rng(5)
+    lat = HoneyCombLattice(size=144, l=12, seed=2, angle=11.0)
+    img = (lat.to_image() + rng.normal(0, 0.15, (144, 144))).astype(np.float64)[:128, :144]
+    patches = extract_patches(img, 16, 5)
+    rec = reconstruct_patches(patches * 1.0, img.shape, 5)
+    clean, s = denoise_svd(img, 16, 6, extraction_step=5, verbose=False, return_s=True)
+    flat = patches.reshape(patches.shape[0], -1)
+    u, sv, vt = np.linalg.svd(flat, full_matrices=False)
+    exact = reconstruct_patches(((u[:, :6] * sv[:6]) @ vt[:6]).reshape(-1, 16, 16), img.shape, 5)
+    save("denoise.npz", img=img, patch_shape=np.array(patches.shape), patch_sha=np.array(sha(patches)), patch_head=patches[:3],
+         rec=rec, clean=clean, s=s, exact=exact, s_exact=sv[:8])
+    print("randomized vs exact: frame", np.abs(clean - exact).max(), "s", np.abs(s - sv[:6]).max() / sv[0])
+
+
 if __name__ == "__main__":
     golden_index()
     golden_basis()
@@ -228,3 +297,6 @@ if __name__ == "__main__":
     golden_render()
     golden_peaks()
     golden_pca()
+    golden_datasets()
+    golden_clustering()
+    golden_denoise()

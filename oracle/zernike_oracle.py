@@ -475,3 +475,114 @@ def pca(X: np.ndarray, n_components: int = 2) -> np.ndarray:
     signs[signs == 0] = 1.0
     vt *= signs[:, None]
     return (X - mean) @ vt.T
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "next" row f1, second part: lattice coordinates and the TMD simulator
+# ---------------------------------------------------------------------------------------------------------------
+def honeycomb_coords(size: int, l: float = 12.0, angle: float = 0.0, random_shift: bool = True, seed=None,
+                     jitter: float = 0.0):
+    """All generated A / B sites of ``HoneyCombLattice`` (mtflearn/datasets/_honeycomb_lattice.py:69-140): origin
+    shift u1, u2 = rng.random(2) (``:75-79``), sites n1, n2 in [-N, N] with N = ceil(size/l)+3 (``:85, :112-117``),
+    rotation, centring, jitter drawn A first then B (``:123-135``).  Returns (coords_A, coords_B, rng)."""
+    rng = np.random.default_rng(seed)
+    u1, u2 = rng.random(2) if random_shift else (0.0, 0.0)
+    a1 = np.array([1.5 * l, np.sqrt(3.0) * l / 2.0])
+    a2 = np.array([1.5 * l, -np.sqrt(3.0) * l / 2.0])
+    d_a, d_b = np.array([0.0, 0.0]), np.array([float(l), 0.0])
+    n_idx = int(np.ceil(int(size) / float(l))) + 3
+    offset = u1 * a1 + u2 * a2
+    idx = np.arange(-n_idx, n_idx + 1, dtype=np.float64)
+    big_r = (idx[:, None, None] * a1 + idx[None, :, None] * a2).reshape(-1, 2)
+    th = np.deg2rad(float(angle))
+    rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    centre = np.array([int(size) / 2.0, int(size) / 2.0])
+    out = []
+    for d in (d_a, d_b):
+        out.append((big_r + d + offset) @ rot.T + centre)
+    if jitter > 0.0:
+        out[0] = out[0] + rng.normal(0.0, jitter, out[0].shape)
+        out[1] = out[1] + rng.normal(0.0, jitter, out[1].shape)
+    return out[0], out[1], rng
+
+
+def tmd_blur(shape_hw, atoms: np.ndarray, scales: np.ndarray, sigma: float, amp: float) -> np.ndarray:
+    """One species of ``TMDImageSimulator.simulate`` (mtflearn/datasets/_tmd_simulator.py:151-186):
+    ``place_atoms_delta`` (round to pixels, drop outside, float32 ``np.add.at``), ``gaussian_kernel`` of size
+    ``int(6 sigma) | 1`` and ``scipy.signal.fftconvolve(delta, kernel, mode='same')`` -- the same library call."""
+    from scipy.signal import fftconvolve
+    h, w = shape_hw
+    delta = np.zeros((h, w), dtype=np.float32)
+    xi = np.round(atoms[:, 0]).astype(int)
+    yi = np.round(atoms[:, 1]).astype(int)
+    ok = (xi >= 0) & (xi < w) & (yi >= 0) & (yi < h)
+    np.add.at(delta, (yi[ok], xi[ok]), scales[ok])
+    ksize = int(6 * sigma) | 1
+    r = np.arange(-ksize // 2 + 1, ksize // 2 + 1)
+    gx, gy = np.meshgrid(r, r)
+    kernel = amp * np.exp(-(gx ** 2 + gy ** 2) / (2 * sigma ** 2))
+    return fftconvolve(delta, kernel, mode="same"), delta
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "next" row f4, second part: cluster labels (the reference delegates to scikit-learn; same library calls here)
+# ---------------------------------------------------------------------------------------------------------------
+def _reorder_by_count(lbs: np.ndarray) -> np.ndarray:
+    """mtflearn/clustering/_clustering_functions.py:18-22: clusters renumbered by decreasing size."""
+    unique, counts = np.unique(lbs, return_counts=True)
+    lbs_order = np.argsort(counts)[::-1]
+    order_dict = dict(zip(lbs_order, unique))
+    return np.vectorize(order_dict.get)(lbs)
+
+
+def kmeans_lbs(X: np.ndarray, n: int, random_state=0) -> np.ndarray:
+    """``kmeans_lbs`` (mtflearn/clustering/_clustering_functions.py:8-23): sklearn KMeans(n_clusters=n, random_state)."""
+    from sklearn.cluster import KMeans
+    return _reorder_by_count(KMeans(n_clusters=n, random_state=random_state).fit(X).labels_)
+
+
+def gmm_lbs(X: np.ndarray, n: int, random_state=0) -> np.ndarray:
+    """``gmm_lbs`` (``:25-34``): sklearn GaussianMixture(n, covariance_type='full', random_state).fit(X).predict(X)."""
+    from sklearn.mixture import GaussianMixture
+    return _reorder_by_count(GaussianMixture(n, covariance_type="full", random_state=random_state).fit(X).predict(X))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "next" row f4, third part: patch-SVD denoiser
+# ---------------------------------------------------------------------------------------------------------------
+def patch_starts(extent: int, patch: int, step: int) -> np.ndarray:
+    """``_patch_start_indices`` (mtflearn/denoise/_denoise_svd.py:10-20): every ``step`` pixels plus the last start."""
+    last = extent - patch
+    idx = np.arange(0, last, step)
+    if idx.size == 0 or idx[-1] != last:
+        idx = np.append(idx, last)
+    return idx
+
+
+def denoise_extract(img: np.ndarray, patch: int, step: int) -> np.ndarray:
+    """``extract_patches`` (``:22-48``): patches at the start grid, row-major."""
+    ys, xs = patch_starts(img.shape[0], patch, step), patch_starts(img.shape[1], patch, step)
+    return np.stack([img[y:y + patch, x:x + patch] for y in ys for x in xs])
+
+
+def denoise_reconstruct(patches: np.ndarray, shape_hw, step: int) -> np.ndarray:
+    """``reconstruct_patches`` (``:51-70``): overlap-add in grid order, divided by the overlap count."""
+    h, w = shape_hw
+    k = patches.shape[1]
+    ys, xs = patch_starts(h, k, step), patch_starts(w, patches.shape[2], step)
+    img, cnt = np.zeros((h, w)), np.zeros((h, w))
+    it = iter(patches)
+    for y in ys:
+        for x in xs:
+            img[y:y + k, x:x + patches.shape[2]] += next(it)
+            cnt[y:y + k, x:x + patches.shape[2]] += 1.0
+    return img / cnt
+
+
+def denoise_svd_exact(img: np.ndarray, patch: int, n_components: int, step: int):
+    """``denoise_svd`` (``:79-120``) with the exact truncated SVD in place of sklearn's randomized one (which the
+    reference calls with random_state=None; 7 power iterations bring it within 1e-7 of this on the golden frame)."""
+    p = denoise_extract(img, patch, step)
+    u, s, vt = np.linalg.svd(p.reshape(p.shape[0], -1), full_matrices=False)
+    low = (u[:, :n_components] * s[:n_components]) @ vt[:n_components]
+    return denoise_reconstruct(low.reshape(-1, patch, patch), img.shape, step), s[:n_components]

@@ -867,3 +867,94 @@ def test_series_features_threads_and_streams(api, torch):
         np.testing.assert_array_equal(pts1[f], pts[f])
         assert one[f].data.shape == (len(pts[f]), 91)
     assert api.series_features(z, [], 5.0) == ([], [])
+
+
+def test_lattice_and_tmd_generators_golden(golden, torch):
+    """Row f1, second part: GPU HoneyCombLattice (coordinates + frame) and TMDImageSimulator.simulate against the
+    live reference's outputs (tests/golden/datasets.npz)."""
+    from motif_learn_b200.datasets import HoneyCombLattice, TMDImageSimulator
+    g = golden("datasets.npz")
+    for tag, kw in (("a", dict(size=160, l=12, seed=3, angle=17.0, jitter=0.2)),
+                    ("b", dict(size=200, l=10, seed=1, angle=-33.0, random_shift=False))):
+        lat = HoneyCombLattice(**kw)
+        ca, cb = lat.coordinates()
+        np.testing.assert_allclose(ca, g[f"lat_{tag}_A"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(cb, g[f"lat_{tag}_B"], rtol=0, atol=1e-10)
+        pa, pb = lat.get_points()
+        assert pa.shape == g[f"lat_{tag}_ptsA"].shape and pb.shape == g[f"lat_{tag}_ptsB"].shape
+        np.testing.assert_allclose(pa, g[f"lat_{tag}_ptsA"], rtol=0, atol=1e-10)
+        img = lat.to_image(normalize=(tag == "b"))
+        assert img.dtype == np.float32 and img.shape == g[f"lat_{tag}_img"].shape
+        np.testing.assert_allclose(img, g[f"lat_{tag}_img"], rtol=0, atol=4e-7)
+        assert lat.to_image(as_tensor=True).is_cuda
+    with pytest.raises(ValueError):
+        HoneyCombLattice(size=64, l=12.0, a=5.0)
+    for tag, kw, basis in (("a", dict(size=(96, 128), a=20, theta=7.0), None),
+                           ("b", dict(size=(80, 80), a=16, theta=30.0), [(0.0, 0.0, 'TM'), (1 / 3, 1 / 3, 'X'), (2 / 3, 2 / 3, 'X')])):
+        sim = TMDImageSimulator(basis=basis, **kw)
+        sim.add_random_vacancies('X', 3, 2, seed=0)
+        sim.add_random_dopants('TM', 4, seed=1)
+        img, masks = sim.simulate(return_masks=True)
+        assert img.dtype == np.float32
+        np.testing.assert_allclose(img, g[f"tmd_{tag}_img"], rtol=0, atol=3e-7)     # FFT round-off + float32 sum order
+        for label, m in masks.items():
+            np.testing.assert_array_equal(m, g[f"tmd_{tag}_mask_{label}"])
+        np.testing.assert_array_equal(sim.lbs, g[f"tmd_{tag}_lbs"])
+        assert [str(v) for v in sim.labels] == [str(v) for v in g[f"tmd_{tag}_labels"]]
+        np.testing.assert_allclose(sim.pts, g[f"tmd_{tag}_pts"], rtol=0, atol=1e-10)
+
+
+def test_cluster_labels_golden(golden, torch):
+    """Row f4: kmeans_lbs / gmm_lbs on the GPU give the labels of the live reference (scikit-learn, random_state=0):
+    identical seeding (same RandomState stream), Lloyd / EM passes in float64 on the device."""
+    from motif_learn_b200.clustering import gmm_lbs, kmeans_lbs, sort_lbs
+    g = golden("clustering.npz")
+    x = g["feats"]
+    for data in (x, torch.from_numpy(x).cuda()):
+        got = kmeans_lbs(data, 3)
+        assert isinstance(got, np.ndarray) and got.dtype == np.int64
+        np.testing.assert_array_equal(got, g["kmeans3"])
+    np.testing.assert_array_equal(kmeans_lbs(x, 5), g["kmeans5"])     # clusters that split a family: same trajectory
+    np.testing.assert_array_equal(gmm_lbs(x, 3), g["gmm3"])
+    np.testing.assert_array_equal(sort_lbs(np.array([7, 7, 2, 7, 2, 9])), np.array([0, 0, 1, 0, 1, 2]))
+    big = np.concatenate([x] * 40) + np.random.default_rng(0).normal(0, 1e-4, (40 * len(x), x.shape[1])).astype(np.float32)
+    np.testing.assert_array_equal(kmeans_lbs(big, 3), zo.kmeans_lbs(big.astype(np.float64), 3))     # 40 000 x 36 vs scikit-learn here
+    with pytest.raises(ValueError):
+        kmeans_lbs(x, 0)
+    with pytest.raises(NotImplementedError):
+        gmm_lbs(x, 3, type="diag")
+
+
+def test_rot_maps_on_complex_moments_documented_difference(api, golden, torch):
+    """The reference squares COMPLEX numbers when rot_maps is called on complex moments (its output is complex);
+    here complex moments are converted back to the real representation first, so the scores are those of the real
+    moments.  Pinned with the live reference's own output so that nobody is surprised."""
+    g = golden("clustering.npz")
+    zc = api.zmoments(g["cdata"], g["cn"], g["cm"])
+    ours = zc.rot_maps([2, 3, 4, 6])
+    np.testing.assert_allclose(ours, g["rot_on_real"], rtol=0, atol=1e-12)
+    assert np.abs(ours - g["rot_on_complex"]).max() > 0.1
+
+
+def test_denoise_svd_golden(golden, torch):
+    """Row f4: patch-SVD denoiser -- gather kernel on the strided grid, randomized SVD with library linear algebra,
+    overlap-add kernel -- against the live reference's frame (one draw of ITS randomized SVD) and the exact rank-r one."""
+    from motif_learn_b200.denoise import DenoiseSVD, denoise_svd, extract_patches, reconstruct_patches
+    g = golden("denoise.npz")
+    img = g["img"]
+    p = extract_patches(img, 16, 5)
+    assert p.shape == tuple(g["patch_shape"]) and p.dtype == np.float32
+    np.testing.assert_array_equal(p[:3], g["patch_head"].astype(np.float32))
+    np.testing.assert_array_equal(p, zo.denoise_extract(img, 16, 5).astype(np.float32))
+    rec = reconstruct_patches(zo.denoise_extract(img, 16, 5), img.shape, 5)
+    np.testing.assert_allclose(rec, g["rec"], rtol=0, atol=1e-13)
+    clean, s = denoise_svd(img, 16, 6, extraction_step=5, verbose=False, return_s=True)
+    assert clean.dtype == np.float64 and clean.shape == img.shape
+    np.testing.assert_allclose(clean, g["exact"], rtol=0, atol=5e-6)          # float32 gather of the float64 frame
+    np.testing.assert_allclose(clean, g["clean"], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(s, g["s"], rtol=1e-6)
+    job = DenoiseSVD(torch.from_numpy(img).cuda(), 6, 16, 5)
+    out = job.run()
+    assert out.is_cuda and np.abs(out.cpu().numpy() - g["exact"]).max() < 5e-6
+    with pytest.raises(ValueError):
+        denoise_svd(img, 200, 3)
