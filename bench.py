@@ -338,6 +338,7 @@ class Ctx:
     def __init__(self, torch, dist, rank, world, local, args, pk):
         self.torch, self.dist, self.rank, self.world, self.local, self.args, self.pk = torch, dist, rank, world, local, args, pk
         self.gpu_index = physical_gpu_index(local)
+        self.frame_max = 1.0
 
     def max_over_ranks(self, x: float) -> float:
         if self.world == 1:
@@ -407,12 +408,22 @@ def sample_rows(n: int, count: int = 4096):
     return np.concatenate([np.arange(0, c), np.arange(mid, mid + c), np.arange(n - c, n)])
 
 
+def value_bound(ctx, frame_max: float):
+    """--value-max: None -> no range hint ('auto' = tf32x3); 'frame' -> the maximum of the frame the patches were cut
+    from (what a K2 -> K3 pipeline knows for free); a number -> that bound."""
+    v = ctx.args.value_max
+    if v in (None, "none", "None"):
+        return None
+    return float(frame_max) if v == "frame" else float(v)
+
+
 def make_patch_batch(ctx, n: int, seed: int):
     """n device-resident 64x64 lattice patches: gathered (K2) at the atom sites of a 2048^2 frame, tiled to n."""
     torch = ctx.torch
     from motif_learn_b200.datasets import honeycomb_frame_gpu
     from motif_learn_b200.features import KeyPoints
     img, pts = honeycomb_frame_gpu(2048, bond=12.0, seed=seed)
+    ctx.frame_max = float(img.abs().max())
     base = KeyPoints(pts, img, PATCH).extract_patches()            # ~21 k patches, device-resident
     reps = -(-n // base.shape[0])
     out = torch.empty((n, PATCH, PATCH), dtype=torch.float32, device="cuda")
@@ -444,13 +455,14 @@ def bench_patches(ctx):
     from motif_learn_b200.features import ZPs
     from motif_learn_b200.parallel import PeerArray, gather_rows
     zo = _oracle()
-    zp = ZPs(N_MAX, PATCH, precision=args.precision)
-    prec = PREC_NAMES[zp._precision_code()]
-    n_modes = len(zp.n)
     batch = args.batch
     patches = make_patch_batch(ctx, batch, seed=ctx.rank)          # batch * 16 KiB >> 126 MB L2
+    vmax = value_bound(ctx, ctx.frame_max)
+    zp = ZPs(N_MAX, PATCH, precision=args.precision, value_max=vmax)
+    prec = PREC_NAMES[zp._precision_code(device_stack=True)]
+    n_modes = len(zp.n)
     gathered = torch.empty((world * batch, n_modes), dtype=torch.float32, device="cuda") if world > 1 else None
-    push = world > 1 and args.gather == "push" and prec in ("tf32", "tf32x3")
+    push = world > 1 and args.gather == "push" and prec in ("tf32", "tf32x3", "f16x3")
     peers = PeerArray(world * batch, n_modes) if push else None
     hold = {}
 
@@ -503,7 +515,8 @@ def bench_patches(ctx):
     alg_bytes = batch * (PATCH * PATCH * 4 + n_modes * 4)
     achieved = alg_bytes * args.steps / (ms_ng / 1e3) / 1e9
     flops = 2.0 * batch * PATCH * PATCH * n_modes
-    kernel = {"fp32": "project_simt_kernel", "tf32": "project_tc_kernel<plain>", "tf32x3": "project_tc3_kernel<plain,pair>"}[prec]
+    kernel = {"fp32": "project_simt_kernel", "tf32": "project_tc_kernel<plain>", "tf32x3": "project_tc3_kernel<plain,pair>",
+              "f16x3": "project_tc3_kernel<plain,pair,f16> (fp16 split, value_max hint)"}[prec]
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
             "traffic": NCU_TRAFFIC.get(prec) if batch == 262144 else None,
             "traffic_source": "profiles/ ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch",
@@ -517,13 +530,20 @@ def bench_patches(ctx):
                          "value": total * sus_steps / (ms_s / 1e3), "achieved": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9,
                          "frac": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9 / pk["hbm_gbs"], "clocks": clocks_s}
 
+    if prec == "f16x3":                                # the same batch without the range hint (tf32x3), same run
+        zp_nohint = ZPs(N_MAX, PATCH, precision=args.precision)
+        ms_t, _, _ = timed(ctx, lambda: zp_nohint.transform(patches), args.steps, 3)
+        roof["without_value_max"] = {"precision": PREC_NAMES[zp_nohint._precision_code(device_stack=True)],
+                                     "kernel": "project_tc3_kernel<plain,pair>", "ms_per_step": ms_t / args.steps,
+                                     "value": total * args.steps / (ms_t / 1e3),
+                                     "frac": alg_bytes * args.steps / (ms_t / 1e3) / 1e9 / pk["hbm_gbs"]}
     if peers is not None:
         peers.close()
     e2e = e2e_patches(ctx, zp, n_modes)
     cfg = workload_config("patches", world)
     cfg["batch_per_gpu"] = batch
     return {"metric": "zernike_patches_per_sec", "value": value, "unit": "patches/s", "ms_per_step": ms / args.steps,
-            "steps": args.steps, "dtype": DTYPES[prec], "precision": prec, "scaling": "weak", "config": cfg, "roofline": roof, "gather": gather,
+            "steps": args.steps, "dtype": DTYPES[prec], "precision": prec, "value_max": vmax, "scaling": "weak", "config": cfg, "roofline": roof, "gather": gather,
             "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
 
 
@@ -749,14 +769,15 @@ def bench_c3(ctx):
     total = args.c3_total
     lo, hi = shard_range(total, rank, world)
     n = hi - lo
-    zp = ZPs(C3_NMAX, PATCH, precision=args.precision)
-    prec = PREC_NAMES[zp._precision_code()]
     n_c = 121
     patches = make_patch_batch(ctx, n, seed=1000 + rank)                 # 16 KiB per patch: 16.4 GiB at N=1
+    vmax = value_bound(ctx, ctx.frame_max)
+    zp = ZPs(C3_NMAX, PATCH, precision=args.precision, value_max=vmax)
+    prec = PREC_NAMES[zp._precision_code(device_stack=True)]
     gathered = torch.empty((total, n_c), dtype=torch.complex64, device="cuda") if world > 1 else None
     hold = {}
 
-    push = world > 1 and args.gather == "push" and prec in ("tf32", "tf32x3")
+    push = world > 1 and args.gather == "push" and prec in ("tf32", "tf32x3", "f16x3")
     peers = PeerArray(total, 2 * n_c) if push else None
 
     def compute(kind="complex"):
@@ -819,12 +840,12 @@ def bench_c3(ctx):
             "peak": pk["hbm_gbs"] if f_h >= f_t else pk["tf32_tflops"], "unit": "GB/s" if f_h >= f_t else "TFLOP/s",
             "frac": max(f_h, f_t), "hbm": {"achieved": gbs, "peak": pk["hbm_gbs"], "frac": f_h},
             "tensor": {"achieved": tfl, "peak": pk["tf32_tflops"], "frac": f_t, "peak_source": pk["tf32_source"]},
-            "traffic": None, "kernel": "project_tc3_kernel<plain> on the complex-interleaved operand" if prec == "tf32x3" else "project_tc_kernel",
+            "traffic": None, "kernel": "project_tc3_kernel<plain> on the complex-interleaved operand" if prec in ("tf32x3", "f16x3") else "project_tc_kernel",
             "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": flops,
             "note": "SURVEY.md 8d: report both fractions, the larger one binds"}
     cfg = workload_config("c3", world)
     return {"metric": "zernike_patches_per_sec", "value": value, "unit": "patches/s", "ms_per_step": ms / steps, "steps": steps,
-            "dtype": DTYPES[prec], "precision": prec, "scaling": "strong", "config": cfg,
+            "dtype": DTYPES[prec], "precision": prec, "value_max": vmax, "scaling": "strong", "config": cfg,
             "details": {"total_patches": total, "patches_per_gpu": n}, "roofline": roof, "gather": gather, "parity": parity,
             "abs_features": {"ms_per_step": ms_abs / steps, "value": total * steps / (ms_abs / 1e3), "unit": "patches/s",
                              "what": "|Zc| epilogue instead of complex (no gather)"},
@@ -923,6 +944,8 @@ def main():
     ap.add_argument("--also", default="all", help="comma list of the other workloads to carry under 'also' (all | none | names)")
     ap.add_argument("--no-also", action="store_true", help="same as --also none")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--value-max", default="frame",
+                    help="range hint for the fp16-split projection: 'frame' (max of the frame the patches come from), a number, or none")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2.5 s sustained leg of the patch workload")
     ap.add_argument("--gather", default="push", choices=["push", "nccl"],
                     help="N>1: how the timed step gathers the features (push = fused P2P stores / copy engines; nccl = all_gather after the kernel)")

@@ -54,7 +54,7 @@ extern "C" {
 #define ZB200_PREC_TF32    1   /* tcgen05 kind::tf32, one pass (fast, ~1e-3 rel)  */
 #define ZB200_PREC_TF32X3  2   /* tcgen05 kind::tf32, 3-pass split (fp32-grade)   */
 #define ZB200_PREC_F16     3   /* dense map only: tcgen05 kind::f16, one pass on a range-scaled frame (~tf32-grade) */
-#define ZB200_PREC_F16X3   4   /* dense map only: fp16 operand split x1+x2, b1+b2, three passes (fp32-grade) */
+#define ZB200_PREC_F16X3   4   /* fp16 operand split x1+x2, b1+b2, three passes (fp32-grade): dense map; patch stacks through zb200_project_patches_ranged_f32 */
 
 /* what the projection epilogue writes */
 #define ZB200_OUT_REAL       0 /* float  [N, M]       real moments  (_zps.py:146-157)             */
@@ -118,6 +118,12 @@ int zb200_gather_patches_f32(const float* d_img, int H, int W,
 /* Z = X[N,k*k] . V[M,k*k]^T / (pi k^2/4) with the epilogue selected by out_kind. */
 int zb200_project_patches_f32(const zb200_plan* plan, const float* d_patches, int64_t n_patches,
                               int precision, int out_kind, void* d_out, void* d_out2, void* stream);
+/* The same projection in the fp16-split arithmetic (ZB200_PREC_F16X3: x = x1 + x2, V = b1 + b2 in fp16, three
+ * tcgen05 kind::f16 passes -- fp32-grade like TF32X3 with a quarter fewer tensor-core instructions and half the basis
+ * traffic).  fp16 has a narrow exponent range: value_max must bound |patch values|; inputs are scaled by the power
+ * of two that brings value_max to <= 2^14.  Values beyond 4 x value_max overflow to inf/NaN in the output. */
+int zb200_project_patches_ranged_f32(const zb200_plan* plan, const float* d_patches, int64_t n_patches, double value_max,
+                                     int out_kind, void* d_out, void* d_out2, void* stream);
 /* Fused n-fold scores of patches (rot_maps on real moments, _zmoments.py:420-462):
  * h_weights[F,M] is construct_rot_maps_matrix on the FULL mode list with zeros on
  * unselected modes, h_select[M] is 1 for modes kept by unselect(). d_scores [N,F]. */
@@ -162,7 +168,8 @@ int zb200_peer_buffer_free(void* d_ptr);
 int zb200_peer_buffer_open(const unsigned char* handle /* [64] */, void** d_ptr);
 int zb200_peer_buffer_close(void* d_ptr);
 int zb200_project_patches_push_f32(const zb200_plan* plan, const float* d_patches, int64_t n_patches, int precision,
-                                   int out_kind, void* d_out, void* const* d_out_peers, int n_peers, void* stream);
+                                   int out_kind, double value_max /* ZB200_PREC_F16X3 only */, void* d_out,
+                                   void* const* d_out_peers, int n_peers, void* stream);
 /* Copy-engine forwarding of a 2-D block (e.g. the F row bands of a score map) into a peer's array. */
 int zb200_peer_copy_2d(void* d_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t width_bytes,
                        size_t height, void* stream);

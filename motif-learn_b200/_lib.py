@@ -51,6 +51,7 @@ SIGNATURES = {
     "zb200_plan_basis_to_host": (_int, [_vp, _vp]),
     "zb200_gather_patches_f32": (_int, [_vp, _int, _int, _vp, _i64, _int, _vp, _vp]),
     "zb200_project_patches_f32": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _vp]),
+    "zb200_project_patches_ranged_f32": (_int, [_vp, _vp, _i64, C.c_double, _int, _vp, _vp, _vp]),
     "zb200_project_patches_scores_f32": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "zb200_project_peaks_f32": (_int, [_vp, _vp, _int, _int, _vp, _i64, _int, _int, _vp, _vp, _vp]),
     "zb200_project_patches_host": (_int, [_vp, _vp, _i64, _int, _vp]),
@@ -59,7 +60,7 @@ SIGNATURES = {
     "zb200_peer_buffer_free": (_int, [_vp]),
     "zb200_peer_buffer_open": (_int, [_vp, C.POINTER(_vp)]),
     "zb200_peer_buffer_close": (_int, [_vp]),
-    "zb200_project_patches_push_f32": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp]),
+    "zb200_project_patches_push_f32": (_int, [_vp, _vp, _i64, _int, _int, C.c_double, _vp, _vp, _int, _vp]),
     "zb200_peer_copy_2d": (_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp]),
     "zb200_moment_map_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "zb200_symmetry_map_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),

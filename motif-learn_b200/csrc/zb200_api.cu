@@ -86,10 +86,11 @@ static int alloc_operand(Operand& op, int rows, int k_pad) {
     ZB_CUDA(cudaMalloc(&op.lo, bytes));
     ZB_CUDA(cudaMalloc(&op.cb, bytes));
     ZB_CUDA(cudaMalloc(&op.t, bytes));
+    ZB_CUDA(cudaMalloc(&op.hb, bytes));
     return ZB200_OK;
 }
 static void free_operand(Operand& op) {
-    cudaFree(op.full); cudaFree(op.hi); cudaFree(op.lo); cudaFree(op.cb); cudaFree(op.t);
+    cudaFree(op.full); cudaFree(op.hi); cudaFree(op.lo); cudaFree(op.cb); cudaFree(op.t); cudaFree(op.hb);
     op = Operand();
 }
 
@@ -247,7 +248,7 @@ extern "C" int zb200_plan_basis_to_host(const zb200_plan* p, double* h_out) {
 extern "C" int zb200_plan_supports(const zb200_plan* p, int precision, int out_kind) {
     if (!p || out_kind < ZB200_OUT_REAL || out_kind > ZB200_OUT_ABS_PHASE) return 0;
     if (precision == ZB200_PREC_FP32) return out_kind == ZB200_OUT_REAL ? 1 : 0;
-    if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3)
+    if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3 || precision == ZB200_PREC_F16X3)
         return tc_supported(p, precision, out_kind != ZB200_OUT_REAL) ? 1 : 0;
     return 0;
 }
@@ -263,7 +264,7 @@ extern "C" int zb200_plan_supports_map(const zb200_plan* p, int precision) {
 namespace zb200 {
 int project_any(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind,
                 void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds,
-                int norm_kind, cudaStream_t s) {
+                int norm_kind, cudaStream_t s, double value_max) {
     if (precision == ZB200_PREC_FP32) {
         if (out_kind != ZB200_OUT_REAL || d_w) {
             set_error("the fp32 SIMT projection only produces real moments (out_kind REAL)");
@@ -271,8 +272,9 @@ int project_any(const zb200_plan* p, const float* d_patches, int64_t n, int prec
         }
         return project_simt(p, d_patches, n, static_cast<float*>(d_out), s);
     }
-    if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3) {
-        return project_tc(p, d_patches, n, precision, out_kind, d_out, d_out2, d_w, d_sel, n_folds, norm_kind, s);
+    if (precision == ZB200_PREC_TF32 || precision == ZB200_PREC_TF32X3 || precision == ZB200_PREC_F16X3) {
+        return project_tc(p, d_patches, n, precision, out_kind, d_out, d_out2, d_w, d_sel, n_folds, norm_kind, s, nullptr,
+                          nullptr, value_max);
     }
     set_error("unknown precision %d", precision);
     return ZB200_EINVAL;
@@ -288,6 +290,19 @@ extern "C" int zb200_project_patches_f32(const zb200_plan* p, const float* d_pat
     ZB_CHECK_ARG(d_patches && d_out, "project: null device pointer");
     ZB_CHECK_ARG(out_kind != ZB200_OUT_ABS_PHASE || d_out2, "project: ABS_PHASE needs d_out2");
     return project_any(p, d_patches, n, precision, out_kind, d_out, d_out2, nullptr, nullptr, 0, 0, as_stream(stream));
+}
+
+extern "C" int zb200_project_patches_ranged_f32(const zb200_plan* p, const float* d_patches, int64_t n, double value_max,
+                                                int out_kind, void* d_out, void* d_out2, void* stream) {
+    ZB_CHECK_ARG(p, "project_ranged: plan is null");
+    ZB_CHECK_ARG(n >= 0, "project_ranged: negative patch count");
+    ZB_CHECK_ARG(out_kind >= ZB200_OUT_REAL && out_kind <= ZB200_OUT_ABS_PHASE, "project_ranged: bad out_kind %d", out_kind);
+    ZB_CHECK_ARG(value_max > 0.0 && value_max < 1e30, "project_ranged: value_max must be a positive finite bound of |x|");
+    if (n == 0) return ZB200_OK;
+    ZB_CHECK_ARG(d_patches && d_out, "project_ranged: null device pointer");
+    ZB_CHECK_ARG(out_kind != ZB200_OUT_ABS_PHASE || d_out2, "project_ranged: ABS_PHASE needs d_out2");
+    return project_any(p, d_patches, n, ZB200_PREC_F16X3, out_kind, d_out, d_out2, nullptr, nullptr, 0, 0, as_stream(stream),
+                       value_max);
 }
 
 extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float* d_patches, int64_t n,

@@ -5,6 +5,7 @@
 #include "zb200_basis_math.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace zb200 {
 
@@ -44,7 +45,7 @@ __device__ __forceinline__ float to_tf32_rn(float f) {
 __global__ void pack_kernel(const double* __restrict__ basis, const int* __restrict__ row_map,
                             int rows_pad, int kk, int k_pad, double inv_area,
                             float* __restrict__ full, float* __restrict__ hi, float* __restrict__ lo,
-                            __nv_bfloat16* __restrict__ cb, float* __restrict__ tr) {
+                            __nv_bfloat16* __restrict__ cb, float* __restrict__ tr, __half* __restrict__ hb) {
     const int kidx = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (kidx >= k_pad) return;
@@ -63,6 +64,12 @@ __global__ void pack_kernel(const double* __restrict__ basis, const int* __restr
     cb[cbo] = __float2bfloat16_rn(f);
     cb[cbo + 8] = __float2bfloat16_rn((float)(v - (double)h));
     tr[(size_t)kidx * rows_pad + r] = f;
+    // fp16-split operand (V itself, not V/area): k-block kb of the row = [32 x b1 | 32 x b2]
+    const double raw = (src >= 0 && kidx < kk) ? basis[(size_t)src * kk + kidx] : 0.0;
+    const __half b1 = __double2half(raw);
+    const size_t hbo = (size_t)r * 2 * k_pad + (size_t)(kidx >> 5) * 64 + (kidx & 31);
+    hb[hbo] = b1;
+    hb[hbo + 32] = __double2half(raw - (double)__half2float(b1));
 }
 
 int launch_basis(zb200_plan* p, cudaStream_t s) {
@@ -80,7 +87,8 @@ static int pack_one(zb200_plan* p, Operand& op, const int* h_map, cudaStream_t s
     ZB_CUDA(cudaMemcpyAsync(d_map, h_map, sizeof(int) * op.rows_pad, cudaMemcpyHostToDevice, s));
     dim3 grid((unsigned)ceil_div(p->k_pad, 128), (unsigned)op.rows_pad);
     pack_kernel<<<grid, 128, 0, s>>>(p->basis64, d_map, op.rows_pad, p->kk, p->k_pad, p->inv_area,
-                                     op.full, op.hi, op.lo, reinterpret_cast<__nv_bfloat16*>(op.cb), op.t);
+                                     op.full, op.hi, op.lo, reinterpret_cast<__nv_bfloat16*>(op.cb), op.t,
+                                     reinterpret_cast<__half*>(op.hb));
     ZB_LAUNCHED();
     ZB_CUDA(cudaStreamSynchronize(s));
     ZB_CUDA(cudaFree(d_map));

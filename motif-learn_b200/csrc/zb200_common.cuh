@@ -88,11 +88,15 @@ struct Operand {
     float* lo = nullptr;
     uint32_t* cb = nullptr;  // bf16 pairs, same byte geometry as one fp32 row per operand row
     float* t = nullptr;
+    // fp16-split operand of the f16x3 projection: per 32-tap k-block and row 128 bytes = 32 x half b1 (RN_f16(V))
+    // then 32 x half b2 (RN_f16(V - b1)); V, not V/area (fp16 range) -- same byte geometry as one fp32 row
+    uint32_t* hb = nullptr;
     // TMA descriptors over [rows_pad][k_pad] 4-byte words, SW128, box 32 x rows_pad/C for cluster
     // sizes C = 1, 2, 4 (index log2 C): each CTA of a cluster fetches 1/C of the rows and multicasts
     CUtensorMap tmap_hi[3];
     CUtensorMap tmap_cb[3];
     CUtensorMap tmap_lo_f32[3];   // over the fp32 `lo` operand (dense-map 3xTF32 path)
+    CUtensorMap tmap_hb[3];       // over `hb`
     int max_cluster = 1;     // largest C with rows_pad % (8 C) == 0
     bool has_tmap = false;
 };
@@ -159,7 +163,8 @@ int init_tensor_maps(zb200_plan* plan);
 void free_host_pipe(zb200_plan* plan);
 // precision / epilogue dispatch of the patch projection (zb200_api.cu)
 int project_any(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind, void* d_out,
-                void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind, cudaStream_t s);
+                void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind, cudaStream_t s,
+                double value_max = 0.0);
 
 int project_simt(const zb200_plan* plan, const float* d_patches, int64_t n, float* d_out_real, cudaStream_t s);
 // frame + window corners for the fused gather -> projection path (K2 inside K3)
@@ -177,9 +182,11 @@ struct PeerTargets {
     int n = 0;
     float* out[7] = {};
 };
+// value_max: an upper bound of |patch values| for the f16x3 mode (sets the power-of-two input scale); ignored otherwise
 int project_tc(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind,
                void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
-               cudaStream_t s, const GatherSource* gather = nullptr, const PeerTargets* peers = nullptr);
+               cudaStream_t s, const GatherSource* gather = nullptr, const PeerTargets* peers = nullptr,
+               double value_max = 0.0);
 bool tc_supported(const zb200_plan* plan, int precision, bool complex_order);
 
 int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,

@@ -72,16 +72,16 @@ extern "C" int zb200_peer_copy_2d(void* d_dst, size_t dst_pitch, const void* d_s
 }
 
 extern "C" int zb200_project_patches_push_f32(const zb200_plan* p, const float* d_patches, int64_t n, int precision,
-                                              int out_kind, void* d_out, void* const* d_out_peers, int n_peers,
-                                              void* stream) {
+                                              int out_kind, double value_max, void* d_out, void* const* d_out_peers,
+                                              int n_peers, void* stream) {
     ZB_CHECK_ARG(p, "project_push: plan is null");
     ZB_CHECK_ARG(n >= 0, "project_push: negative patch count");
     ZB_CHECK_ARG(out_kind >= ZB200_OUT_REAL && out_kind <= ZB200_OUT_ABS, "project_push: out_kind %d not supported", out_kind);
     ZB_CHECK_ARG(n_peers >= 0 && n_peers <= 7 && (n_peers == 0 || d_out_peers), "project_push: 0..7 peers");
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG(d_patches && d_out, "project_push: null device pointer");
-    if (precision != ZB200_PREC_TF32 && precision != ZB200_PREC_TF32X3) {
-        set_error("project_push: the peer push lives in the tensor-core projection kernels (precision tf32 / tf32x3)");
+    if (precision != ZB200_PREC_TF32 && precision != ZB200_PREC_TF32X3 && precision != ZB200_PREC_F16X3) {
+        set_error("project_push: the peer push lives in the tensor-core projection kernels (precision tf32 / tf32x3 / f16x3)");
         return ZB200_EUNSUP;
     }
     PeerTargets peers;
@@ -93,5 +93,5 @@ extern "C" int zb200_project_patches_push_f32(const zb200_plan* p, const float* 
         peers.out[g] = static_cast<float*>(d_out_peers[g]);
     }
     return project_tc(p, d_patches, n, precision, out_kind, d_out, nullptr, nullptr, nullptr, 0, 0, as_stream(stream), nullptr,
-                      &peers);
+                      &peers, value_max);
 }

@@ -92,6 +92,9 @@ struct Params {
     // NVLink (P2P stores from an otherwise idle warp, tile by tile while the next tiles are being computed)
     int n_peers;
     float* peer_out[kMaxPeers];
+    // f16x3 mode: inputs are multiplied by x_scale (a power of two that brings |x| <= 2^14) before the fp16 split,
+    // the basis operand holds V (not V/area): results are multiplied by out_scale = 1 / (area * x_scale)
+    float x_scale, out_scale;
 };
 
 // ---- epilogue: 16 accumulator columns of one patch -----------------------------------------------
@@ -410,7 +413,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 constexpr int kRegsCtl = 48, kRegsEpi = 176, kRegsSplit = 112;     // (48 + 2*176 + 112) * 128 = 64 Ki
 constexpr int kMaxColChunks = 8;     // 8 x 16 = 128 running sums per epilogue thread
 
-template <int kOut, bool kPair>
+// kF16 = the fp16-split arithmetic (ZB200_PREC_F16X3): x = x1 + x2, V = b1 + b2 in fp16, three kind::f16 MMAs
+// (x1.b1, x2.b1, x1.b2) per 16 taps, all with A in TMEM -- 6 MMAs per 32-tap k-block and sub-tile instead of 8, no
+// MMA reads X from shared memory (the splitter releases the X stage as soon as it holds the row in registers), and
+// the basis stream is ONE 128-byte row per k-block ([32 x b1 | 32 x b2]) instead of two ([Bhi] + [Bcb]).
+template <int kOut, bool kPair, bool kF16>
 __global__ void __launch_bounds__(512, 1)
 project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_bhi,
                    const __grid_constant__ CUtensorMap map_blo, const Params p) {
@@ -421,7 +428,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // two rings: X (HBM stream, deep: bytes in flight hide the DRAM latency) and B (L2 stream, 2 slots)
     // [Bhi | Bcb] of one k-block; a CTA of a pair stages only its half of the rows of each
     const uint32_t bop_bytes = kPair ? b_bytes / 2 : b_bytes;
-    const uint32_t bst_bytes = 2 * bop_bytes;
+    const uint32_t bst_bytes = kF16 ? bop_bytes : 2 * bop_bytes;
     uint8_t* b_ring = smem + (size_t)p.n_stages * x_bytes;
     auto stage_x = [&](int s) { return smem + (size_t)s * x_bytes; };
     auto stage_bhi = [&](int s) { return b_ring + (size_t)s * bst_bytes; };
@@ -460,7 +467,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], kF16 ? 4 : 1);          // f16x3: the four splitter warps release the X stage
         }
         // pair mode: the leader's MMA thread is the only committer (multicast to both CTAs) and collects the
         // splitter / epilogue arrivals of both CTAs
@@ -537,6 +544,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                             // from each CTA of the pair)
                             mbar_arrive_expect_tx(&bfull[sb], bst_bytes);
                             tma_load_2d(stage_bhi(sb), &map_bhi, &bfull[sb], (p.kb0 + kb) * kBlockK, (int)crank * b_rows, kEvictLast);
+                            if (!kF16)
                             tma_load_2d(stage_blo(sb), &map_blo, &bfull[sb], (p.kb0 + kb) * kBlockK, (int)crank * b_rows, kEvictLast);
                             if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
                             continue;
@@ -544,11 +552,12 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         mbar_arrive_expect_tx(&bfull[sb], bst_bytes);
                         if (p.cluster == 1) {
                             tma_load_2d(stage_bhi(sb), &map_bhi, &bfull[sb], (p.kb0 + kb) * kBlockK, 0, kEvictLast);
-                            tma_load_2d(stage_blo(sb), &map_blo, &bfull[sb], (p.kb0 + kb) * kBlockK, 0, kEvictLast);
+                            if (!kF16) tma_load_2d(stage_blo(sb), &map_blo, &bfull[sb], (p.kb0 + kb) * kBlockK, 0, kEvictLast);
                         } else {
                             const size_t off = (size_t)crank * b_rows * 128;
                             tma_load_2d_mc(stage_bhi(sb) + off, &map_bhi, &bfull[sb], (p.kb0 + kb) * kBlockK, (int)crank * b_rows, cmask,
                                            kEvictLast);
+                            if (!kF16)
                             tma_load_2d_mc(stage_blo(sb) + off, &map_blo, &bfull[sb], (p.kb0 + kb) * kBlockK, (int)crank * b_rows, cmask,
                                            kEvictLast);
                         }
@@ -618,6 +627,50 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                             const uint32_t bhl = b_lo0 + (uint32_t)sb * b_step;
                             const uint32_t bcl = bhl + (bop_bytes >> 4);
                             const uint32_t a0 = lo_base + (uint32_t)(lb * p.subtiles) * kBlockK;
+                            if constexpr (kF16) {
+                                // fp16 split: per 16 taps x1.b1, x2.b1, x1.b2 -- A from TMEM (x1 in columns [0,16) of the
+                                // staging buffer, x2 in [16,32)), B = [b1 | b2] halves of the 128-byte operand row
+                                const uint32_t idesc_h = make_idesc_f16(p.n_pad, kPair ? 256 : 128);
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    if (!((km >> (2 * j)) & 3u)) continue;       // 16 taps outside the unit disk
+                                    const uint64_t b1d = desc_from_lo(bhl + 2 * j), b2d = desc_from_lo(bhl + 4 + 2 * j);
+                                    const uint32_t a1 = a0 + 8 * j, a2 = a0 + 16 + 8 * j;
+                                    if constexpr (kPair) {
+                                        umma_bf16_ts_2(d0, a1, b1d, idesc_h, acc_run);
+                                        umma_bf16_ts_2(d0, a2, b1d, idesc_h, 1u);
+                                        umma_bf16_ts_2(d0, a1, b2d, idesc_h, 1u);
+                                        if (p.subtiles == 2) {
+                                            umma_bf16_ts_2(d0 + p.n_pad, a1 + kBlockK, b1d, idesc_h, acc_run);
+                                            umma_bf16_ts_2(d0 + p.n_pad, a2 + kBlockK, b1d, idesc_h, 1u);
+                                            umma_bf16_ts_2(d0 + p.n_pad, a1 + kBlockK, b2d, idesc_h, 1u);
+                                        }
+                                    } else {
+                                        umma_bf16_ts(d0, a1, b1d, idesc_h, acc_run);
+                                        umma_bf16_ts(d0, a2, b1d, idesc_h, 1u);
+                                        umma_bf16_ts(d0, a1, b2d, idesc_h, 1u);
+                                        if (p.subtiles == 2) {
+                                            umma_bf16_ts(d0 + p.n_pad, a1 + kBlockK, b1d, idesc_h, acc_run);
+                                            umma_bf16_ts(d0 + p.n_pad, a2 + kBlockK, b1d, idesc_h, 1u);
+                                            umma_bf16_ts(d0 + p.n_pad, a1 + kBlockK, b2d, idesc_h, 1u);
+                                        }
+                                    }
+                                    acc_run = 1u;
+                                }
+                                if constexpr (kPair) {
+                                    umma_commit_2mc(&bempty[sb], 3);
+                                    umma_commit_2mc(&lo_empty[lb], 3);
+                                    if (kb == kb_end - 1) umma_commit_2mc(&acc_full[buf], 3);
+                                } else {
+                                    if (p.cluster == 1) umma_commit(&bempty[sb]);
+                                    else umma_commit_mc(&bempty[sb], cmask);
+                                    umma_commit(&lo_empty[lb]);
+                                    if (kb == kb_end - 1) umma_commit(&acc_full[buf]);
+                                }
+                                if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+                                if (++s == p.n_stages) { s = 0; ph ^= 1; }
+                                continue;
+                            }
                             // Xhi.Bhi (tf32; the tensor core truncates the raw X itself) and the bf16 correction
                             // Xlo.Bhi + Xhi.Blo, for the 4 K-steps of the k-block and each sub-tile
                             if constexpr (kPair) {
@@ -715,6 +768,29 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             w[6] = pack2(b.x, b.y);
             w[7] = pack2(b.z, b.w);
         };
+        // fp16 split of a pair: x1 = the top 11 significand bits of x' = x * scale (exact in fp16), x2 = RN_f16(x' - x1)
+        const float xsc = p.x_scale;
+        auto split2h = [&](float a, float b, uint32_t& w1, uint32_t& w2) {
+            a *= xsc;
+            b *= xsc;
+            const uint32_t ta = __float_as_uint(a) & 0xFFFFE000u, tb = __float_as_uint(b) & 0xFFFFE000u;
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(__uint_as_float(tb)), "f"(__uint_as_float(ta)));   // low half = a
+            uint64_t va, vb, vd;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(va) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(vb) : "r"(ta ^ 0x80000000u), "r"(tb ^ 0x80000000u));
+            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(vd) : "l"(va), "l"(vb));
+            uint32_t l0, l1;
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(l0), "=r"(l1) : "l"(vd));
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w2) : "f"(__uint_as_float(l1)), "f"(__uint_as_float(l0)));
+        };
+        // one row of a k-block (8 chunks of 4 taps) -> 32 TMEM columns: x1 pairs in [0,16), x2 pairs in [16,32)
+        auto split_row_h = [&](const float4 (&x)[8], uint32_t* w) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                split2h(x[c].x, x[c].y, w[2 * c], w[16 + 2 * c]);
+                split2h(x[c].z, x[c].w, w[2 * c + 1], w[16 + 2 * c + 1]);
+            }
+        };
         auto lds128 = [](uint32_t addr) {
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -809,14 +885,20 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 tc_fence_after();
                 if (!(ZB200_TC3_PROF && (p.dbg & 2))) {
                     uint32_t lo[32];
+                    if constexpr (kF16) split_row_h(x0, lo);
+                    else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) split8(x0[2 * c], x0[2 * c + 1], lo + 8 * c);
+                        for (int c = 0; c < 4; ++c) split8(x0[2 * c], x0[2 * c + 1], lo + 8 * c);
+                    }
                     tmem_st32(lo_base + lane_addr + (uint32_t)(lb * p.subtiles + 0) * kBlockK, lo);
                 }
                 if (p.subtiles == 2 && !(ZB200_TC3_PROF && (p.dbg & 2))) {
                     uint32_t lo[32];
+                    if constexpr (kF16) split_row_h(x1, lo);
+                    else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) split8(x1[2 * c], x1[2 * c + 1], lo + 8 * c);
+                        for (int c = 0; c < 4; ++c) split8(x1[2 * c], x1[2 * c + 1], lo + 8 * c);
+                    }
                     tmem_st32(lo_base + lane_addr + (uint32_t)(lb * p.subtiles + 1) * kBlockK, lo);
                 }
                 const long long t_st = prof ? clock64() : 0;
@@ -827,6 +909,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if (lane == 0) {
                     if (kPair && crank != 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&lo_full[lb]), 0));
                     else mbar_arrive(&lo_full[lb]);
+                    if constexpr (kF16) mbar_arrive(&empty[s]);      // the row lives in TMEM now: no MMA reads this X stage
                 }
                 if (++s == p.n_stages) { s = 0; ph ^= 1; }
             }
@@ -883,7 +966,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     if (cc < n_cc) {
                         uint32_t v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(sum[cc][i]);
+                        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(kF16 ? sum[cc][i] * p.out_scale : sum[cc][i]);
                         epilogue_chunk<kOut>(p, row, c_beg + cc * 16, v, sc);
                     }
                 }
@@ -984,6 +1067,9 @@ int init_tensor_maps(zb200_plan* p) {
             rc = tc::encode_2d(&op->tmap_lo_f32[lg], op->lo, (uint64_t)p->k_pad, (uint64_t)op->rows_pad,
                                (uint64_t)p->k_pad * 4, (uint32_t)(op->rows_pad / c));
             if (rc) return rc;
+            rc = tc::encode_2d(&op->tmap_hb[lg], op->hb, (uint64_t)p->k_pad, (uint64_t)op->rows_pad,
+                               (uint64_t)p->k_pad * 4, (uint32_t)(op->rows_pad / c));
+            if (rc) return rc;
             op->max_cluster = c;
         }
         op->has_tmap = true;
@@ -993,16 +1079,21 @@ int init_tensor_maps(zb200_plan* p) {
 
 int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind, void* d_out,
                void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind, cudaStream_t s,
-               const GatherSource* gsrc, const PeerTargets* peers) {
+               const GatherSource* gsrc, const PeerTargets* peers, double value_max) {
     using namespace tc;
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG(gsrc || (reinterpret_cast<uintptr_t>(d_patches) & 15) == 0,
                  "project: patch pointer must be 16-byte aligned");
+    const bool h3 = precision == ZB200_PREC_F16X3;
+    if (h3 && !(value_max > 0.0)) {
+        set_error("the f16x3 projection needs an upper bound of |patch values| (value_max > 0) to scale them into fp16 range");
+        return ZB200_EINVAL;
+    }
     if (gsrc && (precision != ZB200_PREC_TF32X3 || p->size < 32)) {
         set_error("fused gather+projection needs precision tf32x3 and a window of at least 32 pixels");
         return ZB200_EUNSUP;
     }
-    const bool x3 = precision == ZB200_PREC_TF32X3;
+    const bool x3 = precision == ZB200_PREC_TF32X3 || h3;       // the fp32-grade kernel family
     const bool scores = d_w != nullptr;
     const bool cplx = !scores && out_kind != ZB200_OUT_REAL;
     const Operand& op = cplx ? p->cplx : p->real;
@@ -1034,6 +1125,14 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                                                        : (out_kind == ZB200_OUT_COMPLEX ? 2 * p->n_complex : p->n_complex));
     prm.chunk_kb = 8;
     if (kn.tc_chunk) prm.chunk_kb = kn.tc_chunk;
+    prm.x_scale = prm.out_scale = 1.f;
+    if (h3) {
+        int e = 0;
+        frexp(value_max, &e);                               // value_max = f * 2^e, f in [0.5, 1): |x| * 2^(14-e) <= 2^14
+        const int sh = 14 - e < -100 ? -100 : (14 - e > 100 ? 100 : 14 - e);
+        prm.x_scale = (float)ldexp(1.0, sh);
+        prm.out_scale = (float)(p->inv_area * ldexp(1.0, -sh));
+    }
     if (gsrc) {
         prm.gather = 1;
         prm.g_img = gsrc->img;
@@ -1094,7 +1193,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     prm.b_stages = 3;
     if (kn.tc_bstages) prm.b_stages = kn.tc_bstages;
     if (x3) {
-        const int bst = (prm.pair ? 1 : 2) * prm.n_pad * 128, xb = sub * kTileRows * 128;
+        const int bst = (prm.pair ? 1 : 2) * prm.n_pad * 128 / (h3 ? 2 : 1), xb = sub * kTileRows * 128;
         prm.n_stages = (kSmemLimit - bar_bytes - prm.b_stages * bst) / xb;
     } else
     prm.n_stages = (kSmemLimit - bar_bytes) / stage_bytes(sub);
@@ -1130,7 +1229,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                   : encode_2d(&map_x, d_patches, (uint64_t)p->kk, (uint64_t)n, (uint64_t)p->kk * 4, (uint32_t)(sub * kTileRows));
     if (rc) return rc;
 
-    const size_t smem = x3 ? (size_t)prm.n_stages * sub * kTileRows * 128 + (size_t)prm.b_stages * (prm.pair ? 1 : 2) * prm.n_pad * 128 + bar_bytes
+    const size_t smem = x3 ? (size_t)prm.n_stages * sub * kTileRows * 128 + (size_t)prm.b_stages * (prm.pair ? 1 : 2) * prm.n_pad * 128 / (h3 ? 2 : 1) + bar_bytes
                            : (size_t)prm.n_stages * stage_bytes(sub) + bar_bytes;
     int grid = prm.n_tiles < p->sm_count ? prm.n_tiles : p->sm_count;
     grid = (grid / cluster) * cluster;                               // whole clusters only (148 = 2*74 = 4*37)
@@ -1150,16 +1249,26 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                             : (out_kind == ZB200_OUT_ABS ? kOutAbs : (out_kind == ZB200_OUT_ABS_PHASE ? kOutAbsPhase : kOutPlain));
 #define ZB_TC_LAUNCH(KOUT)                                                                                            \
     if (kout == KOUT) {                                                                                               \
-        if (x3 && prm.pair) {                                                                                         \
-            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        if (h3 && prm.pair) {                                                                                         \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                                 \
             cfg.blockDim = dim3(512);                                                                                 \
-            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true, true>, map_x, op.tmap_hb[lg], op.tmap_hb[lg], prm)); \
+        } else if (h3) {                                                                                              \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                                 \
+            cfg.blockDim = dim3(512);                                                                                 \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, false, true>, map_x, op.tmap_hb[lg], op.tmap_hb[lg], prm)); \
+        } else if (x3 && prm.pair) {                                                                                  \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                                 \
+            cfg.blockDim = dim3(512);                                                                                 \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true, false>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
         } else if (x3) {                                                                                              \
-            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                                 \
             cfg.blockDim = dim3(512);                                                                                 \
-            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, false>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, false, false>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
         } else {                                                                                                      \
             ZB_CUDA(cudaFuncSetAttribute(project_tc_kernel<KOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                          (int)smem));                                                                 \

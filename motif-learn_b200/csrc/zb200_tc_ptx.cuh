@@ -242,6 +242,14 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int n, int m = 128) {
     d |= (uint32_t)(m >> 4) << 24;  // M / 16   (256 with cta_group::2)
     return d;
 }
+// kind::f16 with fp16 (not bf16) operands
+__device__ __forceinline__ uint32_t make_idesc_f16(int n, int m = 128) {
+    uint32_t d = 0;
+    d |= 1u << 4;                   // c_format = F32;  a_format = b_format = 0 = F16
+    d |= (uint32_t)(n >> 3) << 17;  // N / 8
+    d |= (uint32_t)(m >> 4) << 24;  // M / 16   (256 with cta_group::2)
+    return d;
+}
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(

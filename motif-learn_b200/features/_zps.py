@@ -15,6 +15,12 @@ images through the sliding-window map kernel.  Extra, keyword-only options:
                'tf32x3'; dense maps: the fp16-split 'f16x3', then 'tf32x3'), otherwise the fp32 SIMT
                kernel.  'f16x3'/'f16' are dense-map kernels; for patch stacks they mean 'tf32x3'/'tf32'.
                Stated error bounds: DESIGN.md.
+``value_max``  None | float -- an upper bound of ``|pixel values|`` of the patch stacks this transformer will see
+               (e.g. 1.0 for frames normalised to [0, 1]).  With it, CUDA patch stacks run through the fp16-split
+               projection ('f16x3': three fp16 tensor-core passes on x = x1 + x2, V = b1 + b2 -- fp32-grade like
+               'tf32x3', a quarter fewer tensor-core instructions and half the basis traffic).  fp16 has a narrow
+               exponent range, so the inputs are scaled by a power of two derived from this bound; values beyond it
+               by more than 4x overflow to inf / NaN in the result (loud, not silent).  Without it 'auto' is 'tf32x3'.
 ``output``     'auto' | 'numpy' | 'torch' -- 'auto' returns what it was given: numpy in ->
                float64 numpy out (like the reference); CUDA tensor in -> float32 CUDA tensor.
 """
@@ -83,7 +89,7 @@ class ZPs(BaseEstimator, TransformerMixin):
         Size of the polynomial grid (size x size).
     """
 
-    def __init__(self, n_max: int, size: int, *, precision: str = "auto", output: str = "auto"):
+    def __init__(self, n_max: int, size: int, *, precision: str = "auto", output: str = "auto", value_max=None):
         if n_max < 0:
             raise ValueError("n_max must be non-negative.")
         if size <= 0:
@@ -109,8 +115,11 @@ class ZPs(BaseEstimator, TransformerMixin):
             raise ValueError("output must be one of 'auto', 'numpy', 'torch'")
         self.n_max = n_max
         self.size = size
+        if value_max is not None and not (np.isfinite(value_max) and value_max > 0):
+            raise ValueError("value_max must be a positive finite bound of |pixel values| (or None)")
         self.precision = precision
         self.output = output
+        self.value_max = value_max
         self.n, self.m = _mode_table(n_max)
         self._basis_host = None
 
@@ -174,7 +183,7 @@ class ZPs(BaseEstimator, TransformerMixin):
                 f"as large as polynomial size ({self.size}x{self.size})"
             )
 
-    def _precision_code(self, for_map: bool = False) -> int:
+    def _precision_code(self, for_map: bool = False, device_stack: bool = False) -> int:
         lib = _lib.load()
         if self.precision == "auto":
             if for_map:
@@ -183,11 +192,32 @@ class ZPs(BaseEstimator, TransformerMixin):
                         return code
                 return _lib.PREC_FP32
             ok = lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3, _lib.OUT_REAL)
+            if ok and device_stack and self.value_max is not None:
+                return _lib.PREC_F16X3
             return _lib.PREC_TF32X3 if ok else _lib.PREC_FP32
         code = _lib.PRECISIONS[self.precision]
         if not for_map and code in (_lib.PREC_F16, _lib.PREC_F16X3):
+            if code == _lib.PREC_F16X3 and device_stack and self.value_max is not None:
+                return code
             code = _lib.PREC_TF32 if code == _lib.PREC_F16 else _lib.PREC_TF32X3
         return code
+
+    def _project(self, dev, code, out, out2=None):
+        """One launch of the projection on a CUDA stack with the epilogue ``code``; picks the fp16-split kernel when
+        ``value_max`` allows it."""
+        lib = _lib.load()
+        prec = self._precision_code(device_stack=True)
+        if prec == _lib.PREC_F16X3 and not lib.zb200_plan_supports(self._plan, prec, code):
+            prec = self._precision_code()
+        o2 = None if out2 is None else int(out2.data_ptr())
+        if prec == _lib.PREC_F16X3:
+            _lib.check(lib.zb200_project_patches_ranged_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]),
+                                                            float(self.value_max), code, int(out.data_ptr()), o2,
+                                                            self._stream()), "project_patches_ranged")
+        else:
+            _lib.check(lib.zb200_project_patches_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]), prec, code,
+                                                     int(out.data_ptr()), o2, self._stream()), "project_patches")
+        return prec
 
     def _want_host(self, given) -> bool:
         if self.output == "auto":
@@ -217,9 +247,7 @@ class ZPs(BaseEstimator, TransformerMixin):
         dev = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32)).cuda() if host_in else images
         dev = dev.to(device="cuda", dtype=torch.float32).contiguous()
         out = torch.empty((n_img, n_modes), dtype=torch.float32, device=dev.device)
-        _lib.check(lib.zb200_project_patches_f32(self._plan, int(dev.data_ptr()), n_img, self._precision_code(),
-                                                 _lib.OUT_REAL, int(out.data_ptr()), None, self._stream()),
-                   "project_patches")
+        self._project(dev, _lib.OUT_REAL, out)
         data = _host_f64(out) if self._want_host(images) else out
         return zmoments(data=data, n=self.n, m=self.m, patch_size=self.size)
 
@@ -227,9 +255,7 @@ class ZPs(BaseEstimator, TransformerMixin):
         """Real moments (N, M) float32 of a CUDA patch stack, always a CUDA tensor (internal)."""
         torch = _lib.require_cuda()
         out = torch.empty((int(dev.shape[0]), len(self.n)), dtype=torch.float32, device=dev.device)
-        _lib.check(_lib.load().zb200_project_patches_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]),
-                                                         self._precision_code(), _lib.OUT_REAL, int(out.data_ptr()), None,
-                                                         self._stream()), "project_patches")
+        self._project(dev, _lib.OUT_REAL, out)
         return zmoments(data=out, n=self.n, m=self.m, patch_size=self.size)
 
     def transform_features(self, images, kind: str = "abs"):
@@ -268,9 +294,7 @@ class ZPs(BaseEstimator, TransformerMixin):
             out = torch.empty((n_img, n_c), dtype=torch.float32, device=dev.device)
             if kind == "abs_phase":
                 out2 = torch.empty_like(out)
-        _lib.check(lib.zb200_project_patches_f32(self._plan, int(dev.data_ptr()), n_img, prec, code,
-                                                 int(out.data_ptr()), None if out2 is None else int(out2.data_ptr()),
-                                                 self._stream()), "project_patches")
+        self._project(dev, code, out, out2)
         return out if out2 is None else (out, out2)
 
     def transform_allgather(self, images, peers, row0: int, kind: str = "real"):
@@ -292,12 +316,13 @@ class ZPs(BaseEstimator, TransformerMixin):
         n = int(dev.shape[0])
         if row0 < 0 or row0 + n > peers.rows:
             raise ValueError("rows [row0, row0 + n) fall outside the peer array")
-        prec = self._precision_code()
-        if prec not in (_lib.PREC_TF32, _lib.PREC_TF32X3) or not lib.zb200_plan_supports(self._plan, prec, code):
+        prec = self._precision_code(device_stack=True)
+        if prec not in (_lib.PREC_TF32, _lib.PREC_TF32X3, _lib.PREC_F16X3) or not lib.zb200_plan_supports(self._plan, prec, code):
             raise ValueError("transform_allgather needs a tensor-core precision supported for this shape")
         others = [r for r in range(peers.world) if r != peers.rank]
         ptrs = (C.c_void_p * max(1, len(others)))(*[peers.row_ptr(r, row0) for r in others])
         _lib.check(lib.zb200_project_patches_push_f32(self._plan, int(dev.data_ptr()), n, prec, code,
+                                                      float(self.value_max or 0.0),
                                                       C.c_void_p(peers.row_ptr(peers.rank, row0)), ptrs, len(others),
                                                       self._stream()), "project_patches_push")
         return peers.local[row0:row0 + n]
@@ -455,15 +480,40 @@ class ZPs(BaseEstimator, TransformerMixin):
         self._validate_size(image)
         torch = _lib.require_cuda()
         lib = _lib.load()
-        dev = self._image_on_device(image)
+        out = self._map_device(self._image_on_device(image), row0, rows)
+        data = _host_f64(out) if self._want_host(image) else out
+        return zmoments(data=data, n=self.n, m=self.m, patch_size=self.size)
+
+    def _map_device(self, dev, row0: int = 0, rows: Optional[int] = None):
+        """Moment maps (M, rows, W) of a CUDA frame as a CUDA tensor (internal)."""
+        torch = _lib.require_cuda()
         h, w = int(dev.shape[0]), int(dev.shape[1])
         rows = h - row0 if rows is None else rows
         out = torch.empty((len(self.n), rows, w), dtype=torch.float32, device=dev.device)
-        _lib.check(lib.zb200_moment_map_f32(self._plan, int(dev.data_ptr()), h, w, row0, rows,
-                                            self._precision_code(for_map=True), int(out.data_ptr()), self._stream()),
+        _lib.check(_lib.load().zb200_moment_map_f32(self._plan, int(dev.data_ptr()), h, w, row0, rows,
+                                                    self._precision_code(for_map=True), int(out.data_ptr()), self._stream()),
                    "moment_map")
-        data = _host_f64(out) if self._want_host(image) else out
-        return zmoments(data=data, n=self.n, m=self.m, patch_size=self.size)
+        return out
+
+    def mirror_map(self, image, theta=None, p=2, m_unselect=(0, 1), band_rows: int = 64):
+        """``transform(image).mirror_map(theta, p, m_unselect)`` (mtflearn/features/_zmoments.py:464-493) without the
+        (M, H, W) moment maps ever existing in full: the frame is processed in bands of ``band_rows`` output rows --
+        dense moment map of the band (K4, bit-identical to the corresponding rows of the full map), then the
+        mirror-score kernel on that band -- so the working set is ``M * band_rows * W`` floats (95 MB at W = 4096)
+        instead of 6.1 GB for a 4096^2 frame.  Returns (H, W)."""
+        if image.ndim != 2:
+            raise ValueError("Images must be 2D or 3D array.")
+        self._validate_size(image)
+        torch = _lib.require_cuda()
+        dev = self._image_on_device(image)
+        h, w = int(dev.shape[0]), int(dev.shape[1])
+        band_rows = max(2, int(band_rows) & ~1)                       # even: the map kernel pairs rows by absolute parity
+        out = torch.empty((h, w), dtype=torch.float32, device=dev.device)
+        for r0 in range(0, h, band_rows):
+            rows = min(band_rows, h - r0)
+            band = zmoments(data=self._map_device(dev, r0, rows), n=self.n, m=self.m, patch_size=self.size)
+            out[r0:r0 + rows] = band.mirror_map(theta=theta, p=p, m_unselect=m_unselect)
+        return _host_f64(out) if self._want_host(image) else out
 
     def symmetry_map(self, image, n_folds, p=2, m_unselect=None, row0: int = 0, rows: Optional[int] = None):
         """Fused ``transform(image).rot_maps(n_folds, p, m_unselect)`` that never writes the

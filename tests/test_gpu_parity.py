@@ -958,3 +958,59 @@ def test_denoise_svd_golden(golden, torch):
     assert out.is_cuda and np.abs(out.cpu().numpy() - g["exact"]).max() < 5e-6
     with pytest.raises(ValueError):
         denoise_svd(img, 200, 3)
+
+
+# ---- fp16-split projection (round 2) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n_max,size,count", [(12, 64, 1500), (20, 64, 300), (10, 32, 700), (12, 48, 257), (3, 6, 5)])
+def test_projection_f16x3_vs_oracle(api, torch, n_max, size, count):
+    """ZB200_PREC_F16X3 on patch stacks (value_max given): the strict fp32-grade gate against the oracle, every
+    fused epilogue, and invariance under the scale of the data (the power-of-two input scale follows value_max)."""
+    rng = np.random.default_rng(n_max * 1000 + size)
+    patches = rng.random((count, size, size), dtype=np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        n, m, v = zo.zernike_basis(n_max, size)
+    ref = zo.project_patches(patches.astype(np.float64), v)
+    refc = zo.to_complex(ref, n, m)[0]
+    z = api.ZPs(n_max, size, value_max=1.0)
+    from motif_learn_b200 import _lib
+    if not _lib.load().zb200_plan_supports(z._plan, _lib.PREC_F16X3, _lib.OUT_REAL):
+        pytest.skip("no tensor-core projection for this shape")
+    assert z._precision_code(device_stack=True) == _lib.PREC_F16X3
+    dev = torch.from_numpy(patches).cuda()
+    fp32_close(z.transform(dev).data.cpu().numpy(), ref)
+    zc = z.transform_features(dev, "complex").cpu().numpy()
+    fp32_close(np.concatenate([zc.real, zc.imag], axis=1), np.concatenate([refc.real, refc.imag], axis=1))
+    mag, ph = z.transform_features(dev, "abs_phase")
+    assert np.abs(mag.cpu().numpy() - np.abs(refc)).max() <= 3e-6 * np.abs(refc).max()
+    big = np.abs(refc) > 1e-3 * np.abs(refc).max()
+    assert np.abs(np.angle(np.exp(1j * (ph.cpu().numpy() - np.angle(refc))))[big]).max() < 1e-3
+    # same numbers on rescaled data with a matching bound; the kernel equals tf32x3 to fp32-grade, not bit for bit
+    for scale in (3.7e5, 2.1e-7):
+        zs = api.ZPs(n_max, size, value_max=scale)
+        fp32_close(zs.transform(dev * scale).data.cpu().numpy() / scale, ref)
+    # a bound that is too small by more than 4x is LOUD: inf / NaN, never a silently wrong number
+    bad = api.ZPs(n_max, size, value_max=1e-6).transform(dev).data
+    assert not torch.isfinite(bad).all()
+    # without value_max nothing changes: 'auto' is tf32x3, and numpy input keeps the host pipeline
+    assert api.ZPs(n_max, size)._precision_code(device_stack=True) == _lib.PREC_TF32X3
+    fp32_close(z.transform(patches).data, ref)
+    from sklearn.base import clone
+    assert clone(z).value_max == 1.0
+    with pytest.raises(ValueError):
+        api.ZPs(n_max, size, value_max=-1.0)
+
+
+def test_mirror_map_in_row_bands(api, golden, torch):
+    """ZPs.mirror_map streams the frame through K4 + the mirror kernel band by band (the (M,H,W) maps never exist in
+    full): equal to the materialised route bit for bit, and to the live reference's mirror_map at the golden pixels."""
+    g = golden("lattice.npz")
+    img = g["map_img"]
+    z = api.ZPs(12, 48)
+    dimg = torch.from_numpy(img.astype(np.float32)).cuda()
+    full = z.transform(dimg).mirror_map()
+    for band in (64, 50, 7):
+        assert torch.equal(z.mirror_map(dimg, band_rows=band), full)
+    host = z.mirror_map(img.astype(np.float32))
+    assert isinstance(host, np.ndarray) and host.shape == img.shape
+    np.testing.assert_allclose(host[g["map_ys"], g["map_xs"]], g["map_mirror_pts"], rtol=0, atol=2e-5)
