@@ -499,8 +499,8 @@ def bench_patches(ctx):
     value = total * args.steps / (ms / 1e3)
     gather = None
     if world > 1:
-        ms_ng, _, _ = timed(ctx, compute, args.steps, 1)
-        ms_nccl, _, _ = timed(ctx, step_nccl, args.steps, 1)
+        ms_ng, _, _ = timed(ctx, compute, args.steps, 3)
+        ms_nccl, _, _ = timed(ctx, step_nccl, args.steps, 3)
         if push:                                       # the pushed copies equal the NCCL gather bit for bit, on every rank
             step_push()
             torch.cuda.synchronize()
@@ -525,7 +525,7 @@ def bench_patches(ctx):
 
     # sustained leg: >= 2.5 s of back-to-back launches with the 2 ms clock sampler -- what a long job sees
     sus_steps = args.steps if args.no_sustained else max(args.steps, int(2500.0 / max(ms_ng / args.steps, 1e-3)))
-    ms_s, clocks_s, _ = timed(ctx, compute, sus_steps, 1)
+    ms_s, clocks_s, _ = timed(ctx, compute, sus_steps, 3)
     roof["sustained"] = {"steps": sus_steps, "seconds": ms_s / 1e3, "ms_per_step": ms_s / sus_steps,
                          "value": total * sus_steps / (ms_s / 1e3), "achieved": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9,
                          "frac": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9 / pk["hbm_gbs"], "clocks": clocks_s}
@@ -703,8 +703,8 @@ def bench_map(ctx, tiled=False):
     gather = None
     ms_ng = ms
     if do_gather:
-        ms_ng, _, _ = timed(ctx, compute, steps, 1, between=flush)
-        ms_nccl, _, _ = timed(ctx, step_nccl, steps, 1, between=flush)
+        ms_ng, _, _ = timed(ctx, compute, steps, 3, between=flush)
+        ms_nccl, _, _ = timed(ctx, step_nccl, steps, 3, between=flush)
         if push:
             step_push()
             torch.cuda.synchronize()
@@ -817,8 +817,8 @@ def bench_c3(ctx):
     gather = None
     ms_ng = ms
     if world > 1:
-        ms_ng, _, _ = timed(ctx, compute, steps, 1)
-        ms_nccl, _, _ = timed(ctx, step_nccl, steps, 1)
+        ms_ng, _, _ = timed(ctx, compute, steps, 3)
+        ms_nccl, _, _ = timed(ctx, step_nccl, steps, 3)
         if push:
             step_push()
             torch.cuda.synchronize()
@@ -830,7 +830,7 @@ def bench_c3(ctx):
         assert torch.equal(gathered[lo:hi], hold["z"]), "gathered rows differ from the local shard"
     if peers is not None:
         peers.close()
-    ms_abs, _, _ = timed(ctx, lambda: compute("abs"), steps, 1)
+    ms_abs, _, _ = timed(ctx, lambda: compute("abs"), steps, 3)
     alg_bytes = n * (PATCH * PATCH * 4 + n_c * 8)
     flops = 2.0 * n * PATCH * PATCH * 231
     gbs = alg_bytes * steps / (ms_ng / 1e3) / 1e9
@@ -899,12 +899,12 @@ def bench_c5(ctx):
               "max_err_over_max": err, "gate": "identical peak list; |Zc| abs err <= 3e-6*max|ref|"}
 
     steps = max(2, min(args.steps, 3))
-    ms, clocks, launches = timed(ctx, step, steps, 1)
+    ms, clocks, launches = timed(ctx, step, steps, 3)
     n_patches = ctx.sum_over_ranks(float(sum(hold["counts"])))
     value = n_patches * steps / (ms / 1e3)
     gather = None
     if world > 1:
-        ms_ng, _, _ = timed(ctx, compute, steps, 1)
+        ms_ng, _, _ = timed(ctx, compute, steps, 3)
         mine = float(sum(hold["counts"]))
         gather = gather_report(ctx, "ragged all_gather_into_tensor (NCCL) of the per-rank feature blocks, sizes exchanged first",
                                ms, ms_ng, None, steps, n_patches, int((n_patches - mine) * n_c * 4))

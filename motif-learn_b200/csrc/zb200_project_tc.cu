@@ -91,6 +91,7 @@ struct Params {
     // K5 fused into K3: copies of the output rows go to the same rows of up to 7 peer GPUs' result arrays over
     // NVLink (P2P stores from an otherwise idle warp, tile by tile while the next tiles are being computed)
     int n_peers;
+    uint32_t push_off;    // byte offset of the pusher's staging region (mbarrier + kPushChunk bytes) in dynamic shared memory
     float* peer_out[kMaxPeers];
     // f16x3 mode: inputs are multiplied by x_scale (a power of two that brings |x| <= 2^14) before the fp16 split,
     // the basis operand holds V (not V/area): results are multiplied by out_scale = 1 / (area * x_scale)
@@ -189,18 +190,21 @@ __device__ __forceinline__ void finish_scores(const Params& p, long long row, co
 // ---- K5 inside K3: one warp forwards finished output tiles to the peer GPUs ----------------------------------
 // The epilogue warps store a tile's rows to the local result array, fence, and bump `done` (shared memory, one
 // count per storing warp; a monotonic counter, not an mbarrier: the epilogue never waits for the pusher, so phases
-// could wrap).  The pusher warp then reads the tile's rows back through L2 (ld.cg: a line that straddles two tiles
-// must not be served from a stale L1 copy) and writes them to the same offsets of every peer's array with 16-byte
-// stores -- fully coalesced 512-B warp stores, the packet size NVLink moves efficiently, where the epilogue's own
-// 4-byte stores at a 364-byte stride would not.
-__device__ __forceinline__ void push_tile(const Params& p, long long r0, int n_rows, int lane) {
+// could wrap).  The pusher warp then moves the tile's rows (contiguous in the row-major result) from the local array
+// to the same offsets of every peer's array in 16 KB bulk copies -- large NVLink packets, where the epilogue's own
+// 4-byte stores at a 364-byte stride would not be.
+constexpr uint32_t kPushChunk = 16384;            // bytes staged per bulk copy (shared-memory staging buffer)
+constexpr uint32_t kPushRegion = kPushChunk + 128;  // + its mbarrier
+
+__device__ __forceinline__ void push_tile(const Params& p, long long r0, int n_rows, int lane, uint8_t* stage,
+                                          uint64_t* bar, uint32_t& phase) {
     const size_t nf = (size_t)n_rows * p.row_len;
     const float* src = p.out + (size_t)r0 * p.row_len;
     size_t head = ((16u - (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 2;
     if (head > nf) head = nf;
     const size_t nv = (nf - head) >> 2, tail0 = head + (nv << 2);
     const size_t off = (size_t)r0 * p.row_len;
-    // at most 3 leading and 3 trailing floats around the 16-byte aligned body
+    // at most 3 leading and 3 trailing floats around the 16-byte aligned body: plain P2P stores
     if ((size_t)lane < head) {
         const float v = __ldcg(src + lane);
         for (int g = 0; g < p.n_peers; ++g) p.peer_out[g][off + lane] = v;
@@ -209,33 +213,55 @@ __device__ __forceinline__ void push_tile(const Params& p, long long r0, int n_r
         const float v = __ldcg(src + tail0 + lane);
         for (int g = 0; g < p.n_peers; ++g) p.peer_out[g][off + tail0 + lane] = v;
     }
-    // two 16-byte loads in flight per lane: the pusher lives in the control warpgroup (48 registers per thread after
-    // setmaxnreg.dec), so the loop is kept small; its latency is hidden behind a whole tile of computation
-    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
-    for (size_t i = lane; i < nv; i += 64) {
-        const bool two = i + 32 < nv;
-        const uint4 a = __ldcg(s4 + i);
-        uint4 b = a;
-        if (two) b = __ldcg(s4 + i + 32);
-        for (int g = 0; g < p.n_peers; ++g) {
-            uint4* d4 = reinterpret_cast<uint4*>(p.peer_out[g] + off + head);
-            d4[i] = a;
-            if (two) d4[i + 32] = b;
+    // the body moves through the copy engine of the SM: bulk load of a chunk from the local result array (L2) into
+    // the staging buffer, then one bulk store per peer; the elected thread only orchestrates.  (A register loop --
+    // ld.cg then st per peer -- is bound by the L2 load latency at ~0.7 GB/s per warp: fine for one peer, 4.5x
+    // slower than the whole kernel for three.)
+    if (lane == 0) {
+        const size_t body = nv << 4;
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(src + head);
+        const uint32_t st = smem_u32(stage), br = smem_u32(bar);
+        for (size_t o = 0; o < body; o += kPushChunk) {
+            const uint32_t n = (uint32_t)(body - o < kPushChunk ? body - o : kPushChunk);
+            mbar_arrive_expect_tx(bar, n);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st),
+                         "l"(sb + o), "r"(n), "r"(br)
+                         : "memory");
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            for (int g = 0; g < p.n_peers; ++g) {
+                uint8_t* dst = reinterpret_cast<uint8_t*>(p.peer_out[g] + off + head) + o;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(st), "r"(n) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staging buffer may be overwritten
         }
     }
+    __syncwarp();
 }
 
-__device__ __forceinline__ void pusher_loop(const Params& p, volatile unsigned* done, int warps_per_tile, int my_tiles, int lane) {
+__device__ __forceinline__ void pusher_loop(const Params& p, volatile unsigned* done, int warps_per_tile, int my_tiles, int lane,
+                                            uint8_t* region) {
     const int tile_rows = p.subtiles * kTileRows;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(region);
+    uint8_t* stage = region + 128;
+    uint32_t phase = 0;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
     for (int t = 0; t < my_tiles; ++t) {
         const long long r0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * tile_rows;
         if (r0 >= p.n_patches) break;
         const unsigned want = (unsigned)(t + 1) * (unsigned)warps_per_tile;
         while (*done < want) __nanosleep(256);
         __syncwarp();
+        asm volatile("fence.proxy.async.global;" ::: "memory");      // the rows were written through the generic proxy
         const long long left = p.n_patches - r0;
-        push_tile(p, r0, (int)(left < tile_rows ? left : tile_rows), lane);
+        push_tile(p, r0, (int)(left < tile_rows ? left : tile_rows), lane, stage, bar, phase);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store has left the staging buffer AND landed
     __threadfence_system();
 }
 
@@ -384,12 +410,13 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
             if (p.n_peers) {
                 __threadfence();                              // this tile's rows are in L2 before the pusher is told
+                asm volatile("fence.proxy.async.global;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) atomicAdd(out_done, 1u);
             }
         }
     } else if (warp == 3 && p.n_peers) {
-        pusher_loop(p, out_done, 4, my_tiles, lane);
+        pusher_loop(p, out_done, 4, my_tiles, lane, smem + p.push_off);
     }
 
     tc_fence_before();
@@ -722,7 +749,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             __syncwarp();
         } else if (warp == kWarpAlloc && p.n_peers) {
             // ===================== K5: forward finished tiles to the peer GPUs =====================
-            pusher_loop(p, out_done, p.epi_solo ? 4 : 8, my_tiles, lane);
+            pusher_loop(p, out_done, p.epi_solo ? 4 : 8, my_tiles, lane, smem + p.push_off);
         }
     } else if (wg == 0) {
         // ===================== splitter =====================
@@ -974,6 +1001,7 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
             if (p.n_peers) {
                 __threadfence();                              // this tile's rows are in L2 before the pusher is told
+                asm volatile("fence.proxy.async.global;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) atomicAdd(out_done, 1u);
             }
@@ -1157,7 +1185,10 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
 
     // tile shape: two 128-patch accumulators per tile when TMEM/smem allow and there is enough work
     // to keep every SM busy with 256-patch tiles
-    const int bar_bytes = 1024 + 8 * (2 * 8 + 24) + 16;
+    const bool pushing = peers && peers->n > 0;
+    // barriers (+ alignment slack); with peers also the pusher's staging region, 128-byte aligned behind them
+    const int bar_core = 1024 + 8 * (2 * 8 + 24) + 16;
+    const int bar_bytes = pushing ? round_up(bar_core, 128) + 128 + (int)kPushRegion : bar_core;
     auto stage_bytes = [&](int sub) { return sub * kTileRows * 128 + (x3 ? 2 : 1) * prm.n_pad * 128; };
     int sub = 2;
     if (scores && n_folds > kFusedFolds) {
@@ -1229,8 +1260,11 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                   : encode_2d(&map_x, d_patches, (uint64_t)p->kk, (uint64_t)n, (uint64_t)p->kk * 4, (uint32_t)(sub * kTileRows));
     if (rc) return rc;
 
-    const size_t smem = x3 ? (size_t)prm.n_stages * sub * kTileRows * 128 + (size_t)prm.b_stages * (prm.pair ? 1 : 2) * prm.n_pad * 128 / (h3 ? 2 : 1) + bar_bytes
-                           : (size_t)prm.n_stages * stage_bytes(sub) + bar_bytes;
+    const size_t ring_bytes = x3 ? (size_t)prm.n_stages * sub * kTileRows * 128 + (size_t)prm.b_stages * (prm.pair ? 1 : 2) * prm.n_pad * 128 / (h3 ? 2 : 1)
+                                 : (size_t)prm.n_stages * stage_bytes(sub);
+    const size_t smem = ring_bytes + bar_bytes;
+    // rings start at the 1024-byte aligned base (<= 1023 bytes of slack inside bar_core), barriers follow the rings
+    prm.push_off = (uint32_t)round_up((int)ring_bytes + (bar_core - 1024), 128);
     int grid = prm.n_tiles < p->sm_count ? prm.n_tiles : p->sm_count;
     grid = (grid / cluster) * cluster;                               // whole clusters only (148 = 2*74 = 4*37)
     if (grid < cluster) grid = cluster;
