@@ -191,20 +191,58 @@ __device__ __forceinline__ void finish_scores(const Params& p, long long row, co
 // The epilogue warps store a tile's rows to the local result array, fence, and bump `done` (shared memory, one
 // count per storing warp; a monotonic counter, not an mbarrier: the epilogue never waits for the pusher, so phases
 // could wrap).  The pusher warp then moves the tile's rows (contiguous in the row-major result) from the local array
-// to the same offsets of every peer's array in 16 KB bulk copies -- large NVLink packets, where the epilogue's own
+// to the same offsets of every peer's array in 512-byte warp stores -- large NVLink packets, where the epilogue's own
 // 4-byte stores at a 364-byte stride would not be.
-constexpr uint32_t kPushChunk = 16384;            // bytes staged per bulk copy (shared-memory staging buffer)
-constexpr uint32_t kPushRegion = kPushChunk + 128;  // + its mbarrier
+constexpr uint32_t kPushChunk = 8192;               // bytes per staged chunk; two staging buffers
+constexpr uint32_t kPushRegion = 2 * kPushChunk + 128;  // + their mbarriers
+
+// Body of a tile (16-byte aligned, `body` bytes at `sb` locally, at `off_bytes` inside every peer's array):
+// chunks are bulk-loaded from the local result array (L2 hits) into two shared-memory buffers -- the load of chunk
+// c+1 is in flight while chunk c is being stored -- and written to the peers with 16-byte st.global from the whole
+// warp (512 contiguous bytes per instruction and peer).  Remote stores are posted, so the warp streams at the rate
+// NVLink accepts them; the first version issued one bulk STORE per peer instead and ran at ~3 GB/s per SM (the copy
+// engine's window of outstanding remote writes), a register loop with ld.cg at ~0.7 GB/s per warp (L2 load latency).
+__device__ __forceinline__ void push_body(const Params& p, const uint8_t* sb, size_t body, size_t off_bytes, int lane,
+                                          uint8_t* stage, uint64_t* bars, uint32_t (&phase)[2]) {
+    const int n_chunks = (int)((body + kPushChunk - 1) / kPushChunk);
+    auto issue = [&](int c) {
+        const size_t o = (size_t)c * kPushChunk;
+        const uint32_t n = (uint32_t)(body - o < kPushChunk ? body - o : kPushChunk);
+        const int b = c & 1;
+        mbar_arrive_expect_tx(&bars[b], n);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(stage + (size_t)b * kPushChunk)),
+                     "l"(sb + o), "r"(n), "r"(smem_u32(&bars[b]))
+                     : "memory");
+    };
+    if (n_chunks > 0 && lane == 0) issue(0);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1;
+        if (c + 1 < n_chunks && lane == 0) issue(c + 1);          // buffer (c+1)&1 was drained before the last __syncwarp
+        mbar_wait(&bars[b], phase[b]);
+        phase[b] ^= 1u;
+        const size_t o = (size_t)c * kPushChunk;
+        const uint32_t nv = (uint32_t)((body - o < kPushChunk ? body - o : kPushChunk) >> 4);
+        const uint32_t src = smem_u32(stage + (size_t)b * kPushChunk);
+        for (uint32_t i = lane; i < nv; i += 32) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + (i << 4)));
+            for (int g = 0; g < p.n_peers; ++g)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.peer_out[g]) + off_bytes + o + ((size_t)i << 4)) = v;
+        }
+        __syncwarp();
+    }
+}
 
 __device__ __forceinline__ void push_tile(const Params& p, long long r0, int n_rows, int lane, uint8_t* stage,
-                                          uint64_t* bar, uint32_t& phase) {
+                                          uint64_t* bars, uint32_t (&phase)[2]) {
     const size_t nf = (size_t)n_rows * p.row_len;
     const float* src = p.out + (size_t)r0 * p.row_len;
     size_t head = ((16u - (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 2;
     if (head > nf) head = nf;
     const size_t nv = (nf - head) >> 2, tail0 = head + (nv << 2);
     const size_t off = (size_t)r0 * p.row_len;
-    // at most 3 leading and 3 trailing floats around the 16-byte aligned body: plain P2P stores
+    // at most 3 leading and 3 trailing floats around the 16-byte aligned body
     if ((size_t)lane < head) {
         const float v = __ldcg(src + lane);
         for (int g = 0; g < p.n_peers; ++g) p.peer_out[g][off + lane] = v;
@@ -213,41 +251,18 @@ __device__ __forceinline__ void push_tile(const Params& p, long long r0, int n_r
         const float v = __ldcg(src + tail0 + lane);
         for (int g = 0; g < p.n_peers; ++g) p.peer_out[g][off + tail0 + lane] = v;
     }
-    // the body moves through the copy engine of the SM: bulk load of a chunk from the local result array (L2) into
-    // the staging buffer, then one bulk store per peer; the elected thread only orchestrates.  (A register loop --
-    // ld.cg then st per peer -- is bound by the L2 load latency at ~0.7 GB/s per warp: fine for one peer, 4.5x
-    // slower than the whole kernel for three.)
-    if (lane == 0) {
-        const size_t body = nv << 4;
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(src + head);
-        const uint32_t st = smem_u32(stage), br = smem_u32(bar);
-        for (size_t o = 0; o < body; o += kPushChunk) {
-            const uint32_t n = (uint32_t)(body - o < kPushChunk ? body - o : kPushChunk);
-            mbar_arrive_expect_tx(bar, n);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st),
-                         "l"(sb + o), "r"(n), "r"(br)
-                         : "memory");
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            for (int g = 0; g < p.n_peers; ++g) {
-                uint8_t* dst = reinterpret_cast<uint8_t*>(p.peer_out[g] + off + head) + o;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(st), "r"(n) : "memory");
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staging buffer may be overwritten
-        }
-    }
-    __syncwarp();
+    push_body(p, reinterpret_cast<const uint8_t*>(src + head), nv << 4, (off + head) * sizeof(float), lane, stage, bars, phase);
 }
 
 __device__ __forceinline__ void pusher_loop(const Params& p, volatile unsigned* done, int warps_per_tile, int my_tiles, int lane,
                                             uint8_t* region) {
     const int tile_rows = p.subtiles * kTileRows;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(region);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(region);
     uint8_t* stage = region + 128;
-    uint32_t phase = 0;
+    uint32_t phase[2] = {0u, 0u};
     if (lane == 0) {
-        mbar_init(bar, 1);
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
         fence_barrier_init();
     }
     __syncwarp();
@@ -259,9 +274,8 @@ __device__ __forceinline__ void pusher_loop(const Params& p, volatile unsigned* 
         __syncwarp();
         asm volatile("fence.proxy.async.global;" ::: "memory");      // the rows were written through the generic proxy
         const long long left = p.n_patches - r0;
-        push_tile(p, r0, (int)(left < tile_rows ? left : tile_rows), lane, stage, bar, phase);
+        push_tile(p, r0, (int)(left < tile_rows ? left : tile_rows), lane, stage, bars, phase);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store has left the staging buffer AND landed
     __threadfence_system();
 }
 

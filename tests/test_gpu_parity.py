@@ -690,6 +690,17 @@ def test_integration_stubs_bind_the_c_abi_directly(torch):
     host = np.empty((len(n), 70, 90), dtype=np.float64)
     assert lib.zb200_download_as_f64(dev.data_ptr(), dev.numel(), host.ctypes.data, stream) == 0
     fp32_close(host, zo.moment_map_fft(image.astype(np.float64), v, n))
+    # third stub of INTEGRATION.md: the notebooks' patch route end to end from a host frame
+    lib.zb200_project_peaks_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_int, C.c_int, C.c_void_p]
+    frame = np.ascontiguousarray(rng.random((120, 150)), dtype=np.float32)
+    pts = zo.clear_border(rng.uniform(0, 120, (40, 2)), frame.shape, 24).astype(np.float64)
+    counts = np.array([len(pts)], dtype=np.int64)
+    frames = (C.c_void_p * 1)(frame.ctypes.data)
+    feats = np.empty((len(pts), len(n)), dtype=np.float64)
+    assert lib.zb200_project_peaks_host(plan, frames, 1, 120, 150, pts.ctypes.data, counts.ctypes.data, 2, 0, 1,
+                                        feats.ctypes.data) == 0, lib.zb200_last_error()
+    fp32_close(feats, zo.project_patches(zo.extract_patches(frame, pts, 24).astype(np.float64), v))
 
 
 # ---- host-buffer routes (round 2) -----------------------------------------------------------------

@@ -145,7 +145,7 @@ def test_zps_validation_messages():
 def test_zps_is_sklearn_estimator():
     from sklearn.base import clone
     z = ZPs(10, 32, precision="fp32")
-    assert z.get_params() == {"n_max": 10, "size": 32, "precision": "fp32", "output": "auto"}
+    assert z.get_params() == {"n_max": 10, "size": 32, "precision": "fp32", "output": "auto", "value_max": None}
     c = clone(z)
     assert (c.n_max, c.size, c.precision) == (10, 32, "fp32")
     assert z.fit(None) is z
