@@ -653,7 +653,7 @@ def bench_map(ctx, tiled=False):
     torch, args, pk, world, rank = ctx.torch, ctx.args, ctx.pk, ctx.world, ctx.rank
     from motif_learn_b200.datasets import honeycomb_frame_gpu
     from motif_learn_b200.features import ZPs
-    from motif_learn_b200.parallel import PeerArray, gather_rows, push_score_bands, row_band, shard_sizes
+    from motif_learn_b200.parallel import PeerArray, gather_rows, row_band, shard_sizes, symmetry_map_allgather
     name = "map4k" if tiled else "map"
     size, window = (4096, 64) if tiled else (2048, 48)
     zp = ZPs(N_MAX, window, precision=args.precision)
@@ -681,9 +681,9 @@ def bench_map(ctx, tiled=False):
         gather_rows(hold["s"].permute(1, 0, 2), out=full, sizes=shard_sizes(size, world))
 
     def step_push():
+        # four sub-bands: the copy engines forward sub-band i (one 2-D copy per peer) while i+1 is being computed
         peers.begin()
-        compute()
-        push_score_bands(peers, hold["s"], row0, size)                 # copy engines: F row bands per peer in one 2-D copy
+        hold["parts"] = symmetry_map_allgather(zp, dimg, FOLDS, peers, row0, rows, size, n_sub=4)
         peers.fence()
 
     step = step_push if push else (step_nccl if do_gather else compute)
@@ -709,7 +709,7 @@ def bench_map(ctx, tiled=False):
             step_push()
             torch.cuda.synchronize()
             assert torch.equal(peers.local.view(len(FOLDS), size, size), full.permute(1, 0, 2)), "pushed score map differs from the NCCL gather"
-        gather = gather_report(ctx, "row bands forwarded to every peer by the copy engines (cudaMemcpy2DAsync over NVLink)" if push
+        gather = gather_report(ctx, "4 sub-bands per rank, each forwarded to every peer by the copy engines (cudaMemcpy2DAsync over NVLink) while the next is computed" if push
                                else "all_gather_into_tensor (NCCL) after the kernel", ms, ms_ng, ms_nccl if push else None,
                                steps, units, (size - rows) * len(FOLDS) * size * 4)
         assert torch.equal(full[row0:row0 + rows].permute(1, 0, 2), hold["s"]), "gathered band differs from the local one"

@@ -56,6 +56,7 @@ constexpr int kFoldsPerLaunch = 8;
 struct MapParams {
     int H, W;
     int row0, rows;
+    int plane_row0;      // first frame row held by the operand planes (they cover only the rows this band reads)
     int k, half, pad;
     int n_pad, n_modes;
     int n_terms;         // 1: x1.b1 only (11-bit operands);  3: fp32-grade split
@@ -138,17 +139,17 @@ __device__ __forceinline__ int frame_exponent(unsigned int absmax_bits) {
 // ---- pre-pass 2: frame -> overlapped fp16 operand planes [part][phase r][H][Wq][8] --------------------
 //   plane(part, r)[y][q][t] = part(img[y][4q + t + r - pad] * 2^(140-E)),   zero outside the row
 // also writes scale[0] = 2^(E-140) / area for the epilogue.
-__global__ void map_prepare_kernel(const float* __restrict__ img, int H, int W, int Wq, int pad, int n_parts,
+__global__ void map_prepare_kernel(const float* __restrict__ img, int y_first, int n_rows, int W, int Wq, int pad, int n_parts,
                                    const unsigned int* __restrict__ absmax_bits, double inv_area,
                                    uint4* __restrict__ planes, float* __restrict__ scale) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long plane_units = (long long)H * Wq;
+    const long long plane_units = (long long)n_rows * Wq;
     const int E = frame_exponent(*absmax_bits);
     if (i == 0) *scale = (float)ldexp(inv_area, E - 140);
     if (i >= plane_units) return;
     const float mult = __uint_as_float((uint32_t)(267 - E) << 23);       // 2^(140-E)
     const int y = (int)(i / Wq), q = (int)(i - (long long)y * Wq);
-    const float* row = img + (long long)y * W;
+    const float* row = img + (long long)(y_first + y) * W;
     const int xb = 4 * q - pad;
     __half h1[11], h2[11];
 #pragma unroll
@@ -390,7 +391,7 @@ map_h_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant_
                         mbar_arrive_expect_tx(&img_full[s], slot_bytes);
                         uint8_t* slot = img_ring + (size_t)s * slot_bytes;
                         // dead tiles (past the end, cluster padding) read far outside the frame: all zeros
-                        const int yy = live ? y0 - p.half + p.a_first + st : -4 * p.k - 8;
+                        const int yy = live ? y0 - p.half + p.a_first + st - p.plane_row0 : -4 * p.k - 8;
                         for (int pt = 0; pt < n_bops; ++pt)
                             for (int bx = 0; bx < p.n_box; ++bx)
                                 tma_load_3d(slot + (size_t)pt * copy_bytes + (size_t)bx * p.bw_q * 16, &map_img, &img_full[s],
@@ -760,7 +761,15 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
     const int n_parts = x3 ? 2 : 1;
     const int Wq = (W - 1 + prm.pad) / 4 + 1;
     const int n_maps = 4 * n_parts;
-    const size_t plane_bytes = (size_t)H * Wq * 16;
+    // frame rows the band's windows read: output row y uses rows [y - half + a_first, y - half + a_first + n_rows]
+    // (the +1: rows are computed in pairs), zero outside the frame.  Only those rows are expanded -- a row band of a
+    // large frame (image-tile sharding, ZPs.mirror_map) no longer pays for the whole frame (0.1 ms at 4096^2).
+    const int first_row = (row0 & ~1) - prm.half + prm.a_first;
+    const int last_row = ((row0 + rows - 1) | 1) - prm.half + prm.a_first + prm.n_rows;
+    prm.plane_row0 = first_row < 0 ? 0 : first_row;
+    const int plane_end = last_row + 1 > H ? H : last_row + 1;
+    const int plane_rows = plane_end > prm.plane_row0 ? plane_end - prm.plane_row0 : 1;
+    const size_t plane_bytes = (size_t)plane_rows * Wq * 16;
     uint8_t* scratch = nullptr;
     ZB_CUDA(cudaMallocAsync(&scratch, 256 + (size_t)n_maps * plane_bytes, s));
     unsigned int* d_bits = reinterpret_cast<unsigned int*>(scratch);
@@ -774,9 +783,9 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
         const int blocks = (int)(ceil_div(n, 256 * 8) < 4 * p->sm_count ? ceil_div(n, 256 * 8) : 4 * p->sm_count);
         map_absmax_kernel<<<blocks, 256, 0, s>>>(d_img, n, d_bits);
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        const long long units = (long long)H * Wq;
-        map_prepare_kernel<<<(unsigned)ceil_div(units, 128), 128, 0, s>>>(d_img, H, W, Wq, prm.pad, n_parts, d_bits, p->inv_area,
-                                                                           planes, d_scale);
+        const long long units = (long long)plane_rows * Wq;
+        map_prepare_kernel<<<(unsigned)ceil_div(units, 128), 128, 0, s>>>(d_img, prm.plane_row0, plane_rows, W, Wq, prm.pad, n_parts,
+                                                                           d_bits, p->inv_area, planes, d_scale);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     // 3-D TMA descriptor [plane][row][4-byte words], box = 4*bw_q words x 1 row x 1 plane, no swizzle, zero fill outside
@@ -784,7 +793,7 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
     {
         auto enc = get_encode();
         if (!enc) { cudaFreeAsync(scratch, s); set_error("cuTensorMapEncodeTiled is not available"); return ZB200_ECUDA; }
-        cuuint64_t dims[3] = {(cuuint64_t)Wq * 4, (cuuint64_t)H, (cuuint64_t)n_maps};
+        cuuint64_t dims[3] = {(cuuint64_t)Wq * 4, (cuuint64_t)plane_rows, (cuuint64_t)n_maps};
         cuuint64_t strides[2] = {(cuuint64_t)Wq * 16, (cuuint64_t)plane_bytes};
         cuuint32_t box[3] = {(cuuint32_t)prm.bw_q * 4, 1, 1};
         cuuint32_t estr[3] = {1, 1, 1};

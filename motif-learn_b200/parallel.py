@@ -239,3 +239,38 @@ def push_score_bands(arr: PeerArray, band, row0: int, height: int, stream=None):
     for r in range(arr.world):
         _lib.check(lib.zb200_peer_copy_2d(arr.row_ptr(r, row0), height * width * 4, int(band.data_ptr()), rows * width * 4,
                                           rows * width * 4, n_f, st), "peer_copy_2d")
+
+
+_side_streams: dict = {}
+
+
+def symmetry_map_allgather(zps, image, n_folds, arr: PeerArray, row0: int, rows: int, height: int, n_sub: int = 4,
+                           p=2, m_unselect=None):
+    """This rank's row band ``[row0, row0 + rows)`` of the fused symmetry map of one frame, computed in ``n_sub``
+    sub-bands whose scores are forwarded to every rank's copy of the ``(F, H, W)`` map (``arr``: a PeerArray of
+    ``F*H`` rows) by the copy engines WHILE the next sub-band is being computed -- only the last sub-band's copies are
+    exposed.  Sub-bands start on even rows (the map kernel pairs rows by absolute parity), so the result is the
+    single-call map bit for bit.  Call ``arr.begin()`` before and ``arr.fence()`` after."""
+    import torch
+    dev = torch.cuda.current_device()
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    n_sub = max(1, min(int(n_sub), max(1, rows // 2)))
+    step = -(-rows // n_sub)
+    step += step & 1
+    keep = []
+    for r in range(row0, row0 + rows, step):
+        n = min(step, row0 + rows - r)
+        band = zps.symmetry_map(image, n_folds, p=p, m_unselect=m_unselect, row0=r, rows=n)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        push_score_bands(arr, band, r, height, stream=side.cuda_stream)
+        band.record_stream(side)
+        keep.append(band)
+    done = torch.cuda.Event()
+    done.record(side)
+    main.wait_event(done)
+    return keep

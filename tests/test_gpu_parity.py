@@ -833,6 +833,12 @@ def _nccl_worker(rank, world, port, out_dir):
         arr.fence()
         torch.cuda.synchronize()
         ok = ok and bool(torch.equal(arr.local.view(2, 200, 160), full))
+        arr.local.zero_()
+        arr.begin()
+        par.symmetry_map_allgather(z, img, [2, 3], arr, r0, rr, 200, n_sub=3)      # sub-bands overlapped with the copies
+        arr.fence()
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(arr.local.view(2, 200, 160), full))
         arr.close()
         torch.save({"ok": ok, "n": int(feats.shape[0])}, os.path.join(out_dir, f"r{rank}.pt"))
     finally:
