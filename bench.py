@@ -575,7 +575,10 @@ def e2e_patches(ctx, zp, n_modes):
         pts_list.append(clear_border(q, tile.shape, PATCH))
     res = zp_host.transform_peaks_batch(frames[:4], pts_list[:4])           # warm-up: every staging slot, pool threads
     ref = zo.project_patches(zo.extract_patches(frames[1], pts_list[1][:512], PATCH).astype(np.float64), zp.polynomials)
-    fp32_close(res[1].data[:512], ref, "e2e frame route")
+    if args.precision == "tf32":                                            # fast mode: stated bound 1e-3 * max
+        assert np.abs(res[1].data[:512] - ref).max() <= 1e-3 * np.abs(ref).max(), "parity FAILED for the e2e frame route (tf32)"
+    else:
+        fp32_close(res[1].data[:512], ref, "e2e frame route")
     steps = max(2, min(args.steps, 5))
     n_patches = sum(len(q) for q in pts_list)
     result = np.zeros((n_patches, n_modes))                                 # a frame loop keeps ONE result buffer (out=)

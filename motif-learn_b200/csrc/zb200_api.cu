@@ -47,6 +47,7 @@ const Knobs& knobs() {
         v.tc_bstages = knob("ZB200_TC_BSTAGES", 1, 4, 0);
         v.tc_stages = knob("ZB200_TC_STAGES", 1, 8, 0);
         v.tc_accbufs = knob("ZB200_TC_ACCBUFS", 1, 2, 0);
+        v.tc_split2 = knob("ZB200_TC_SPLIT2", 0, 1, -1);
         v.map_gskip = knob("ZB200_MAP_GSKIP", 0, 1, -1);
         v.map_bstages = knob("ZB200_MAP_BSTAGES", 2, 8, 0);
         v.map_slots = knob("ZB200_MAP_SLOTS", 2, 16, 0);
@@ -199,12 +200,15 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
     } while (0)
 
     {
-        // keep stream-ordered scratch (score tables, operand planes of the dense map) cached in the
-        // default pool across synchronisation points instead of returning it to the driver
+        // keep stream-ordered scratch (score tables, operand planes of the dense map, peak-detection keys) cached in
+        // the default pool across synchronisation points instead of returning it to the driver -- up to 2 GiB (the
+        // working sets above are 0.4-0.6 GB at 4096^2); anything beyond goes back at the next synchronisation so the
+        // host application's own allocator is not starved.  An already larger threshold is left alone.
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess) {
-            uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            uint64_t have = 0, keep = 2ull << 30;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &have) == cudaSuccess && have < keep)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
         cudaGetLastError();
     }

@@ -452,13 +452,19 @@ project_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #define ZB200_TC3_PROF ZB200_DEBUG_HOOKS
 #endif
 constexpr int kRegsCtl = 48, kRegsEpi = 176, kRegsSplit = 112;     // (48 + 2*176 + 112) * 128 = 64 Ki
+constexpr int kRegsSplit2 = 96, kRegsEpi2 = 248;                   // kSplit2: (48 + 2*96 + 248) * 128 = 61 Ki
+constexpr int kCC2 = 6;                                            // kSplit2: 6 x 16 accumulator columns per sub-tile
 constexpr int kMaxColChunks = 8;     // 8 x 16 = 128 running sums per epilogue thread
 
 // kF16 = the fp16-split arithmetic (ZB200_PREC_F16X3): x = x1 + x2, V = b1 + b2 in fp16, three kind::f16 MMAs
 // (x1.b1, x2.b1, x1.b2) per 16 taps, all with A in TMEM -- 6 MMAs per 32-tap k-block and sub-tile instead of 8, no
 // MMA reads X from shared memory (the splitter releases the X stage as soon as it holds the row in registers), and
 // the basis stream is ONE 128-byte row per k-block ([32 x b1 | 32 x b2]) instead of two ([Bhi] + [Bcb]).
-template <int kOut, bool kPair, bool kF16>
+// kSplit2 = the layout for the metric shape (two 128-patch sub-tiles, <= 96 operand rows, TMA-fed X): TWO splitter
+// warpgroups (warpgroup g splits sub-tile g: one row per thread and k-block instead of two, so the serial chain
+// LDS -> split -> tcgen05.st -> arrive that paces the kernel under the power cap is half as long) and ONE epilogue
+// warpgroup that drains both accumulators (2 x 96 running sums per thread, 248 registers).
+template <int kOut, bool kPair, bool kF16, bool kSplit2>
 __global__ void __launch_bounds__(512, 1)
 project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_bhi,
                    const __grid_constant__ CUtensorMap map_blo, const Params p) {
@@ -508,20 +514,20 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kF16 ? 4 : 1);          // f16x3: the four splitter warps release the X stage
+            mbar_init(&empty[s], kF16 ? (kSplit2 ? 8 : 4) : 1);   // f16x3: the splitter warps release the X stage
         }
         // pair mode: the leader's MMA thread is the only committer (multicast to both CTAs) and collects the
         // splitter / epilogue arrivals of both CTAs
         for (int b = 0; b < 4; ++b) {
             mbar_init(&bfull[b], 1);
             mbar_init(&bempty[b], kPair ? 1 : p.cluster);
-            mbar_init(&lo_full[b], kPair ? 8 : 4);
+            mbar_init(&lo_full[b], (kPair ? 8 : 4) * (kSplit2 ? 2 : 1));
             mbar_init(&lo_empty[b], 1);
             mbar_init(&bpeer[b], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], (p.epi_solo ? 4 : 8) * (kPair ? 2 : 1));
+            mbar_init(&acc_empty[b], ((p.epi_solo || kSplit2) ? 4 : 8) * (kPair ? 2 : 1));
         }
         fence_barrier_init();
     }
@@ -763,7 +769,162 @@ project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             __syncwarp();
         } else if (warp == kWarpAlloc && p.n_peers) {
             // ===================== K5: forward finished tiles to the peer GPUs =====================
-            pusher_loop(p, out_done, p.epi_solo ? 4 : 8, my_tiles, lane, smem + p.push_off);
+            pusher_loop(p, out_done, (p.epi_solo || kSplit2) ? 4 : 8, my_tiles, lane, smem + p.push_off);
+        }
+    } else if (kSplit2 && wg <= 1) {
+        // ===================== splitter, one sub-tile per warpgroup =====================
+        reg_dec<kRegsSplit2>();
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                              // row inside this warpgroup's 128-row sub-tile
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t x_ring_u32 = smem_u32(smem);
+        const uint32_t swz = (uint32_t)(r & 7) << 4;
+        const float xsc = p.x_scale;
+        int s = 0;
+        uint32_t ph = 0, it = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+                const int lb = (int)(it & lo_mask);
+                const uint32_t lo_ph = (it >> lo_shift) & 1u;
+                mbar_wait(&full[s], ph);
+                const uint32_t rowp = x_ring_u32 + (uint32_t)s * x_bytes + (uint32_t)(wg * kTileRows + r) * 128u;
+                float4 x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(x[c].x), "=f"(x[c].y), "=f"(x[c].z), "=f"(x[c].w)
+                                 : "r"(rowp + (((uint32_t)c << 4) ^ swz)));
+                mbar_wait(&lo_empty[lb], lo_ph ^ 1u);
+                tc_fence_after();
+                uint32_t lo[32];
+                auto pack_h = [](float hi_half, float lo_half) {
+                    uint32_t v;
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(hi_half), "f"(lo_half));
+                    return v;
+                };
+                auto pack_b = [](float hi_half, float lo_half) {
+                    uint32_t v;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(hi_half), "f"(lo_half));
+                    return v;
+                };
+                // (a - trunc(a), b - trunc(b)) as one packed add; trunc = the top 11 significand bits
+                auto residual2 = [](float a, float b, uint32_t ta, uint32_t tb, float& ra, float& rb) {
+                    uint64_t va, vb, vd;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(va) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(vb) : "r"(ta ^ 0x80000000u), "r"(tb ^ 0x80000000u));
+                    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(vd) : "l"(va), "l"(vb));
+                    uint32_t l0, l1;
+                    asm("mov.b64 {%0, %1}, %2;" : "=r"(l0), "=r"(l1) : "l"(vd));
+                    ra = __uint_as_float(l0);
+                    rb = __uint_as_float(l1);
+                };
+                if constexpr (kF16) {
+                    // columns [0,16): x1 pairs, [16,32): x2 pairs (see split_row_h of the one-warpgroup splitter)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float a = (h ? x[c].z : x[c].x) * xsc, b = (h ? x[c].w : x[c].y) * xsc;
+                            const uint32_t ta = __float_as_uint(a) & 0xFFFFE000u, tb = __float_as_uint(b) & 0xFFFFE000u;
+                            float ra, rb;
+                            residual2(a, b, ta, tb, ra, rb);
+                            lo[2 * c + h] = pack_h(__uint_as_float(tb), __uint_as_float(ta));
+                            lo[16 + 2 * c + h] = pack_h(rb, ra);
+                        }
+                    }
+                } else {
+                    // per 8 taps: columns 0..3 Xlo pairs, 4..7 Xhi pairs (bf16), like split8
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4& v = x[2 * c8 + (j >> 1)];
+                            const float a = (j & 1) ? v.z : v.x, b = (j & 1) ? v.w : v.y;
+                            const uint32_t ta = __float_as_uint(a) & 0xFFFFE000u, tb = __float_as_uint(b) & 0xFFFFE000u;
+                            float ra, rb;
+                            residual2(a, b, ta, tb, ra, rb);
+                            lo[8 * c8 + j] = pack_b(rb, ra);
+                            lo[8 * c8 + 4 + j] = pack_b(b, a);
+                        }
+                    }
+                }
+                tmem_st32(lo_base + lane_addr + (uint32_t)(lb * 2 + wg) * kBlockK, lo);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (kPair && crank != 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&lo_full[lb]), 0));
+                    else mbar_arrive(&lo_full[lb]);
+                    if constexpr (kF16) mbar_arrive(&empty[s]);
+                }
+                if (++s == p.n_stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (kSplit2) {
+        // ===================== epilogue, one warpgroup for both sub-tiles =====================
+        reg_inc<kRegsEpi2>();
+        const int q = warp & 3;
+        const int n_cc = p.n_pad / 16;                            // <= kCC2
+        uint32_t ck = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int tile = blockIdx.x + t * gridDim.x;
+            float sum[2][kCC2][16];
+#pragma unroll
+            for (int sb2 = 0; sb2 < 2; ++sb2)
+#pragma unroll
+                for (int cc = 0; cc < kCC2; ++cc)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) sum[sb2][cc][i] = 0.f;
+            for (int c = 0; c < n_chunks; ++c, ++ck) {
+                const int buf = p.acc_bufs == 2 ? (int)(ck & 1) : 0;
+                mbar_wait(&acc_full[buf], p.acc_bufs == 2 ? ((ck >> 1) & 1u) : (ck & 1u));
+                tc_fence_after();
+#pragma unroll
+                for (int sb2 = 0; sb2 < 2; ++sb2) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sb2) * p.n_pad);
+#pragma unroll
+                    for (int cc = 0; cc < kCC2; ++cc) {
+                        if (cc < n_cc) {
+                            uint32_t v[16];
+                            tmem_ld16(taddr + cc * 16, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) sum[sb2][cc][i] += __uint_as_float(v[i]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (kPair && crank != 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&acc_empty[buf]), 0));
+                    else mbar_arrive(&acc_empty[buf]);
+                }
+            }
+#pragma unroll
+            for (int sb2 = 0; sb2 < 2; ++sb2) {
+                const long long row = (long long)tile * 2 * kTileRows + sb2 * kTileRows + q * 32 + lane;
+                if (row < p.n_patches) {
+                    ScoreAcc sc;
+                    if constexpr (kOut == kOutScores) sc.clear();
+#pragma unroll
+                    for (int cc = 0; cc < kCC2; ++cc) {
+                        if (cc < n_cc) {
+                            uint32_t v[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                v[i] = __float_as_uint(kF16 ? sum[sb2][cc][i] * p.out_scale : sum[sb2][cc][i]);
+                            epilogue_chunk<kOut>(p, row, cc * 16, v, sc);
+                        }
+                    }
+                    if constexpr (kOut == kOutScores) finish_scores(p, row, sc);
+                }
+            }
+            if (p.n_peers) {
+                __threadfence();
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) atomicAdd(out_done, 1u);
+            }
         }
     } else if (wg == 0) {
         // ===================== splitter =====================
@@ -1269,6 +1430,9 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     }
     prm.n_tiles = (int)ceil_div(n, (int64_t)sub * kTileRows);
 
+    // two splitter warpgroups + one epilogue warpgroup: two 128-patch sub-tiles, <= 96 operand rows, TMA-fed X, CTA pairs
+    bool split2 = x3 && prm.pair && sub == 2 && prm.n_pad <= 16 * kCC2 && !gsrc;
+    if (kn.tc_split2 == 0) split2 = false;
     CUtensorMap map_x;
     int rc = gsrc ? encode_2d(&map_x, op.hi, (uint64_t)p->k_pad, (uint64_t)op.rows_pad, (uint64_t)p->k_pad * 4, 8)   // unused
                   : encode_2d(&map_x, d_patches, (uint64_t)p->kk, (uint64_t)n, (uint64_t)p->kk * 4, (uint32_t)(sub * kTileRows));
@@ -1297,26 +1461,36 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
                             : (out_kind == ZB200_OUT_ABS ? kOutAbs : (out_kind == ZB200_OUT_ABS_PHASE ? kOutAbsPhase : kOutPlain));
 #define ZB_TC_LAUNCH(KOUT)                                                                                            \
     if (kout == KOUT) {                                                                                               \
-        if (h3 && prm.pair) {                                                                                         \
-            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        if (split2 && h3) {                                                                                           \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                                 \
             cfg.blockDim = dim3(512);                                                                                 \
-            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true, true>, map_x, op.tmap_hb[lg], op.tmap_hb[lg], prm)); \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true, true, true>, map_x, op.tmap_hb[lg], op.tmap_hb[lg], prm)); \
+        } else if (split2) {                                                                                          \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                                 \
+            cfg.blockDim = dim3(512);                                                                                 \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true, false, true>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
+        } else if (h3 && prm.pair) {                                                                                  \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                                 \
+            cfg.blockDim = dim3(512);                                                                                 \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true, true, false>, map_x, op.tmap_hb[lg], op.tmap_hb[lg], prm)); \
         } else if (h3) {                                                                                              \
-            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                                 \
             cfg.blockDim = dim3(512);                                                                                 \
-            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, false, true>, map_x, op.tmap_hb[lg], op.tmap_hb[lg], prm)); \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, false, true, false>, map_x, op.tmap_hb[lg], op.tmap_hb[lg], prm)); \
         } else if (x3 && prm.pair) {                                                                                  \
-            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                                 \
             cfg.blockDim = dim3(512);                                                                                 \
-            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true, false>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, true, false, false>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
         } else if (x3) {                                                                                              \
-            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            ZB_CUDA(cudaFuncSetAttribute(project_tc3_kernel<KOUT, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                                 \
             cfg.blockDim = dim3(512);                                                                                 \
-            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, false, false>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
+            ZB_CUDA(cudaLaunchKernelEx(&cfg, project_tc3_kernel<KOUT, false, false, false>, map_x, op.tmap_hi[lg], op.tmap_cb[lg], prm)); \
         } else {                                                                                                      \
             ZB_CUDA(cudaFuncSetAttribute(project_tc_kernel<KOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                          (int)smem));                                                                 \

@@ -68,6 +68,20 @@ def _plan_for(n_max: int, size: int):
     return plan
 
 
+def release_plans(device=None) -> int:
+    """Destroy the cached plans (fp64 basis, packed operands, host staging buffers: a few MB for n_max=12 up to
+    1-2 GB once the host frame route has run) of ``device`` (all devices when None); returns how many were freed.
+    Plans are rebuilt on demand.  No call that uses a plan may be in flight."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    freed = 0
+    with _plans_lock:
+        for key in [k for k in _plans if device is None or k[2] == device]:
+            lib.zb200_plan_destroy(_plans.pop(key))
+            freed += 1
+    return freed
+
+
 def _mode_table(n_max: int):
     lib = _lib.load()
     count = lib.zb200_num_modes(int(n_max))

@@ -1031,3 +1031,12 @@ def test_mirror_map_in_row_bands(api, golden, torch):
     host = z.mirror_map(img.astype(np.float32))
     assert isinstance(host, np.ndarray) and host.shape == img.shape
     np.testing.assert_allclose(host[g["map_ys"], g["map_xs"]], g["map_mirror_pts"], rtol=0, atol=2e-5)
+
+
+def test_release_plans_rebuilds_on_demand(api):
+    z = api.ZPs(6, 16)
+    a = z.transform(np.ones((3, 16, 16), dtype=np.float32)).data
+    assert api.release_plans() >= 1
+    assert api.release_plans() == 0
+    b = api.ZPs(6, 16).transform(np.ones((3, 16, 16), dtype=np.float32)).data       # the plan is rebuilt
+    np.testing.assert_array_equal(a, b)
