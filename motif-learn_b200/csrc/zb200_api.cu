@@ -48,6 +48,7 @@ const Knobs& knobs() {
         v.tc_stages = knob("ZB200_TC_STAGES", 1, 8, 0);
         v.tc_accbufs = knob("ZB200_TC_ACCBUFS", 1, 2, 0);
         v.tc_split2 = knob("ZB200_TC_SPLIT2", 0, 1, -1);
+        v.tc_fold = knob("ZB200_TC_FOLD", 0, 1, -1);
         v.map_gskip = knob("ZB200_MAP_GSKIP", 0, 1, -1);
         v.map_bstages = knob("ZB200_MAP_BSTAGES", 2, 8, 0);
         v.map_slots = knob("ZB200_MAP_SLOTS", 2, 16, 0);
@@ -141,6 +142,7 @@ extern "C" void zb200_plan_destroy(zb200_plan* p) {
     free_operand(p->real);
     free_operand(p->cplx);
     free_map_half_operand(p);
+    free_fold_operand(p);
     free_host_pipe(p);
     delete p;
 }
@@ -237,6 +239,7 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
     ZB_PLAN_CUDA(cudaDeviceSynchronize());
     ZB_PLAN_TRY(init_tensor_maps(p));
     ZB_PLAN_TRY(init_map_half_operand(p));
+    ZB_PLAN_TRY(init_fold_operand(p));
     *out_plan = p;
     return ZB200_OK;
 }

@@ -54,6 +54,7 @@ struct Knobs {
     int tc_bstages = 0;    // ZB200_TC_BSTAGES 1..4
     int tc_stages = 0;     // ZB200_TC_STAGES  1..8
     int tc_accbufs = 0;    // ZB200_TC_ACCBUFS 1|2
+    int tc_fold = -1;      // ZB200_TC_FOLD    0|1   mirror-folded projection when the plan has a folded operand
     int tc_split2 = -1;    // ZB200_TC_SPLIT2  0|1   two splitter warpgroups + one epilogue warpgroup (metric shape)
     int tc_debug = 0;      // ZB200_TC_DEBUG   bit mask, needs a -DZB200_DEBUG_HOOKS=1 build (results are wrong when set)
     int map_gskip = -1;    // ZB200_MAP_GSKIP  0|1
@@ -122,6 +123,22 @@ struct MapHalf {
     CUtensorMap tmap_b2[2];
 };
 
+// mirror-folded fp16-split operand of the patch projection (zb200_project_fold.cu): accumulator columns grouped in the
+// four mirror-parity classes, K = the window's upper-left quadrant
+struct FoldOperand {
+    bool ready = false;
+    int cfg = -1;                // compiled class-width configuration
+    int cols = 0;                // accumulator columns = operand rows (all four classes, padded)
+    int nj = 0;                  // 32-tap boxes per half window row
+    int n_sb = 0;                // super-blocks (32 folded taps) in the quadrant
+    int sb_first = 0, sb_count = 0;   // those with taps inside the unit disk
+    uint32_t* fb = nullptr;      // [cols][n_sb * 32] words: per super-block 32 x half b1 | 32 x half b2; rows [rank][class][slot]
+    unsigned char* d_umask = nullptr;   // per super-block: bit h = 16-tap unit h is active
+    short* d_col_real = nullptr;        // [cols] real mode of an accumulator column (-1 = padding)
+    short* d_slot_cplx = nullptr;       // [2][80] complex mode of a slot of the class pairs A (m even) / B (m odd)
+    CUtensorMap tmap;
+};
+
 struct HostPipe;
 }  // namespace zb200
 
@@ -147,6 +164,7 @@ struct zb200_plan {
     zb200::Operand cplx;          // complex-interleaved row order
     zb200::MapHalf map_half[4];   // fp16-split dense-map operands (real row order), <= 128 padded modes each
     int n_map_parts = 0;
+    zb200::FoldOperand fold;      // mirror-folded projection operand (window side % 64 == 0, n_max <= 20)
     // staging set of the host-buffer entry points (zb200_host.cu); calls on one plan take turns under host_mu
     std::mutex host_mu;
     zb200::HostPipe* host = nullptr;
@@ -189,6 +207,12 @@ int project_tc(const zb200_plan* plan, const float* d_patches, int64_t n, int pr
                cudaStream_t s, const GatherSource* gather = nullptr, const PeerTargets* peers = nullptr,
                double value_max = 0.0);
 bool tc_supported(const zb200_plan* plan, int precision, bool complex_order);
+// mirror-folded fp16-split projection (value_max required; REAL / COMPLEX / ABS / ABS_PHASE outputs, peer push)
+int init_fold_operand(zb200_plan* plan);
+void free_fold_operand(zb200_plan* plan);
+bool fold_supported(const zb200_plan* plan);
+int project_fold(const zb200_plan* plan, const float* d_patches, int64_t n, int out_kind, void* d_out, void* d_out2,
+                 cudaStream_t s, const PeerTargets* peers, double value_max);
 
 int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,
              float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds,
