@@ -71,6 +71,11 @@ struct Params {
     uint32_t push_off;
     float* peer_out[kMaxPeers];
     float x_scale, out_scale;
+    // per class, for the issuing thread (read through the constant bank in a rolled loop: with the class constants
+    // unrolled into the instruction stream ptxas ran out of UNIFORM registers as soon as the widths differed)
+    uint32_t cls_idesc[4];    // instruction descriptor: kind::f16, M = 256, N = class width
+    uint32_t cls_brow[4];     // (byte offset of the class's rows inside a B stage) >> 4
+    uint32_t cls_col[4];      // first accumulator column
 };
 
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
@@ -330,12 +335,12 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                                 mbar_wait_cluster(&lo_full[u], uph);
                                 tc_fence_after();
                                 const uint32_t a0 = lo_base + (uint32_t)u * kUnitCols;
-#pragma unroll
+#pragma unroll 1
                                 for (int cl = 0; cl < 4; ++cl) {
-                                    const uint32_t idesc = make_idesc_f16(cls_w(kCfg, cl), 256);
-                                    const uint32_t brow = bl + (uint32_t)((cls_off(kCfg, cl) / 2) * 128 >> 4);
+                                    const uint32_t idesc = p.cls_idesc[cl];
+                                    const uint32_t brow = bl + p.cls_brow[cl];
                                     const uint64_t b1d = desc_from_lo(brow + 2 * h), b2d = desc_from_lo(brow + 4 + 2 * h);
-                                    const uint32_t d = d0 + cls_off(kCfg, cl), a1 = a0 + 16 * cl, a2 = a1 + 8;
+                                    const uint32_t d = d0 + p.cls_col[cl], a1 = a0 + 16 * cl, a2 = a1 + 8;
                                     umma_bf16_ts_2(d, a1, b1d, idesc, acc_run);
                                     umma_bf16_ts_2(d, a2, b1d, idesc, 1u);
                                     umma_bf16_ts_2(d, a1, b2d, idesc, 1u);
@@ -539,7 +544,7 @@ int init_fold_operand(zb200_plan* p) {
         for (int cl = 0; cl < 4; ++cl) ok = ok && count[cl] <= cls_w(c, cl);
         if (ok) cfg = c;
     }
-    if (cfg != 0) return ZB200_OK;       // TODO cfg 1
+    if (cfg < 0) return ZB200_OK;
     const int cols = cfg_cols(cfg);
     f.cfg = cfg;
     f.cols = cols;
@@ -671,6 +676,12 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
     prm.out2 = static_cast<float*>(d_out2);
     prm.col_real = f.d_col_real;
     prm.slot_cplx = f.d_slot_cplx;
+    for (int cl = 0; cl < 4; ++cl) {
+        const int w = cls_w(f.cfg, cl);
+        prm.cls_idesc[cl] = (1u << 4) | ((uint32_t)(w >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // make_idesc_f16(w, 256)
+        prm.cls_brow[cl] = (uint32_t)((cls_off(f.cfg, cl) / 2) * 128) >> 4;
+        prm.cls_col[cl] = (uint32_t)cls_off(f.cfg, cl);
+    }
     {
         int e = 0;
         frexp(value_max, &e);                               // |x| < 2^e: |x| 2^(12-e) <= 2^12, the four-term fold <= 2^14
@@ -738,9 +749,9 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
     ZB_FOLD_LAUNCH(kOutPlain, 0)
     ZB_FOLD_LAUNCH(kOutAbs, 0)
     ZB_FOLD_LAUNCH(kOutAbsPhase, 0)
-    //ZB_FOLD_LAUNCH(kOutPlain, 1)
-    //ZB_FOLD_LAUNCH(kOutAbs, 1)
-    //ZB_FOLD_LAUNCH(kOutAbsPhase, 1)
+    ZB_FOLD_LAUNCH(kOutPlain, 1)
+    ZB_FOLD_LAUNCH(kOutAbs, 1)
+    ZB_FOLD_LAUNCH(kOutAbsPhase, 1)
 #undef ZB_FOLD_LAUNCH
     ZB_LAUNCHED();
     return ZB200_OK;
