@@ -88,6 +88,10 @@ int         zb200_plan_supports(const zb200_plan* plan, int precision, int out_k
 /* Same question for the dense map (K4): the tf32 tcgen05 map needs a window that is a multiple of 8, the
  * fp16-split map (ZB200_PREC_F16 / F16X3) any window up to 128 px; both need <= 128 padded modes. */
 int         zb200_plan_supports_map(const zb200_plan* plan, int precision);
+/* 1 if ZB200_PREC_F16X3 projections of this plan need no value_max: windows whose side is a multiple of 64 pixels
+ * (n_max <= 20) run the mirror-folded kernel, which can take its input scale from a sample of the stack and is backed
+ * by the range-free TF32X3 kernel when an unsampled value overflows (see zb200_project_patches_ranged_f32). */
+int         zb200_plan_supports_autorange(const zb200_plan* plan);
 
 /* ---- K1: basis (replaces ZPs.__init__/_generate_polynomials, _zps.py:23-90) - */
 /* (n_max+1)(n_max+2)/2, or negative on bad n_max. */
@@ -121,7 +125,14 @@ int zb200_project_patches_f32(const zb200_plan* plan, const float* d_patches, in
 /* The same projection in the fp16-split arithmetic (ZB200_PREC_F16X3: x = x1 + x2, V = b1 + b2 in fp16, three
  * tcgen05 kind::f16 passes -- fp32-grade like TF32X3 with a quarter fewer tensor-core instructions and half the basis
  * traffic).  fp16 has a narrow exponent range: value_max must bound |patch values|; inputs are scaled by the power
- * of two that brings value_max to <= 2^14.  Values beyond 4 x value_max overflow to inf/NaN in the output. */
+ * of two that brings value_max to <= 2^14.  Values beyond 4 x value_max overflow to inf/NaN in the output.
+ * Windows whose side is a multiple of 64 pixels (n_max <= 20) run the MIRROR-FOLDED kernel: the four mirror images of
+ * a quadrant pixel are combined first (every Zernike plane is even or odd under the two mirrors of the grid), so each
+ * of the four parity classes is a GEMM over a quarter of the taps and its own modes only.  For those plans
+ * (zb200_plan_supports_autorange) value_max = 0 asks for AUTO-RANGE: the scale comes from the largest |x| of up to
+ * 1024 evenly spread patches, and if an unsampled value overflows (a result is not finite) the range-free TF32X3
+ * kernel enqueued behind recomputes the stack -- same stream, no host synchronisation.  zb200_project_patches_f32
+ * with ZB200_PREC_F16X3 is the same auto-range call. */
 int zb200_project_patches_ranged_f32(const zb200_plan* plan, const float* d_patches, int64_t n_patches, double value_max,
                                      int out_kind, void* d_out, void* d_out2, void* stream);
 /* Fused n-fold scores of patches (rot_maps on real moments, _zmoments.py:420-462):

@@ -260,6 +260,8 @@ extern "C" int zb200_plan_supports(const zb200_plan* p, int precision, int out_k
     return 0;
 }
 
+extern "C" int zb200_plan_supports_autorange(const zb200_plan* p) { return p && fold_supported(p) && knobs().tc_fold != 0 ? 1 : 0; }
+
 extern "C" int zb200_plan_supports_map(const zb200_plan* p, int precision) {
     if (!p) return 0;
     if (precision == ZB200_PREC_FP32) return 1;
@@ -304,7 +306,11 @@ extern "C" int zb200_project_patches_ranged_f32(const zb200_plan* p, const float
     ZB_CHECK_ARG(p, "project_ranged: plan is null");
     ZB_CHECK_ARG(n >= 0, "project_ranged: negative patch count");
     ZB_CHECK_ARG(out_kind >= ZB200_OUT_REAL && out_kind <= ZB200_OUT_ABS_PHASE, "project_ranged: bad out_kind %d", out_kind);
-    ZB_CHECK_ARG(value_max > 0.0 && value_max < 1e30, "project_ranged: value_max must be a positive finite bound of |x|");
+    ZB_CHECK_ARG(value_max >= 0.0 && value_max < 1e30, "project_ranged: value_max must be a positive finite bound of |x| (0 = auto-range)");
+    if (value_max == 0.0 && !fold_supported(p)) {
+        set_error("project_ranged: auto-range (value_max = 0) needs the mirror-folded kernel (window side a multiple of 64, n_max <= 20)");
+        return ZB200_EUNSUP;
+    }
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG(d_patches && d_out, "project_ranged: null device pointer");
     ZB_CHECK_ARG(out_kind != ZB200_OUT_ABS_PHASE || d_out2, "project_ranged: ABS_PHASE needs d_out2");

@@ -205,14 +205,14 @@ struct PeerTargets {
 int project_tc(const zb200_plan* plan, const float* d_patches, int64_t n, int precision, int out_kind,
                void* d_out, void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind,
                cudaStream_t s, const GatherSource* gather = nullptr, const PeerTargets* peers = nullptr,
-               double value_max = 0.0);
+               double value_max = 0.0, const unsigned* run_if = nullptr);
 bool tc_supported(const zb200_plan* plan, int precision, bool complex_order);
 // mirror-folded fp16-split projection (value_max required; REAL / COMPLEX / ABS / ABS_PHASE outputs, peer push)
 int init_fold_operand(zb200_plan* plan);
 void free_fold_operand(zb200_plan* plan);
 bool fold_supported(const zb200_plan* plan);
 int project_fold(const zb200_plan* plan, const float* d_patches, int64_t n, int out_kind, void* d_out, void* d_out2,
-                 cudaStream_t s, const PeerTargets* peers, double value_max);
+                 cudaStream_t s, const PeerTargets* peers, double value_max, uint32_t* d_aux = nullptr);
 
 int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,
              float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds,

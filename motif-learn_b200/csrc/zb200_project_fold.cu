@@ -71,6 +71,12 @@ struct Params {
     uint32_t push_off;
     float* peer_out[kMaxPeers];
     float x_scale, out_scale;
+    // auto-range (no value_max from the caller): absmax = bits of the largest sampled |x| (range_sample_kernel); the
+    // kernel derives the power-of-two scale from it; flag is raised when a result is not finite (an unsampled value
+    // beyond 8x the sampled maximum overflowed fp16) -- the caller then recomputes with the range-free kernel
+    const uint32_t* absmax;
+    unsigned* flag;
+    float inv_area;
     // per class, for the issuing thread (read through the constant bank in a rolled loop: with the class constants
     // unrolled into the instruction stream ptxas ran out of UNIFORM registers as soon as the widths differed)
     uint32_t cls_idesc[4];    // instruction descriptor: kind::f16, M = 256, N = class width
@@ -114,6 +120,29 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
+// power-of-two input scale for |x| <= bound (bits of a non-negative float): |x| 2^sh <= 2^11, so the four-term fold
+// stays below 2^13 and an unsampled value up to 8x the bound still converts to a finite fp16
+__device__ __forceinline__ int auto_shift(uint32_t bound_bits) {
+    const int e = (int)((bound_bits >> 23) & 255u) - 126;          // bound < 2^e  (frexp exponent)
+    const int sh = bound_bits == 0u ? 0 : 11 - e;
+    return sh < -100 ? -100 : (sh > 100 ? 100 : sh);
+}
+__device__ __forceinline__ float pow2i(int sh) { return __uint_as_float((uint32_t)(127 + sh) << 23); }
+
+// largest |x| of `n_sample` patches spread evenly over the stack (one block per sampled patch)
+__global__ void range_sample_kernel(const float* __restrict__ x, long long n, int kk, int n_sample, uint32_t* __restrict__ absmax) {
+    const long long patch = (long long)blockIdx.x * n / n_sample;
+    const float4* src = reinterpret_cast<const float4*>(x + patch * (long long)kk);
+    uint32_t m = 0;
+    for (int i = threadIdx.x; i < kk / 4; i += blockDim.x) {
+        const float4 v = __ldg(src + i);
+        m = max(max(m, __float_as_uint(v.x) & 0x7FFFFFFFu), max(__float_as_uint(v.y) & 0x7FFFFFFFu,
+                max(__float_as_uint(v.z) & 0x7FFFFFFFu, __float_as_uint(v.w) & 0x7FFFFFFFu)));
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(absmax, m);       // non-negative floats (and NaNs above them) order like their bits
+}
+
 // ---- epilogue of one class pair (X_re, X_im): kRe / kIm = their widths in 16-column chunks ----------------------
 // The thread owns one patch: running fp32 sums of the K chunks (round-to-nearest adds; the tensor core's own fp32
 // accumulation truncates), then the store path of kOut.  Columns are class-ordered, so real moments go out through
@@ -121,7 +150,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 template <int kOut, int kRe, int kIm>
 __device__ __forceinline__ void epilogue_pair(const Params& p, uint32_t tmem_base, int n_cols, int col0, int g, int q, int lane,
                                               bool remote, uint64_t* acc_full, uint64_t* acc_empty, unsigned* out_done,
-                                              int my_tiles, int n_chunks) {
+                                              int my_tiles, int n_chunks, float out_scale) {
     constexpr int kCC = kRe + kIm;
     uint32_t ck = 0;
     for (int t = 0; t < my_tiles; ++t) {
@@ -152,7 +181,15 @@ __device__ __forceinline__ void epilogue_pair(const Params& p, uint32_t tmem_bas
             }
         }
         if (row < p.n_patches) {
-            const float sc = p.out_scale;
+            const float sc = out_scale;
+            if (p.flag) {
+                uint32_t worst = 0;
+#pragma unroll
+                for (int cc = 0; cc < kCC; ++cc)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) worst = max(worst, __float_as_uint(sum[cc][i]) & 0x7FFFFFFFu);
+                if (worst >= 0x7F800000u) atomicOr(p.flag, 1u);
+            }
             if (kOut == kOutPlain && p.out_kind == ZB200_OUT_REAL) {
                 float* dst = p.out + row * (long long)p.row_len;
 #pragma unroll
@@ -251,6 +288,12 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const uint32_t crank = cluster_rank();
     const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;     // lock-step within the pair
     const int n_chunks = (p.sb_count + p.chunk_sb - 1) / p.chunk_sb;
+    float x_scale = p.x_scale, out_scale = p.out_scale;
+    if (p.absmax) {
+        const int sh = auto_shift(__ldg(p.absmax));
+        x_scale = pow2i(sh);
+        out_scale = p.inv_area * pow2i(-sh);
+    }
 
     if (wg == 3) {
         reg_dec<Regs<kCfg>::ctl>();
@@ -368,7 +411,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         const uint32_t swz = (uint32_t)(r & 7) << 4;
         const uint32_t row_u32 = smem_u32(smem) + (uint32_t)r * 128u;
-        const uint64_t sc2 = pk2(p.x_scale, p.x_scale);
+        const uint64_t sc2 = pk2(x_scale, x_scale);
         int s = 0;
         uint32_t ph = 0;
         int u = 0;
@@ -438,10 +481,10 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         else reg_inc<Regs<kCfg>::epi_b>();
         if (g == 0)
             epilogue_pair<kOut, cls_w(kCfg, 0) / 16, cls_w(kCfg, 1) / 16>(p, tmem_base, kCols, cls_off(kCfg, 0), 0, q, lane, crank != 0,
-                                                                          acc_full, acc_empty, out_done, my_tiles, n_chunks);
+                                                                          acc_full, acc_empty, out_done, my_tiles, n_chunks, out_scale);
         else
             epilogue_pair<kOut, cls_w(kCfg, 2) / 16, cls_w(kCfg, 3) / 16>(p, tmem_base, kCols, cls_off(kCfg, 2), 1, q, lane, crank != 0,
-                                                                          acc_full, acc_empty, out_done, my_tiles, n_chunks);
+                                                                          acc_full, acc_empty, out_done, my_tiles, n_chunks, out_scale);
     }
 
     tc_fence_before();
@@ -649,8 +692,11 @@ int init_fold_operand(zb200_plan* p) {
 
 bool fold_supported(const zb200_plan* p) { return p->fold.ready; }
 
+// value_max > 0: the caller's bound of |x|.  value_max <= 0: auto-range -- d_aux (two zeroed 32-bit words owned by the
+// caller: [0] sampled absmax bits, [1] overflow flag) receives the largest |x| of up to 1024 evenly spread patches, the
+// kernel scales by it and raises d_aux[1] if any result is not finite (then every row must be recomputed).
 int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out_kind, void* d_out, void* d_out2,
-                 cudaStream_t s, const PeerTargets* peers, double value_max) {
+                 cudaStream_t s, const PeerTargets* peers, double value_max, uint32_t* d_aux) {
     using namespace fold;
     const FoldOperand& f = p->fold;
     if (!f.ready) {
@@ -659,7 +705,7 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
     }
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG((reinterpret_cast<uintptr_t>(d_patches) & 15) == 0, "project: patch pointer must be 16-byte aligned");
-    ZB_CHECK_ARG(value_max > 0.0, "the folded projection needs an upper bound of |patch values| (value_max > 0)");
+    ZB_CHECK_ARG(value_max > 0.0 || d_aux, "the folded projection needs an upper bound of |patch values| or auto-range scratch");
     ZB_CHECK_ARG(out_kind != ZB200_OUT_COMPLEX || (reinterpret_cast<uintptr_t>(d_out) & 7) == 0,
                  "project: complex output must be 8-byte aligned");
     Params prm{};
@@ -682,7 +728,15 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
         prm.cls_brow[cl] = (uint32_t)((cls_off(f.cfg, cl) / 2) * 128) >> 4;
         prm.cls_col[cl] = (uint32_t)cls_off(f.cfg, cl);
     }
-    {
+    prm.inv_area = (float)p->inv_area;
+    if (!(value_max > 0.0)) {
+        const int n_sample = (int)(n < 1024 ? n : 1024);
+        range_sample_kernel<<<n_sample, 256, 0, s>>>(d_patches, (long long)n, p->kk, n_sample, d_aux);
+        ZB_LAUNCHED();
+        prm.absmax = d_aux;
+        prm.flag = d_aux + 1;
+        prm.x_scale = prm.out_scale = 1.f;
+    } else {
         int e = 0;
         frexp(value_max, &e);                               // |x| < 2^e: |x| 2^(12-e) <= 2^12, the four-term fold <= 2^14
         const int sh = 12 - e < -100 ? -100 : (12 - e > 100 ? 100 : 12 - e);

@@ -96,6 +96,8 @@ struct Params {
     // f16x3 mode: inputs are multiplied by x_scale (a power of two that brings |x| <= 2^14) before the fp16 split,
     // the basis operand holds V (not V/area): results are multiplied by out_scale = 1 / (area * x_scale)
     float x_scale, out_scale;
+    // conditional launch (fallback of the auto-ranged folded kernel): every CTA returns at once unless *run_if != 0
+    const unsigned* run_if;
 };
 
 template <int kOut>
@@ -332,6 +334,7 @@ template <int kOut, bool kPair, bool kF16, bool kSplit2>
 __global__ void __launch_bounds__(512, 1)
 project_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_bhi,
                    const __grid_constant__ CUtensorMap map_blo, const Params p) {
+    if (p.run_if && *reinterpret_cast<const volatile unsigned*>(p.run_if) == 0u) return;     // uniform over the grid
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t x_bytes = (uint32_t)p.subtiles * kTileRows * 128;
@@ -1146,13 +1149,14 @@ int init_tensor_maps(zb200_plan* p) {
 
 int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int precision, int out_kind, void* d_out,
                void* d_out2, const float* d_w, const uint8_t* d_sel, int n_folds, int norm_kind, cudaStream_t s,
-               const GatherSource* gsrc, const PeerTargets* peers, double value_max) {
+               const GatherSource* gsrc, const PeerTargets* peers, double value_max, const unsigned* run_if) {
     using namespace tc;
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG(gsrc || (reinterpret_cast<uintptr_t>(d_patches) & 15) == 0,
                  "project: patch pointer must be 16-byte aligned");
     const bool h3 = precision == ZB200_PREC_F16X3;
-    if (h3 && !(value_max > 0.0)) {
+    const bool folded = h3 && !gsrc && !d_w && fold_supported(p) && knobs().tc_fold != 0;
+    if (h3 && !folded && !(value_max > 0.0)) {
         set_error("the f16x3 projection needs an upper bound of |patch values| (value_max > 0) to scale them into fp16 range");
         return ZB200_EINVAL;
     }
@@ -1163,8 +1167,21 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
     const bool x3 = precision == ZB200_PREC_TF32X3 || h3;       // the fp32-grade kernel family
     const bool scores = d_w != nullptr;
     // windows of 64 / 128 pixels: the mirror-folded kernel (a quarter of the multiply-adds, zb200_project_fold.cu)
-    if (h3 && !gsrc && !scores && fold_supported(p) && knobs().tc_fold != 0)
-        return project_fold(p, d_patches, n, out_kind, d_out, d_out2, s, peers, value_max);
+    if (folded) {
+        if (value_max > 0.0) return project_fold(p, d_patches, n, out_kind, d_out, d_out2, s, peers, value_max);
+        // no bound from the caller: scale by the largest |x| of a sample of the stack; should an unsampled value be
+        // more than 8x larger (fp16 overflow, flagged by the kernel), the range-free tf32x3 kernel behind it runs --
+        // otherwise its CTAs return at once
+        uint32_t* aux = nullptr;
+        ZB_CUDA(cudaMallocAsync(&aux, 2 * sizeof(uint32_t), s));
+        ZB_CUDA(cudaMemsetAsync(aux, 0, 2 * sizeof(uint32_t), s));
+        int rc = project_fold(p, d_patches, n, out_kind, d_out, d_out2, s, peers, 0.0, aux);
+        if (!rc && tc_supported(p, ZB200_PREC_TF32X3, out_kind != ZB200_OUT_REAL))
+            rc = project_tc(p, d_patches, n, ZB200_PREC_TF32X3, out_kind, d_out, d_out2, nullptr, nullptr, 0, 0, s, nullptr, peers,
+                            0.0, aux + 1);
+        cudaFreeAsync(aux, s);
+        return rc;
+    }
     const bool cplx = !scores && out_kind != ZB200_OUT_REAL;
     const Operand& op = cplx ? p->cplx : p->real;
     if (!tc_supported(p, precision, cplx)) {
@@ -1222,6 +1239,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
         prm.n_peers = peers->n;
         for (int g = 0; g < peers->n; ++g) prm.peer_out[g] = peers->out[g];
     }
+    prm.run_if = run_if;
     prm.dbg = kn.tc_debug;                                  // 0 unless a debug-hook build runs with ZB200_EXPERIMENT=1
     if (prm.dbg & 4) prm.chunk_kb = prm.k_blocks;
 

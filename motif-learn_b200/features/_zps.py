@@ -20,7 +20,10 @@ images through the sliding-window map kernel.  Extra, keyword-only options:
                projection ('f16x3': three fp16 tensor-core passes on x = x1 + x2, V = b1 + b2 -- fp32-grade like
                'tf32x3', a quarter fewer tensor-core instructions and half the basis traffic).  fp16 has a narrow
                exponent range, so the inputs are scaled by a power of two derived from this bound; values beyond it
-               by more than 4x overflow to inf / NaN in the result (loud, not silent).  Without it 'auto' is 'tf32x3'.
+               by more than 4x overflow to inf / NaN in the result (loud, not silent).  Without it 'auto' is 'tf32x3',
+               except for 64- and 128-pixel windows (n_max <= 20): those run the mirror-folded fp16-split kernel
+               (a quarter of the multiply-adds), which takes its scale from a sample of the stack when no bound is
+               given and is backed by 'tf32x3' on the same stream should an unsampled value overflow.
 ``output``     'auto' | 'numpy' | 'torch' -- 'auto' returns what it was given: numpy in ->
                float64 numpy out (like the reference); CUDA tensor in -> float32 CUDA tensor.
 """
@@ -197,8 +200,11 @@ class ZPs(BaseEstimator, TransformerMixin):
                 f"as large as polynomial size ({self.size}x{self.size})"
             )
 
-    def _precision_code(self, for_map: bool = False, device_stack: bool = False) -> int:
+    def _precision_code(self, for_map: bool = False, device_stack: bool = False, host_route: bool = False) -> int:
+        """``device_stack``: a CUDA patch stack goes through ``_project`` (which can pass ``value_max``);
+        ``host_route``: the library's own host pipelines (no ``value_max`` argument: auto-range only)."""
         lib = _lib.load()
+        auto_range = bool(lib.zb200_plan_supports_autorange(self._plan))     # the mirror-folded kernel: 64 / 128 px windows
         if self.precision == "auto":
             if for_map:
                 for code in (_lib.PREC_F16X3, _lib.PREC_TF32X3):
@@ -206,12 +212,13 @@ class ZPs(BaseEstimator, TransformerMixin):
                         return code
                 return _lib.PREC_FP32
             ok = lib.zb200_plan_supports(self._plan, _lib.PREC_TF32X3, _lib.OUT_REAL)
-            if ok and device_stack and self.value_max is not None:
+            if ok and ((device_stack and self.value_max is not None) or ((device_stack or host_route) and auto_range)):
                 return _lib.PREC_F16X3
             return _lib.PREC_TF32X3 if ok else _lib.PREC_FP32
         code = _lib.PRECISIONS[self.precision]
         if not for_map and code in (_lib.PREC_F16, _lib.PREC_F16X3):
-            if code == _lib.PREC_F16X3 and device_stack and self.value_max is not None:
+            if code == _lib.PREC_F16X3 and ((device_stack and self.value_max is not None)
+                                            or ((device_stack or host_route) and auto_range)):
                 return code
             code = _lib.PREC_TF32 if code == _lib.PREC_F16 else _lib.PREC_TF32X3
         return code
@@ -226,7 +233,7 @@ class ZPs(BaseEstimator, TransformerMixin):
         o2 = None if out2 is None else int(out2.data_ptr())
         if prec == _lib.PREC_F16X3:
             _lib.check(lib.zb200_project_patches_ranged_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]),
-                                                            float(self.value_max), code, int(out.data_ptr()), o2,
+                                                            float(self.value_max or 0.0), code, int(out.data_ptr()), o2,
                                                             self._stream()), "project_patches_ranged")
         else:
             _lib.check(lib.zb200_project_patches_f32(self._plan, int(dev.data_ptr()), int(dev.shape[0]), prec, code,
@@ -255,7 +262,7 @@ class ZPs(BaseEstimator, TransformerMixin):
             # H2D/kernel/D2H pipeline inside the library
             src = np.ascontiguousarray(images, dtype=np.float32)
             out = np.empty((n_img, n_modes), dtype=np.float64)
-            _lib.check(lib.zb200_project_patches_host(self._plan, np_ptr(src), n_img, self._precision_code(),
+            _lib.check(lib.zb200_project_patches_host(self._plan, np_ptr(src), n_img, self._precision_code(host_route=True),
                                                       np_ptr(out)), "project_patches_host")
             return zmoments(data=out, n=self.n, m=self.m, patch_size=self.size)
         dev = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32)).cuda() if host_in else images
@@ -474,7 +481,7 @@ class ZPs(BaseEstimator, TransformerMixin):
                 raise ValueError(f"out must be a C-contiguous {np.dtype(dtype).name} array of shape (>= {shape[0]}, {shape[1]})")
             out = out[:shape[0]]
         ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
-        prec = self._precision_code()
+        prec = self._precision_code(host_route=True)
         _lib.check(lib.zb200_project_peaks_host(self._plan, ptrs, len(frames), int(h), int(w), np_ptr(flat), np_ptr(counts),
                                                 prec, code, _lib.F64, np_ptr(out)), "project_peaks_host")
         edges = np.concatenate([[0], np.cumsum(counts)])

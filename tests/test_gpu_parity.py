@@ -448,11 +448,15 @@ def test_fused_gather_projection(api, torch):
         fused = z.transform_peaks(dimg, kept, fused=True)
         assert fused.data.is_cuda and fused.data.shape == ref.shape
         fp32_close(fused.data.cpu().numpy(), ref)
-        unfused = z.transform(torch.from_numpy(patches).cuda()).data
+        # bit for bit against the unfused kernel of the same arithmetic (tf32x3; 'auto' on 64-pixel windows is the
+        # mirror-folded fp16-split kernel, compared through the gate)
+        unfused = api.ZPs(n_max, k, precision="tf32x3").transform(torch.from_numpy(patches).cuda()).data
         assert torch.equal(fused.data, unfused)
         refabs = np.abs(zo.to_complex(ref, n, m)[0])
         assert np.abs(z.transform_peaks(dimg, kept, "abs", fused=True).cpu().numpy() - refabs).max() <= 3e-6 * refabs.max()
-        assert torch.equal(z.transform_peaks(dimg, kept).data, unfused)     # default: gather kernel + projection
+        default = z.transform_peaks(dimg, kept).data                         # default: gather kernel + projection
+        assert torch.equal(default, z.transform(torch.from_numpy(patches).cuda()).data)
+        fp32_close(default.cpu().numpy(), ref)
         host = z.transform_peaks(img, kept, fused=True)           # numpy frame in -> float64 numpy out
         assert isinstance(host.data, np.ndarray) and host.data.dtype == np.float64
         fp32_close(host.data, ref)
@@ -1009,13 +1013,56 @@ def test_projection_f16x3_vs_oracle(api, torch, n_max, size, count):
     # a bound that is too small by more than 4x is LOUD: inf / NaN, never a silently wrong number
     bad = api.ZPs(n_max, size, value_max=1e-6).transform(dev).data
     assert not torch.isfinite(bad).all()
-    # without value_max nothing changes: 'auto' is tf32x3, and numpy input keeps the host pipeline
-    assert api.ZPs(n_max, size)._precision_code(device_stack=True) == _lib.PREC_TF32X3
+    # without value_max 'auto' is tf32x3 -- or, for the windows the mirror-folded kernel serves, its auto-ranged form;
+    # numpy input keeps the host pipeline
+    auto = bool(_lib.load().zb200_plan_supports_autorange(z._plan))
+    assert auto == (size % 64 == 0 and n_max <= 20)
+    assert api.ZPs(n_max, size)._precision_code(device_stack=True) == (_lib.PREC_F16X3 if auto else _lib.PREC_TF32X3)
+    fp32_close(api.ZPs(n_max, size).transform(dev).data.cpu().numpy(), ref)
     fp32_close(z.transform(patches).data, ref)
     from sklearn.base import clone
     assert clone(z).value_max == 1.0
     with pytest.raises(ValueError):
         api.ZPs(n_max, size, value_max=-1.0)
+
+
+@pytest.mark.parametrize("n_max,count", [(12, 5000), (20, 2100), (4, 129)])
+def test_folded_projection_auto_range_and_fallback(api, torch, n_max, count):
+    """64-pixel windows without value_max: the mirror-folded kernel scales by the largest |x| of 1024 evenly spread
+    patches.  Same results as with a bound; values up to 8x the sampled maximum still convert; beyond that the
+    overflow flag makes the tf32x3 kernel behind it recompute the stack (nothing silent, no host round trip)."""
+    size = 64
+    rng = np.random.default_rng(7 + n_max)
+    patches = rng.random((count, size, size), dtype=np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        n, m, v = zo.zernike_basis(n_max, size)
+    z = api.ZPs(n_max, size)
+    from motif_learn_b200 import _lib
+    assert _lib.load().zb200_plan_supports_autorange(z._plan) == 1
+    sampled = {(i * count) // min(count, 1024) for i in range(min(count, 1024))}
+    hidden = next(i for i in range(count) if i not in sampled) if len(sampled) < count else None
+    for boost in (1.0, 6.0, 300.0):
+        x = patches.copy()
+        if hidden is None and boost > 1.0:
+            continue
+        if hidden is not None:
+            x[hidden] *= boost                              # a patch the range sample never sees
+        ref = zo.project_patches(x.astype(np.float64), v)
+        refc = zo.to_complex(ref, n, m)[0]
+        dev = torch.from_numpy(x).cuda()
+        fp32_close(z.transform(dev).data.cpu().numpy(), ref)
+        zc = z.transform_features(dev, "complex").cpu().numpy()
+        fp32_close(np.concatenate([zc.real, zc.imag], axis=1), np.concatenate([refc.real, refc.imag], axis=1))
+        mag = z.transform_features(dev, "abs").cpu().numpy()
+        assert np.abs(mag - np.abs(refc)).max() <= 3e-6 * np.abs(refc).max()
+    # the host pipelines take the same route
+    fp32_close(z.transform(patches[:700]).data, zo.project_patches(patches[:700].astype(np.float64), v))
+    # tiny and huge data scales
+    for scale in (1e-20, 1e20):
+        dev = torch.from_numpy(patches[:300] * np.float32(scale)).cuda()
+        fp32_close(z.transform(dev).data.cpu().numpy() / scale, zo.project_patches(patches[:300].astype(np.float64), v))
+    assert torch.equal(z.transform(torch.zeros((3, size, size), device="cuda")).data, torch.zeros((3, len(n)), device="cuda"))
 
 
 def test_mirror_map_in_row_bands(api, golden, torch):
