@@ -515,8 +515,10 @@ def bench_patches(ctx):
     alg_bytes = batch * (PATCH * PATCH * 4 + n_modes * 4)
     achieved = alg_bytes * args.steps / (ms_ng / 1e3) / 1e9
     flops = 2.0 * batch * PATCH * PATCH * n_modes
+    folded = prec == "f16x3" and PATCH % 64 == 0
     kernel = {"fp32": "project_simt_kernel", "tf32": "project_tc_kernel<plain>", "tf32x3": "project_tc3_kernel<plain,pair>",
-              "f16x3": "project_tc3_kernel<plain,pair,f16> (fp16 split, value_max hint)"}[prec]
+              "f16x3": ("project_fold_kernel<plain,0> (mirror-folded fp16 split" if folded else "project_tc3_kernel<plain,pair,f16> (fp16 split")
+                       + (", value_max hint)" if vmax else ", auto-range: range_sample_kernel + conditional tf32x3 launch behind it)")}[prec]
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
             "traffic": NCU_TRAFFIC.get(prec) if batch == 262144 else None,
             "traffic_source": "profiles/ ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch",
@@ -530,13 +532,20 @@ def bench_patches(ctx):
                          "value": total * sus_steps / (ms_s / 1e3), "achieved": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9,
                          "frac": alg_bytes * sus_steps / (ms_s / 1e3) / 1e9 / pk["hbm_gbs"], "clocks": clocks_s}
 
-    if prec == "f16x3":                                # the same batch without the range hint (tf32x3), same run
+    if prec == "f16x3" and vmax:                       # the same batch without the range hint, same run
         zp_nohint = ZPs(N_MAX, PATCH, precision=args.precision)
         ms_t, _, _ = timed(ctx, lambda: zp_nohint.transform(patches), args.steps, 3)
-        roof["without_value_max"] = {"precision": PREC_NAMES[zp_nohint._precision_code(device_stack=True)],
-                                     "kernel": "project_tc3_kernel<plain,pair>", "ms_per_step": ms_t / args.steps,
-                                     "value": total * args.steps / (ms_t / 1e3),
+        p_nh = PREC_NAMES[zp_nohint._precision_code(device_stack=True)]
+        roof["without_value_max"] = {"precision": p_nh,
+                                     "kernel": "range_sample_kernel + project_fold_kernel + conditional project_tc3_kernel (auto-range)"
+                                               if p_nh == "f16x3" else "project_tc3_kernel<plain,pair>",
+                                     "ms_per_step": ms_t / args.steps, "value": total * args.steps / (ms_t / 1e3),
                                      "frac": alg_bytes * args.steps / (ms_t / 1e3) / 1e9 / pk["hbm_gbs"]}
+        zp_x3 = ZPs(N_MAX, PATCH, precision="tf32x3")   # the unfolded range-free kernel (what the fallback runs)
+        ms_x, _, _ = timed(ctx, lambda: zp_x3.transform(patches), args.steps, 3)
+        roof["tf32x3_unfolded"] = {"kernel": "project_tc3_kernel<plain,pair>", "ms_per_step": ms_x / args.steps,
+                                   "value": total * args.steps / (ms_x / 1e3),
+                                   "frac": alg_bytes * args.steps / (ms_x / 1e3) / 1e9 / pk["hbm_gbs"]}
     if peers is not None:
         peers.close()
     e2e = e2e_patches(ctx, zp, n_modes)
@@ -843,7 +852,10 @@ def bench_c3(ctx):
             "peak": pk["hbm_gbs"] if f_h >= f_t else pk["tf32_tflops"], "unit": "GB/s" if f_h >= f_t else "TFLOP/s",
             "frac": max(f_h, f_t), "hbm": {"achieved": gbs, "peak": pk["hbm_gbs"], "frac": f_h},
             "tensor": {"achieved": tfl, "peak": pk["tf32_tflops"], "frac": f_t, "peak_source": pk["tf32_source"]},
-            "traffic": None, "kernel": "project_tc3_kernel<plain> on the complex-interleaved operand" if prec in ("tf32x3", "f16x3") else "project_tc_kernel",
+            "traffic": None,
+            "kernel": ("project_fold_kernel<plain,1> (mirror-folded fp16 split, class widths 80/64/64/64)" if prec == "f16x3" and PATCH % 64 == 0
+                       else "project_tc3_kernel<plain> on the complex-interleaved operand" if prec in ("tf32x3", "f16x3") else "project_tc_kernel"),
+            "executed_flops_note": "the folded kernel executes 2*N*(k^2/4)*272*3 fp16 flops; frac is on ALGORITHMIC flops 2*N*k^2*231",
             "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": flops,
             "note": "SURVEY.md 8d: report both fractions, the larger one binds"}
     cfg = workload_config("c3", world)
