@@ -49,6 +49,7 @@ const Knobs& knobs() {
         v.tc_accbufs = knob("ZB200_TC_ACCBUFS", 1, 2, 0);
         v.tc_split2 = knob("ZB200_TC_SPLIT2", 0, 1, -1);
         v.tc_fold = knob("ZB200_TC_FOLD", 0, 1, -1);
+        v.tc_park = knob("ZB200_TC_PARK", 0, 1, -1);
         v.map_gskip = knob("ZB200_MAP_GSKIP", 0, 1, -1);
         v.map_bstages = knob("ZB200_MAP_BSTAGES", 2, 8, 0);
         v.map_slots = knob("ZB200_MAP_SLOTS", 2, 16, 0);

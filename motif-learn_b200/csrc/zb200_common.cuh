@@ -55,6 +55,7 @@ struct Knobs {
     int tc_stages = 0;     // ZB200_TC_STAGES  1..8
     int tc_accbufs = 0;    // ZB200_TC_ACCBUFS 1|2
     int tc_fold = -1;      // ZB200_TC_FOLD    0|1   mirror-folded projection when the plan has a folded operand
+    int tc_park = -1;      // ZB200_TC_PARK    0|1   parked (suspend-time hint) waits of the idle roles in the folded kernel
     int tc_split2 = -1;    // ZB200_TC_SPLIT2  0|1   two splitter warpgroups + one epilogue warpgroup (metric shape)
     int tc_debug = 0;      // ZB200_TC_DEBUG   bit mask, needs a -DZB200_DEBUG_HOOKS=1 build (results are wrong when set)
     int map_gskip = -1;    // ZB200_MAP_GSKIP  0|1

@@ -49,6 +49,14 @@ __host__ __device__ constexpr int cfg_cols(int cfg) { return cls_off(cfg, 3) + c
 constexpr int kSlotMax = 80;
 constexpr int kUnitCols = 64;                 // TMEM columns of one staging unit
 constexpr int kXStage = 4 * kTileRows * 128;  // four boxes of 128 rows x 128 bytes
+// waits of the roles that are idle most of the time (epilogue between chunks, the producers) carry a suspend-time
+// hint: the hardware parks the warp until the phase completes instead of re-issuing try_wait -- the spin loops were
+// 56 % of the kernel's executed instructions (ncu source page), issue slots and power the HBM-bound kernel needs
+constexpr uint32_t kParkNs = 20000;
+__device__ __forceinline__ void wait_idle(uint64_t* bar, uint32_t parity, uint32_t park_ns) {
+    if (park_ns) mbar_wait_parked(bar, parity, park_ns);
+    else mbar_wait(bar, parity);
+}
 
 template <int kCfg> struct Regs;              // setmaxnreg budgets: (ctl + split + epi_a + epi_b) * 128 <= 64 Ki
 template <> struct Regs<0> { static constexpr int ctl = 48, split = 152, epi_a = 152, epi_b = 152; };
@@ -74,6 +82,7 @@ struct Params {
     // auto-range (no value_max from the caller): absmax = bits of the largest sampled |x| (range_sample_kernel); the
     // kernel derives the power-of-two scale from it; flag is raised when a result is not finite (an unsampled value
     // beyond 8x the sampled maximum overflowed fp16) -- the caller then recomputes with the range-free kernel
+    uint32_t park_ns;         // suspend-time hint of the idle roles' waits (0 = plain try_wait loops)
     const uint32_t* absmax;
     unsigned* flag;
     float inv_area;
@@ -162,7 +171,7 @@ __device__ __forceinline__ void epilogue_pair(const Params& p, uint32_t tmem_bas
             for (int i = 0; i < 16; ++i) sum[cc][i] = 0.f;
         for (int c = 0; c < n_chunks; ++c, ++ck) {
             const int buf = p.acc_bufs == 2 ? (int)(ck & 1) : 0;
-            mbar_wait(&acc_full[buf], p.acc_bufs == 2 ? ((ck >> 1) & 1u) : (ck & 1u));
+            wait_idle(&acc_full[buf], p.acc_bufs == 2 ? ((ck >> 1) & 1u) : (ck & 1u), p.park_ns);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * n_cols + col0);
 #pragma unroll
@@ -309,7 +318,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         const int i = sb / p.nj, jb = sb - i * p.nj;
                         const int c_top = i * p.k, c_bot = (p.k - 1 - i) * p.k;
                         const int c_l = jb * 32, c_r = p.k - 32 - jb * 32;
-                        mbar_wait(&xempty[s], ph ^ 1);
+                        wait_idle(&xempty[s], ph ^ 1, p.park_ns);
                         mbar_arrive_expect_tx(&xfull[s], kXStage);
                         uint8_t* st = smem + (size_t)s * kXStage;
                         tma_load_2d(st, &map_x, &xfull[s], c_top + c_l, row0, kEvictFirst);
@@ -328,7 +337,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 uint32_t phb = 0;
                 for (int t = 0; t < my_tiles; ++t)
                     for (int sbi = 0; sbi < p.sb_count; ++sbi) {
-                        mbar_wait(&bempty[sb], phb ^ 1);
+                        wait_idle(&bempty[sb], phb ^ 1, p.park_ns);
                         mbar_arrive_expect_tx(&bfull[sb], kBStage);
                         tma_load_2d(b_ring + (size_t)sb * kBStage, &map_b, &bfull[sb], (p.sb_first + sbi) * 32,
                                     (int)crank * (kCols / 2), kEvictLast);
@@ -344,7 +353,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     uint32_t phb = 0;
                     for (int t = 0; t < my_tiles; ++t)
                         for (int sbi = 0; sbi < p.sb_count; ++sbi) {
-                            mbar_wait(&bfull[sb], phb);
+                            wait_idle(&bfull[sb], phb, p.park_ns);
                             mbar_arrive_cluster(mapa_cluster(smem_u32(&bpeer[sb]), 0));
                             if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
                         }
@@ -759,6 +768,7 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
     if (prm.n_units > 4) prm.n_units = 4;
     prm.chunk_sb = 8;
     if (kn.tc_chunk) prm.chunk_sb = kn.tc_chunk;
+    prm.park_ns = kn.tc_park == 0 ? 0u : kParkNs;
     const int bst = (cols / 2) * 128;
     const int bar_core = 8 * (2 * 8 + 24) + 16;
     const int tail = pushing ? round_up(bar_core, 128) + 128 + (int)kPushRegion : bar_core;
