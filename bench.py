@@ -41,7 +41,9 @@ WORKLOADS = ["patches", "map", "map4k", "c3", "c5"]
 PREC_NAMES = {0: "fp32", 1: "tf32", 2: "tf32x3", 3: "f16", 4: "f16x3"}
 DTYPES = {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)", "f16": "f16", "f16x3": "f16x3(f32-grade)"}
 # DRAM bytes per launch from the committed ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_TRAFFIC = {"tf32x3": 4.198750e9 + 43.819e6, "tf32": 4.181859e9 + 53.549e6}           # 262 144 patches
+NCU_TRAFFIC = {"tf32x3": 4.198750e9 + 43.819e6, "tf32": 4.181859e9 + 53.549e6,            # 262 144 patches
+               "f16x3": 4.163300e9 + 60.865e6}       # project_fold_kernel<0,0>, profiles/r02_prof_fold_raw.csv
+NCU_TRAFFIC_C3_262144 = 4.184101e9 + 223.845e6     # project_fold_kernel<0,1> on 262 144 patches, profiles/r02_prof_c3_raw.csv
 NCU_TRAFFIC_MAP = {"tf32x3": 136.456e6 + 48.684e6, "f16x3": 136.000e6 + 47.324e6}        # 2048^2, k=48
 
 
@@ -852,7 +854,8 @@ def bench_c3(ctx):
             "peak": pk["hbm_gbs"] if f_h >= f_t else pk["tf32_tflops"], "unit": "GB/s" if f_h >= f_t else "TFLOP/s",
             "frac": max(f_h, f_t), "hbm": {"achieved": gbs, "peak": pk["hbm_gbs"], "frac": f_h},
             "tensor": {"achieved": tfl, "peak": pk["tf32_tflops"], "frac": f_t, "peak_source": pk["tf32_source"]},
-            "traffic": None,
+            "traffic": NCU_TRAFFIC_C3_262144 * (n / 262144.0) if prec == "f16x3" and PATCH % 64 == 0 else None,
+            "traffic_source": "profiles/r02_prof_c3_raw.csv: one ncu --set full capture at 262 144 patches, scaled by the launch's patch count",
             "kernel": ("project_fold_kernel<plain,1> (mirror-folded fp16 split, class widths 80/64/64/64)" if prec == "f16x3" and PATCH % 64 == 0
                        else "project_tc3_kernel<plain> on the complex-interleaved operand" if prec in ("tf32x3", "f16x3") else "project_tc_kernel"),
             "executed_flops_note": "the folded kernel executes 2*N*(k^2/4)*272*3 fp16 flops; frac is on ALGORITHMIC flops 2*N*k^2*231",
@@ -878,7 +881,7 @@ def bench_c5(ctx):
     n_frames_total = args.c5_frames
     lo, hi = shard_range(n_frames_total, rank, world)
     zp = ZPs(N_MAX, PATCH, precision=args.precision)
-    prec = PREC_NAMES[zp._precision_code()]
+    prec = PREC_NAMES[zp._precision_code(device_stack=True)]     # the projection inside series_features runs on CUDA stacks
     n_c = 49
     rng = np.random.default_rng(12345)
     angles = rng.uniform(0.0, 60.0, n_frames_total)
