@@ -982,7 +982,8 @@ def test_denoise_svd_golden(golden, torch):
 
 
 # ---- fp16-split projection (round 2) ---------------------------------------------------------------------------
-@pytest.mark.parametrize("n_max,size,count", [(12, 64, 1500), (20, 64, 300), (10, 32, 700), (12, 48, 257), (3, 6, 5)])
+@pytest.mark.parametrize("n_max,size,count", [(12, 64, 1500), (20, 64, 300), (10, 32, 700), (12, 48, 257), (3, 6, 5),
+                                              (13, 128, 200), (14, 128, 150), (0, 64, 130)])
 def test_projection_f16x3_vs_oracle(api, torch, n_max, size, count):
     """ZB200_PREC_F16X3 on patch stacks (value_max given): the strict fp32-grade gate against the oracle, every
     fused epilogue, and invariance under the scale of the data (the power-of-two input scale follows value_max)."""
