@@ -894,7 +894,8 @@ def bench_c5(ctx):
     def compute():
         # per frame: local_max -> clear_border -> gather kernel -> projection with the |Zc| epilogue; the frames are
         # spread over `workers` host threads with one CUDA stream each so their small kernels interleave
-        feats, pts = series_features(zp, frames, PEAK_MIN_DISTANCE, PEAK_THRESHOLD, kind="abs", workers=args.c5_workers)
+        feats, pts = series_features(zp, frames, PEAK_MIN_DISTANCE, PEAK_THRESHOLD, kind="abs", workers=args.c5_workers,
+                                     fused={"auto": None, "off": False}[args.c5_fused])
         hold["feats"], hold["counts"] = feats, [len(q) for q in pts]
 
     def step():
@@ -959,6 +960,7 @@ def main():
     ap.add_argument("--c3-total", type=int, default=C3_TOTAL)
     ap.add_argument("--c5-frames", type=int, default=C5_FRAMES)
     ap.add_argument("--c5-workers", type=int, default=6, help="host threads / CUDA streams of the frame-series pipeline")
+    ap.add_argument("--c5-fused", default="auto", choices=["auto", "off"], help="off: gather kernel + projection instead of the gathering folded kernel")
     ap.add_argument("--also", default="all", help="comma list of the other workloads to carry under 'also' (all | none | names)")
     ap.add_argument("--no-also", action="store_true", help="same as --also none")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")

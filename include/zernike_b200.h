@@ -92,6 +92,10 @@ int         zb200_plan_supports_map(const zb200_plan* plan, int precision);
  * (n_max <= 20) run the mirror-folded kernel, which can take its input scale from a sample of the stack and is backed
  * by the range-free TF32X3 kernel when an unsampled value overflows (see zb200_project_patches_ranged_f32). */
 int         zb200_plan_supports_autorange(const zb200_plan* plan);
+/* 1 if zb200_project_peaks_f32 accepts ZB200_PREC_F16X3 for this plan (64-pixel windows, n_max <= 13): the
+ * mirror-folded kernel then gathers the windows from the frame itself -- KeyPoints.extract_patches + ZPs.transform
+ * (_keypoint.py:60-78 + _zps.py:146-157) in one launch, the frame maximum as the exact range bound. */
+int         zb200_plan_supports_folded_gather(const zb200_plan* plan);
 
 /* ---- K1: basis (replaces ZPs.__init__/_generate_polynomials, _zps.py:23-90) - */
 /* (n_max+1)(n_max+2)/2, or negative on bad n_max. */
@@ -143,8 +147,9 @@ int zb200_project_patches_scores_f32(const zb200_plan* plan, const float* d_patc
                                      int n_folds, int norm_kind, float* d_scores, void* stream);
 /* K2 fused into K3: moments of the windows centred at the peaks, gathered straight from the frame
  * inside the projection kernel -- the patch stack never exists in HBM (replaces
- * KeyPoints.extract_patches + ZPs.transform, _keypoint.py:60-78 + _zps.py:146-157).  tf32x3 only,
- * windows >= 32 px; pixels outside the frame read as 0.  Same epilogues as zb200_project_patches_f32. */
+ * KeyPoints.extract_patches + ZPs.transform, _keypoint.py:60-78 + _zps.py:146-157).  TF32X3 (windows >= 32 px) or,
+ * where zb200_plan_supports_folded_gather says so, F16X3 (the mirror-folded kernel with a gathering warpgroup: the
+ * faster route, no patch stack in HBM); pixels outside the frame read as 0.  Same epilogues as zb200_project_patches_f32. */
 int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_img, int H, int W,
                             const double* d_pts_xy, int64_t n_pts, int precision, int out_kind,
                             void* d_out, void* d_out2, void* stream);

@@ -41,6 +41,7 @@ SIGNATURES = {
     "zb200_plan_supports": (_int, [_vp, _int, _int]),
     "zb200_plan_supports_map": (_int, [_vp, _int]),
     "zb200_plan_supports_autorange": (_int, [_vp]),
+    "zb200_plan_supports_folded_gather": (_int, [_vp]),
     "zb200_num_modes": (_int, [_int]),
     "zb200_num_complex_modes": (_int, [_int]),
     "zb200_mode_table": (_int, [_int, _i32p, _i32p]),

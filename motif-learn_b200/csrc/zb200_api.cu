@@ -262,6 +262,7 @@ extern "C" int zb200_plan_supports(const zb200_plan* p, int precision, int out_k
 }
 
 extern "C" int zb200_plan_supports_autorange(const zb200_plan* p) { return p && fold_supported(p) && knobs().tc_fold != 0 ? 1 : 0; }
+extern "C" int zb200_plan_supports_folded_gather(const zb200_plan* p) { return p && fold_gather_supported(p) && knobs().tc_fold != 0 ? 1 : 0; }
 
 extern "C" int zb200_plan_supports_map(const zb200_plan* p, int precision) {
     if (!p) return 0;

@@ -132,7 +132,8 @@ struct FoldOperand {
     int cols = 0;                // accumulator columns = operand rows (all four classes, padded)
     int nj = 0;                  // 32-tap boxes per half window row
     int n_sb = 0;                // super-blocks (32 folded taps) in the quadrant
-    int sb_first = 0, sb_count = 0;   // those with taps inside the unit disk
+    int sb_count = 0;            // those with taps inside the unit disk
+    unsigned short* d_sb_list = nullptr;   // their indices, ascending
     uint32_t* fb = nullptr;      // [cols][n_sb * 32] words: per super-block 32 x half b1 | 32 x half b2; rows [rank][class][slot]
     unsigned char* d_umask = nullptr;   // per super-block: bit h = 16-tap unit h is active
     short* d_col_real = nullptr;        // [cols] real mode of an accumulator column (-1 = padding)
@@ -213,7 +214,9 @@ int init_fold_operand(zb200_plan* plan);
 void free_fold_operand(zb200_plan* plan);
 bool fold_supported(const zb200_plan* plan);
 int project_fold(const zb200_plan* plan, const float* d_patches, int64_t n, int out_kind, void* d_out, void* d_out2,
-                 cudaStream_t s, const PeerTargets* peers, double value_max, uint32_t* d_aux = nullptr);
+                 cudaStream_t s, const PeerTargets* peers, double value_max, uint32_t* d_aux = nullptr,
+                 const GatherSource* gather = nullptr);
+bool fold_gather_supported(const zb200_plan* plan);
 
 int map_simt(const zb200_plan* plan, const float* d_img, int H, int W, int row0, int rows,
              float* d_moments, float* d_scores, const float* d_w, const uint8_t* d_sel, int n_folds,

@@ -55,15 +55,33 @@ __global__ void corners_kernel(const double* __restrict__ pts, long long n, int 
 
 // shifted, zero-padded copies of the frame for the 16-byte gathers of the fused path:
 //   plane r [y][u] = img0[y][u - L + r]   (img0 = frame, zero outside), u in [0, Wp), Wp % 4 == 0
-__global__ void shift_planes_kernel(const float* __restrict__ img, int H, int W, int Wp, int L, float* __restrict__ planes) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n = (long long)H * Wp;
-    if (i >= n) return;
-    const int y = (int)(i / Wp), u = (int)(i - (long long)y * Wp);
+// absmax (optional): receives the bits of max |frame| (plane 0 reads every pixel once) -- the exact range bound of the
+// folded fp16-split projection that gathers from these planes.
+// One thread per row and group of four padded columns: the seven frame pixels u-L .. u-L+6 give the float4 of every
+// plane; stores are 16 bytes per plane and thread (512 contiguous bytes per warp), 72 MB for a 2048^2 frame.
+__global__ void shift_planes_kernel(const float* __restrict__ img, int H, int W, int Wp, int L, float* __restrict__ planes,
+                                    uint32_t* __restrict__ absmax) {
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    uint32_t m = 0;
+    if (u < Wp) {
+        const float* row = img + (size_t)y * W;
+        float v[7];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int x = u - L + r;
-        planes[(long long)r * n + i] = (x >= 0 && x < W) ? __ldg(img + (long long)y * W + x) : 0.f;
+        for (int e = 0; e < 7; ++e) {
+            const int x = u - L + e;
+            v[e] = (x >= 0 && x < W) ? __ldg(row + x) : 0.f;
+        }
+        const size_t n = (size_t)H * Wp, o = (size_t)y * Wp + u;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            *reinterpret_cast<float4*>(planes + (size_t)r * n + o) = make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) m = max(m, __float_as_uint(v[e]) & 0x7FFFFFFFu);
+    }
+    if (absmax) {
+        m = __reduce_max_sync(0xffffffffu, m);
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(absmax, m);
     }
 }
 
@@ -79,18 +97,44 @@ extern "C" int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_im
     if (n_pts == 0) return ZB200_OK;
     ZB_CHECK_ARG(d_img && d_pts_xy && d_out, "project_peaks: null pointer");
     cudaStream_t s = as_stream(stream);
+    // 64-pixel windows, n_max <= 13: the mirror-folded kernel gathers the windows itself (fp32-grade like tf32x3; the
+    // range bound is the frame maximum, measured by the plane pre-pass)
+    const bool folded = precision == ZB200_PREC_F16X3 && fold_gather_supported(plan) && knobs().tc_fold != 0 && H <= 65535;
+    if (precision == ZB200_PREC_F16X3 && !folded) {
+        set_error("project_peaks: the fp16-split fused gather needs a 64-pixel window and n_max <= 13");
+        return ZB200_EUNSUP;
+    }
     int2* xy0 = nullptr;
-    ZB_CUDA(cudaMallocAsync(&xy0, sizeof(int2) * (size_t)n_pts, s));
+    ZB_CUDA(cudaMallocAsync(&xy0, sizeof(int2) * (size_t)n_pts + 16, s));
     corners_kernel<<<(unsigned)ceil_div(n_pts, 256), 256, 0, s>>>(d_pts_xy, (long long)n_pts, plan->size, xy0);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     GatherSource src{d_img, H, W, xy0};
     float* planes = nullptr;
-    if (plan->size % 4 == 0 && !knobs().gather_4b) {
+    if (folded) {
+        const int L = plan->size, Wp = round_up(W + 2 * L, 4);
+        uint32_t* aux = reinterpret_cast<uint32_t*>(xy0 + n_pts);          // [0] absmax bits, [1] unused
+        int rc = ZB200_OK;
+        if (cudaMallocAsync(&planes, sizeof(float) * 4 * (size_t)H * Wp, s) == cudaSuccess) {
+            ZB_CUDA(cudaMemsetAsync(aux, 0, 16, s));
+            shift_planes_kernel<<<dim3((unsigned)ceil_div(Wp / 4, 128), (unsigned)H), 128, 0, s>>>(d_img, H, W, Wp, L, planes, aux);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            src.planes = planes;
+            src.Wp = Wp;
+            src.L = L;
+            rc = project_fold(plan, nullptr, n_pts, out_kind, d_out, d_out2, s, nullptr, 0.0, aux, &src);
+            cudaFreeAsync(planes, s);
+            cudaFreeAsync(xy0, s);
+            return rc;
+        }
+        cudaGetLastError();                                 // no memory for the planes: the unfolded tf32x3 route below
+        planes = nullptr;
+        precision = ZB200_PREC_TF32X3;
+    }
+    if (plan->size % 4 == 0 && !knobs().gather_4b && H <= 65535) {
         // windows start at arbitrary columns; four copies shifted by 0..3 pixels make every window row 16-byte aligned
         const int L = plan->size, Wp = round_up(W + 2 * L, 4);
         if (cudaMallocAsync(&planes, sizeof(float) * 4 * (size_t)H * Wp, s) == cudaSuccess) {
-            const long long n = (long long)H * Wp;
-            shift_planes_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(d_img, H, W, Wp, L, planes);
+            shift_planes_kernel<<<dim3((unsigned)ceil_div(Wp / 4, 128), (unsigned)H), 128, 0, s>>>(d_img, H, W, Wp, L, planes, nullptr);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             src.planes = planes;
             src.Wp = Wp;

@@ -339,6 +339,8 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
     if (rc) return rc;
     const int L = row_len_of(p, out_kind);
     const size_t frame_bytes = sizeof(float) * (size_t)H * W;
+    // 64-pixel windows, n_max <= 13: one kernel gathers and projects (no patch stack in HBM)
+    const bool fused_gather = precision == ZB200_PREC_F16X3 && fold_gather_supported(p) && knobs().tc_fold != 0;
     bool all_pinned = true;
     for (int f = 0; f < n_frames && all_pinned; ++f) all_pinned = is_pinned(h_frames[f]);
     for (int b = 0; b < kSlots && b < n_frames; ++b) {
@@ -346,7 +348,7 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
         if ((rc = ensure_buf(&h->pin_out[b], &h->pin_out_cap[b], sizeof(float) * max_count * L, kPinned))) return rc;
         if ((rc = ensure_buf(&h->dev_in[b], &h->dev_in_cap[b], frame_bytes, kDevice))) return rc;
         if ((rc = ensure_buf(&h->dev_pts[b], &h->dev_pts_cap[b], sizeof(double) * 2 * max_count, kDevice))) return rc;
-        if ((rc = ensure_buf(&h->dev_pat[b], &h->dev_pat_cap[b], sizeof(float) * max_count * p->kk, kDevice))) return rc;
+        if (!fused_gather && (rc = ensure_buf(&h->dev_pat[b], &h->dev_pat_cap[b], sizeof(float) * max_count * p->kk, kDevice))) return rc;
         if ((rc = ensure_buf(&h->dev_out[b], &h->dev_out_cap[b], sizeof(float) * max_count * L, kDevice))) return rc;
     }
     std::vector<int64_t> first((size_t)n_frames + 1, 0);
@@ -362,12 +364,18 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
         if (cnt > 0) {
             ZB_CUDA(cudaMemcpyAsync(h->dev_pts[b], h_pts_xy + 2 * first[f], sizeof(double) * 2 * (size_t)cnt,
                                     cudaMemcpyHostToDevice, h->st[b]));
-            int r = zb200_gather_patches_f32(static_cast<const float*>(h->dev_in[b]), H, W,
+            int r;
+            if (fused_gather) {
+                r = zb200_project_peaks_f32(p, static_cast<const float*>(h->dev_in[b]), H, W, static_cast<const double*>(h->dev_pts[b]),
+                                            cnt, precision, out_kind, h->dev_out[b], nullptr, h->st[b]);
+            } else {
+                r = zb200_gather_patches_f32(static_cast<const float*>(h->dev_in[b]), H, W,
                                              static_cast<const double*>(h->dev_pts[b]), cnt, p->size,
                                              static_cast<float*>(h->dev_pat[b]), h->st[b]);
-            if (r) return r;
-            r = project_any(p, static_cast<const float*>(h->dev_pat[b]), cnt, precision, out_kind, h->dev_out[b], nullptr,
-                            nullptr, nullptr, 0, 0, h->st[b]);
+                if (r) return r;
+                r = project_any(p, static_cast<const float*>(h->dev_pat[b]), cnt, precision, out_kind, h->dev_out[b], nullptr,
+                                nullptr, nullptr, 0, 0, h->st[b]);
+            }
             if (r) return r;
             ZB_CUDA(cudaMemcpyAsync(h->pin_out[b], h->dev_out[b], sizeof(float) * (size_t)cnt * L, cudaMemcpyDeviceToHost,
                                     h->st[b]));

@@ -58,15 +58,19 @@ __device__ __forceinline__ void wait_idle(uint64_t* bar, uint32_t parity, uint32
     else mbar_wait(bar, parity);
 }
 
-template <int kCfg> struct Regs;              // setmaxnreg budgets: (ctl + split + epi_a + epi_b) * 128 <= 64 Ki
-template <> struct Regs<0> { static constexpr int ctl = 48, split = 152, epi_a = 152, epi_b = 152; };
-template <> struct Regs<1> { static constexpr int ctl = 48, split = 96, epi_a = 200, epi_b = 168; };   // 144 / 128 running sums
+template <int kCfg, bool kGather> struct Regs;   // setmaxnreg budgets: (ctl + split + epi_a + epi_b) * 128 <= 64 Ki
+template <> struct Regs<0, false> { static constexpr int ctl = 48, split = 152, epi_a = 152, epi_b = 152, gather = 0; };
+template <> struct Regs<1, false> { static constexpr int ctl = 48, split = 96, epi_a = 200, epi_b = 168, gather = 0; };   // 144 / 128 running sums
+// K2 fused (a fifth warpgroup gathers the windows): 640 threads start with 96 registers, the pool is 480 x 128
+template <> struct Regs<0, true> { static constexpr int ctl = 40, split = 128, epi_a = 120, epi_b = 120, gather = 72; };
+template <> struct Regs<1, true> { static constexpr int ctl = 40, split = 128, epi_a = 120, epi_b = 120, gather = 72; };   // never launched
 
 struct Params {
     long long n_patches;
     int n_tiles;              // 128-patch tiles
-    int sb_first, sb_count;   // super-blocks (32 folded taps) with a non-zero folded basis: [sb_first, sb_first + sb_count)
-    const unsigned char* umask;   // per super-block: bit h = its 16-tap unit h holds taps of the unit disk
+    int sb_count;             // super-blocks (32 folded taps) with taps inside the unit disk
+    const unsigned short* sb_list;   // their indices (window row i = sb / nj, 32-tap column block jb = sb % nj), ascending
+    const unsigned char* umask;   // per super-block (absolute index): bit h = its 16-tap unit h holds taps of the unit disk
     int k, nj;                // window side, 32-tap boxes per half row (k / 64)
     int n_stages, b_stages, n_units, acc_bufs, chunk_sb;
     int out_kind;             // ZB200_OUT_*
@@ -82,6 +86,11 @@ struct Params {
     // auto-range (no value_max from the caller): absmax = bits of the largest sampled |x| (range_sample_kernel); the
     // kernel derives the power-of-two scale from it; flag is raised when a result is not finite (an unsampled value
     // beyond 8x the sampled maximum overflowed fp16) -- the caller then recomputes with the range-free kernel
+    // K2 fused into K3: windows are gathered from four shifted, zero-padded copies of the frame (16-byte aligned
+    // window rows: plane r [y][u] = frame[y][u - g_L + r], pitch g_Wp) at the corners g_xy
+    const float* g_planes;
+    const int2* g_xy;
+    int g_H, g_Wp, g_L;
     uint32_t park_ns;         // suspend-time hint of the idle roles' waits (0 = plain try_wait loops)
     const uint32_t* absmax;
     unsigned* flag;
@@ -236,8 +245,8 @@ __device__ __forceinline__ void epilogue_pair(const Params& p, uint32_t tmem_bas
     }
 }
 
-template <int kOut, int kCfg>
-__global__ void __launch_bounds__(512, 1)
+template <int kOut, int kCfg, bool kGather>
+__global__ void __launch_bounds__(kGather ? 640 : 512, 1)
 project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kCols = cfg_cols(kCfg);
@@ -268,7 +277,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
-            mbar_init(&xfull[s], 1);
+            mbar_init(&xfull[s], kGather ? 128 : 1);     // gathered: every gathering thread's copies have landed
             mbar_init(&xempty[s], 4);
         }
         for (int b = 0; b < 4; ++b) {
@@ -305,16 +314,16 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
 
     if (wg == 3) {
-        reg_dec<Regs<kCfg>::ctl>();
+        reg_dec<Regs<kCfg, kGather>::ctl>();
         if (warp == kWarpTma) {
             // ===================== X producer: the four mirror boxes of a super-block =====================
-            if (elect_one()) {
+            if (!kGather && elect_one()) {
                 int s = 0;
                 uint32_t ph = 0;
                 for (int t = 0; t < my_tiles; ++t) {
                     const int row0 = (blockIdx.x + t * gridDim.x) * kTileRows;
                     for (int sbi = 0; sbi < p.sb_count; ++sbi) {
-                        const int sb = p.sb_first + sbi;
+                        const int sb = __ldg(p.sb_list + sbi);
                         const int i = sb / p.nj, jb = sb - i * p.nj;
                         const int c_top = i * p.k, c_bot = (p.k - 1 - i) * p.k;
                         const int c_l = jb * 32, c_r = p.k - 32 - jb * 32;
@@ -339,7 +348,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     for (int sbi = 0; sbi < p.sb_count; ++sbi) {
                         wait_idle(&bempty[sb], phb ^ 1, p.park_ns);
                         mbar_arrive_expect_tx(&bfull[sb], kBStage);
-                        tma_load_2d(b_ring + (size_t)sb * kBStage, &map_b, &bfull[sb], (p.sb_first + sbi) * 32,
+                        tma_load_2d(b_ring + (size_t)sb * kBStage, &map_b, &bfull[sb], (int)__ldg(p.sb_list + sbi) * 32,
                                     (int)crank * (kCols / 2), kEvictLast);
                         if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
                     }
@@ -377,7 +386,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         const int sb_end = min(p.sb_count, (c + 1) * p.chunk_sb);
                         uint32_t acc_run = 0u;
                         for (int sbi = c * p.chunk_sb; sbi < sb_end; ++sbi) {
-                            const uint32_t um = __ldg(p.umask + p.sb_first + sbi);
+                            const uint32_t um = __ldg(p.umask + __ldg(p.sb_list + sbi));
                             mbar_wait_cluster(&bpeer[sb], phb);
                             mbar_wait(&bfull[sb], phb);
                             const uint32_t bl = b_lo0 + (uint32_t)sb * (kBStage >> 4);
@@ -414,8 +423,8 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
     } else if (wg == 0) {
         // ===================== butterfly + fp16 split, one patch row per thread =====================
-        if constexpr (Regs<kCfg>::split > 128) reg_inc<Regs<kCfg>::split>();
-        else reg_dec<Regs<kCfg>::split>();
+        if constexpr (Regs<kCfg, kGather>::split > (kGather ? 96 : 128)) reg_inc<Regs<kCfg, kGather>::split>();
+        else reg_dec<Regs<kCfg, kGather>::split>();
         const int r = warp * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         const uint32_t swz = (uint32_t)(r & 7) << 4;
@@ -427,7 +436,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         uint32_t uph = 0;
         for (int t = 0; t < my_tiles; ++t) {
             for (int sbi = 0; sbi < p.sb_count; ++sbi) {
-                const uint32_t um = __ldg(p.umask + p.sb_first + sbi);
+                const uint32_t um = __ldg(p.umask + __ldg(p.sb_list + sbi));
                 mbar_wait(&xfull[s], ph);
                 const uint32_t rowp = row_u32 + (uint32_t)s * kXStage;
 #pragma unroll
@@ -483,11 +492,68 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 if (++s == p.n_stages) { s = 0; ph ^= 1; }
             }
         }
+    } else if (kGather && wg == 4) {
+        // ===================== K2: gather the windows of 128 patches into the X ring =====================
+        // one warp per 32 tile rows; a warp instruction copies the 32-float segments of 4 rows (8 lanes x 16 bytes each)
+        reg_dec<Regs<kCfg, kGather>::gather>();
+        const int gw = warp - 16;
+        const int ch = lane & 7;
+        int s = 0;
+        uint32_t ph = 0;
+        // per lane, the 8 tile rows it serves (row j = 4 it + lane / 8 of this warp's 32): everything that does not
+        // depend on the super-block is computed once per tile -- the first version spent ~45 instructions per copy
+        uint32_t dst_row[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int j = 4 * it + (lane >> 3);
+            dst_row[it] = (uint32_t)j * 128u + (((uint32_t)ch ^ (uint32_t)(j & 7)) << 4);
+        }
+        const unsigned x_hi = (unsigned)(p.g_Wp - 4);
+        for (int t = 0; t < my_tiles; ++t) {
+            const long long base = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTileRows + gw * 32;
+            int2 cn = make_int2(-(1 << 28), -(1 << 28));               // rows past the end: every copy zero-fills
+            if (base + lane < p.n_patches) cn = __ldg(p.g_xy + base + lane);
+            const float* row_ptr[8];      // plane (x0 & 3), frame row y0, padded column x0 - (x0 & 3) + g_L + 4 ch
+            int row_y[8], row_x[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int j = 4 * it + (lane >> 3);
+                const int x0 = __shfl_sync(0xffffffffu, cn.x, j), y0 = __shfl_sync(0xffffffffu, cn.y, j);
+                const int xl = x0 + p.g_L + 4 * ch;                   // segment starts and g_L are multiples of 4
+                const int rr = xl & 3;
+                row_y[it] = y0;
+                row_x[it] = xl - rr;
+                const bool sane = y0 > -(1 << 20) && y0 < (1 << 20) && x0 > -(1 << 20) && x0 < (1 << 20);
+                row_ptr[it] = p.g_planes + (sane ? ((long long)rr * p.g_H + y0) * p.g_Wp + (xl - rr) : 0);
+                if (!sane) row_y[it] = -(1 << 28);
+            }
+            for (int sbi = 0; sbi < p.sb_count; ++sbi) {
+                const int sb = __ldg(p.sb_list + sbi);
+                const int i = sb / p.nj, jb = sb - i * p.nj;
+                wait_idle(&xempty[s], ph ^ 1, p.park_ns);
+                const uint32_t xs = smem_u32(smem) + (uint32_t)s * kXStage + (uint32_t)(gw * 32) * 128u;
+#pragma unroll
+                for (int box = 0; box < 4; ++box) {
+                    const int wr = (box < 2) ? i : p.k - 1 - i;
+                    const int wc = (box & 1) ? p.k - 32 - jb * 32 : jb * 32;
+                    const long long off = (long long)wr * p.g_Wp + wc;
+                    const uint32_t xb = xs + (uint32_t)box * 16384u;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const bool inb = (unsigned)(row_y[it] + wr) < (unsigned)p.g_H && (unsigned)(row_x[it] + wc) <= x_hi;
+                        const float* gp = inb ? row_ptr[it] + off : p.g_planes;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xb + dst_row[it]), "l"(gp), "r"(inb ? 16 : 0) : "memory");
+                    }
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&xfull[s])) : "memory");
+                if (++s == p.n_stages) { s = 0; ph ^= 1; }
+            }
+        }
     } else {
         // ===================== epilogue: warpgroup 1 owns the class pair A, warpgroup 2 the pair B =====================
         const int g = wg - 1, q = warp & 3;
-        if (g == 0) reg_inc<Regs<kCfg>::epi_a>();
-        else reg_inc<Regs<kCfg>::epi_b>();
+        if (g == 0) reg_inc<Regs<kCfg, kGather>::epi_a>();
+        else reg_inc<Regs<kCfg, kGather>::epi_b>();
         if (g == 0)
             epilogue_pair<kOut, cls_w(kCfg, 0) / 16, cls_w(kCfg, 1) / 16>(p, tmem_base, kCols, cls_off(kCfg, 0), 0, q, lane, crank != 0,
                                                                           acc_full, acc_empty, out_done, my_tiles, n_chunks, out_scale);
@@ -572,6 +638,7 @@ void free_fold_operand(zb200_plan* p) {
     FoldOperand& f = p->fold;
     cudaFree(f.fb);
     cudaFree(f.d_umask);
+    cudaFree(f.d_sb_list);
     cudaFree(f.d_col_real);
     cudaFree(f.d_slot_cplx);
     f = FoldOperand();
@@ -650,14 +717,11 @@ int init_fold_operand(zb200_plan* p) {
             if (x * x + y * y <= 1.0 + 1e-9) um[(size_t)sb] |= (unsigned char)(1u << (t / 16));
         }
     }
-    int first = 0, last = f.n_sb;
-    while (first < last && !um[(size_t)first]) ++first;
-    while (last > first && !um[(size_t)last - 1]) --last;
-    for (int sb = first; sb < last; ++sb)
-        if (!um[(size_t)sb]) return ZB200_OK;                             // a hole inside the range: keep the unfolded kernels
-    if (last - first < 1) return ZB200_OK;
-    f.sb_first = first;
-    f.sb_count = last - first;
+    std::vector<unsigned short> sb_list;
+    for (int sb = 0; sb < f.n_sb; ++sb)
+        if (um[(size_t)sb]) sb_list.push_back((unsigned short)sb);
+    if (sb_list.empty()) return ZB200_OK;
+    f.sb_count = (int)sb_list.size();
 
     short *d_row_mode = nullptr;
     signed char *d_sj = nullptr, *d_si = nullptr;
@@ -665,6 +729,8 @@ int init_fold_operand(zb200_plan* p) {
     const size_t fb_bytes = (size_t)cols * f.n_sb * 128;
     ZB_CUDA(cudaMalloc(&f.fb, fb_bytes));
     ZB_CUDA(cudaMalloc(&f.d_umask, (size_t)f.n_sb));
+    ZB_CUDA(cudaMalloc(&f.d_sb_list, sizeof(unsigned short) * sb_list.size()));
+    ZB_CUDA(cudaMemcpy(f.d_sb_list, sb_list.data(), sizeof(unsigned short) * sb_list.size(), cudaMemcpyHostToDevice));
     ZB_CUDA(cudaMalloc(&f.d_col_real, sizeof(short) * col_real.size()));
     ZB_CUDA(cudaMalloc(&f.d_slot_cplx, sizeof(short) * slot_cplx.size()));
     ZB_CUDA(cudaMalloc(&d_row_mode, sizeof(short) * row_mode.size()));
@@ -700,12 +766,15 @@ int init_fold_operand(zb200_plan* p) {
 }
 
 bool fold_supported(const zb200_plan* p) { return p->fold.ready; }
+bool fold_gather_supported(const zb200_plan* p) { return p->fold.ready && p->fold.cfg == 0; }
 
 // value_max > 0: the caller's bound of |x|.  value_max <= 0: auto-range -- d_aux (two zeroed 32-bit words owned by the
 // caller: [0] sampled absmax bits, [1] overflow flag) receives the largest |x| of up to 1024 evenly spread patches, the
 // kernel scales by it and raises d_aux[1] if any result is not finite (then every row must be recomputed).
+// gsrc (optional, n_max <= 13): K2 fused -- the windows are gathered from the shifted planes of a frame by a fifth
+// warpgroup instead of being loaded from a patch stack; d_aux[0] must then hold the bits of max |frame| (or value_max > 0).
 int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out_kind, void* d_out, void* d_out2,
-                 cudaStream_t s, const PeerTargets* peers, double value_max, uint32_t* d_aux) {
+                 cudaStream_t s, const PeerTargets* peers, double value_max, uint32_t* d_aux, const GatherSource* gsrc) {
     using namespace fold;
     const FoldOperand& f = p->fold;
     if (!f.ready) {
@@ -713,15 +782,19 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
         return ZB200_EUNSUP;
     }
     if (n == 0) return ZB200_OK;
-    ZB_CHECK_ARG((reinterpret_cast<uintptr_t>(d_patches) & 15) == 0, "project: patch pointer must be 16-byte aligned");
+    ZB_CHECK_ARG(gsrc || (reinterpret_cast<uintptr_t>(d_patches) & 15) == 0, "project: patch pointer must be 16-byte aligned");
+    if (gsrc && (f.cfg != 0 || !gsrc->planes)) {
+        set_error("folded projection: the fused gather needs n_max <= 13 and the shifted frame planes");
+        return ZB200_EUNSUP;
+    }
     ZB_CHECK_ARG(value_max > 0.0 || d_aux, "the folded projection needs an upper bound of |patch values| or auto-range scratch");
     ZB_CHECK_ARG(out_kind != ZB200_OUT_COMPLEX || (reinterpret_cast<uintptr_t>(d_out) & 7) == 0,
                  "project: complex output must be 8-byte aligned");
     Params prm{};
     prm.n_patches = n;
     prm.n_tiles = (int)ceil_div(n, kTileRows);
-    prm.sb_first = f.sb_first;
     prm.sb_count = f.sb_count;
+    prm.sb_list = f.d_sb_list;
     prm.umask = f.d_umask;
     prm.k = p->size;
     prm.nj = f.nj;
@@ -738,12 +811,21 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
         prm.cls_col[cl] = (uint32_t)cls_off(f.cfg, cl);
     }
     prm.inv_area = (float)p->inv_area;
+    if (gsrc) {
+        prm.g_planes = gsrc->planes;
+        prm.g_xy = gsrc->xy0;
+        prm.g_H = gsrc->H;
+        prm.g_Wp = gsrc->Wp;
+        prm.g_L = gsrc->L;
+    }
     if (!(value_max > 0.0)) {
-        const int n_sample = (int)(n < 1024 ? n : 1024);
-        range_sample_kernel<<<n_sample, 256, 0, s>>>(d_patches, (long long)n, p->kk, n_sample, d_aux);
-        ZB_LAUNCHED();
+        if (!gsrc) {
+            const int n_sample = (int)(n < 1024 ? n : 1024);
+            range_sample_kernel<<<n_sample, 256, 0, s>>>(d_patches, (long long)n, p->kk, n_sample, d_aux);
+            ZB_LAUNCHED();
+            prm.flag = d_aux + 1;
+        }                                                   // gathered: d_aux[0] bounds the whole frame, nothing can overflow
         prm.absmax = d_aux;
-        prm.flag = d_aux + 1;
         prm.x_scale = prm.out_scale = 1.f;
     } else {
         int e = 0;
@@ -787,7 +869,8 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
     prm.push_off = (uint32_t)round_up((int)ring_bytes + bar_core, 128);
 
     CUtensorMap map_x;
-    int rc = encode_2d(&map_x, d_patches, (uint64_t)p->kk, (uint64_t)n, (uint64_t)p->kk * 4, (uint32_t)kTileRows);
+    int rc = gsrc ? encode_2d(&map_x, f.fb, (uint64_t)f.n_sb * 32, (uint64_t)cols, (uint64_t)f.n_sb * 128, 8)       // unused
+                  : encode_2d(&map_x, d_patches, (uint64_t)p->kk, (uint64_t)n, (uint64_t)p->kk * 4, (uint32_t)kTileRows);
     if (rc) return rc;
     int grid = prm.n_tiles < p->sm_count ? prm.n_tiles : p->sm_count;
     grid = (grid / 2) * 2;
@@ -805,17 +888,21 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int kout = out_kind == ZB200_OUT_ABS ? kOutAbs : (out_kind == ZB200_OUT_ABS_PHASE ? kOutAbsPhase : kOutPlain);
-#define ZB_FOLD_LAUNCH(KOUT, CFG)                                                                                              \
-    if (kout == KOUT && f.cfg == CFG) {                                                                                        \
-        ZB_CUDA(cudaFuncSetAttribute(project_fold_kernel<KOUT, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        ZB_CUDA(cudaLaunchKernelEx(&cfg, project_fold_kernel<KOUT, CFG>, map_x, f.tmap, prm));                                 \
+#define ZB_FOLD_LAUNCH(KOUT, CFG, GATHER)                                                                                      \
+    if (kout == KOUT && f.cfg == CFG && (gsrc != nullptr) == GATHER) {                                                         \
+        ZB_CUDA(cudaFuncSetAttribute(project_fold_kernel<KOUT, CFG, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        cfg.blockDim = dim3(GATHER ? 640 : 512);                                                                               \
+        ZB_CUDA(cudaLaunchKernelEx(&cfg, project_fold_kernel<KOUT, CFG, GATHER>, map_x, f.tmap, prm));                         \
     }
-    ZB_FOLD_LAUNCH(kOutPlain, 0)
-    ZB_FOLD_LAUNCH(kOutAbs, 0)
-    ZB_FOLD_LAUNCH(kOutAbsPhase, 0)
-    ZB_FOLD_LAUNCH(kOutPlain, 1)
-    ZB_FOLD_LAUNCH(kOutAbs, 1)
-    ZB_FOLD_LAUNCH(kOutAbsPhase, 1)
+    ZB_FOLD_LAUNCH(kOutPlain, 0, false)
+    ZB_FOLD_LAUNCH(kOutAbs, 0, false)
+    ZB_FOLD_LAUNCH(kOutAbsPhase, 0, false)
+    ZB_FOLD_LAUNCH(kOutPlain, 1, false)
+    ZB_FOLD_LAUNCH(kOutAbs, 1, false)
+    ZB_FOLD_LAUNCH(kOutAbsPhase, 1, false)
+    ZB_FOLD_LAUNCH(kOutPlain, 0, true)
+    ZB_FOLD_LAUNCH(kOutAbs, 0, true)
+    ZB_FOLD_LAUNCH(kOutAbsPhase, 0, true)
 #undef ZB_FOLD_LAUNCH
     ZB_LAUNCHED();
     return ZB200_OK;

@@ -36,14 +36,15 @@ def _worker_streams(torch, count: int):
     return have[:count]
 
 
-def series_features(zps, frames, min_distance, threshold=None, kind: str = "abs", workers: int = 3):
+def series_features(zps, frames, min_distance, threshold=None, kind: str = "abs", workers: int = 3, fused=None):
     """Peaks -> patches -> Zernike features for every frame of ``frames`` (a CUDA tensor (F, H, W) or a sequence
     of 2-D CUDA tensors / numpy arrays).  ``zps`` is the ``ZPs`` transformer; ``kind`` as in
     ``ZPs.transform_peaks`` ('real' returns the (P, M) moment tensors, 'abs' the rotation-invariant |Zc|, ...).
 
     Returns ``(features, points)``: two lists with one entry per frame -- the feature tensor (CUDA, float32 /
     complex64; rows in the order of ``points``) and the kept peak coordinates ((P, 2) int64 numpy, (x, y),
-    brightest first, already filtered by ``clear_border``)."""
+    brightest first, already filtered by ``clear_border``).  ``fused`` is passed to ``ZPs.transform_peaks`` (None: the
+    mirror-folded kernel gathers the windows itself where the plan has it; False: gather kernel + projection)."""
     torch = _lib.require_cuda()
     n_frames = len(frames)
     if n_frames == 0:
@@ -61,7 +62,7 @@ def series_features(zps, frames, min_distance, threshold=None, kind: str = "abs"
                 frame = torch.from_numpy(np.ascontiguousarray(frame, dtype=np.float32)).cuda(non_blocking=True)
             pts = local_max(frame, min_distance, threshold)
             kept = clear_border(pts, tuple(frame.shape), zps.size)
-            feats = zps.transform_peaks(frame, kept, kind, fused=False)
+            feats = zps.transform_peaks(frame, kept, kind, fused=fused)
             data = feats.data if kind == "real" else feats
             for t in (data if isinstance(data, tuple) else (data,)):
                 t.record_stream(caller)                 # allocated on the worker stream, consumed on the caller's

@@ -389,9 +389,10 @@ class ZPs(BaseEstimator, TransformerMixin):
         float64 / complex128 numpy results like the reference (through ``zb200_project_peaks_host``: frame and
         coordinates up, features down), a CUDA frame float32 / complex64 CUDA tensors.
         ``fused=True`` runs gather and projection as ONE kernel (windows go from the L2-resident frame straight
-        into the tensor-core operand; the memory-lean path), ``False`` the gather kernel followed by the
-        projection (the faster one); ``None`` picks the fused kernel when the intermediate patch stack would
-        exceed 8 GiB."""
+        into the tensor-core operand, no patch stack in HBM), ``False`` the gather kernel followed by the
+        projection.  ``None`` (default): 64-pixel windows with n_max <= 13 use the mirror-folded kernel with its
+        gathering warpgroup (the fastest route); other shapes the two-kernel route, or the tf32x3 fused kernel
+        when the intermediate patch stack would exceed 8 GiB."""
         if image.ndim != 2:
             raise ValueError("Images must be 2D or 3D array.")
         torch = _lib.require_cuda()
@@ -402,12 +403,20 @@ class ZPs(BaseEstimator, TransformerMixin):
         to_host = self._want_host(image)
         pts_np = np.ascontiguousarray(np.asarray(pts, dtype=np.float64).reshape(-1, 2))
         can_fuse = (prec == _lib.PREC_TF32X3 and self.size >= 32 and lib.zb200_plan_supports(self._plan, prec, code))
+        # 64-pixel windows, n_max <= 13: the mirror-folded kernel gathers the windows itself -- faster than the gather
+        # kernel + projection (no patch stack in HBM), so it is the default there
+        fold_gather = (self.precision in ("auto", "f16x3") and bool(lib.zb200_plan_supports_folded_gather(self._plan))
+                       and lib.zb200_plan_supports(self._plan, _lib.PREC_F16X3, code))
+        if fold_gather:
+            can_fuse, prec = True, _lib.PREC_F16X3
+        host_route = (to_host and not is_torch(image) and kind != "abs_phase"
+                      and (prec == _lib.PREC_FP32 and kind == "real" or lib.zb200_plan_supports(self._plan, prec, code)))
         if fused is None:
-            fused = can_fuse and pts_np.shape[0] * self.size * self.size * 4 > (8 << 30)
+            # a numpy frame goes through the library's host pipeline (which fuses on its own where it can)
+            fused = (not host_route) and (fold_gather or (can_fuse and pts_np.shape[0] * self.size * self.size * 4 > (8 << 30)))
         if fused and not can_fuse:
             raise ValueError("fused gather+projection needs precision 'tf32x3' (or 'auto' on a supported shape) and size >= 32")
-        if (to_host and not is_torch(image) and not fused and kind != "abs_phase"
-                and (prec == _lib.PREC_FP32 and kind == "real" or lib.zb200_plan_supports(self._plan, prec, code))):
+        if host_route and not fused:
             return self.transform_peaks_batch([image], [pts_np], kind)[0]
         dev = self._image_on_device(image)
         if not fused:

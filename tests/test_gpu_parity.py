@@ -448,15 +448,24 @@ def test_fused_gather_projection(api, torch):
         fused = z.transform_peaks(dimg, kept, fused=True)
         assert fused.data.is_cuda and fused.data.shape == ref.shape
         fp32_close(fused.data.cpu().numpy(), ref)
-        # bit for bit against the unfused kernel of the same arithmetic (tf32x3; 'auto' on 64-pixel windows is the
-        # mirror-folded fp16-split kernel, compared through the gate)
-        unfused = api.ZPs(n_max, k, precision="tf32x3").transform(torch.from_numpy(patches).cuda()).data
-        assert torch.equal(fused.data, unfused)
+        # the tf32x3 fused kernel equals the unfused kernel of the same arithmetic bit for bit
+        zt = api.ZPs(n_max, k, precision="tf32x3")
+        unfused = zt.transform(torch.from_numpy(patches).cuda()).data
+        assert torch.equal(zt.transform_peaks(dimg, kept, fused=True).data, unfused)
         refabs = np.abs(zo.to_complex(ref, n, m)[0])
         assert np.abs(z.transform_peaks(dimg, kept, "abs", fused=True).cpu().numpy() - refabs).max() <= 3e-6 * refabs.max()
-        default = z.transform_peaks(dimg, kept).data                         # default: gather kernel + projection
-        assert torch.equal(default, z.transform(torch.from_numpy(patches).cuda()).data)
+        zc = z.transform_peaks(dimg, kept, "complex", fused=True).cpu().numpy()
+        refc = zo.to_complex(ref, n, m)[0]
+        fp32_close(np.concatenate([zc.real, zc.imag], axis=1), np.concatenate([refc.real, refc.imag], axis=1))
+        # default route: 64-pixel windows gather inside the mirror-folded kernel (frame maximum as the range bound),
+        # the other shapes run gather kernel + projection; the two-kernel route stays available
+        default = z.transform_peaks(dimg, kept).data
         fp32_close(default.cpu().numpy(), ref)
+        two = z.transform_peaks(dimg, kept, fused=False).data
+        assert torch.equal(two, z.transform(torch.from_numpy(patches).cuda()).data)
+        fp32_close(two.cpu().numpy(), ref)
+        if k == 64:
+            assert torch.equal(default, fused.data)
         host = z.transform_peaks(img, kept, fused=True)           # numpy frame in -> float64 numpy out
         assert isinstance(host.data, np.ndarray) and host.data.dtype == np.float64
         fp32_close(host.data, ref)
