@@ -17,7 +17,7 @@ struct Scratch {
     explicit Scratch(cudaStream_t st) : s(st) {}
     ~Scratch() { if (ptr) cudaFreeAsync(ptr, s); }
     int upload(const void* host, size_t bytes) {
-        ZB_CUDA(cudaMallocAsync(&ptr, bytes ? bytes : 1, s));
+        ZB_CUDA(scratch_alloc(&ptr, bytes ? bytes : 1, s));
         if (bytes) ZB_CUDA(cudaMemcpyAsync(ptr, host, bytes, cudaMemcpyHostToDevice, s));
         return ZB200_OK;
     }
@@ -258,7 +258,7 @@ int upload_weights(const float* h_weights, const uint8_t* h_select, int n_folds,
         for (int c = 0; c < n_cols; ++c) hw[(size_t)f * cols_pad + c] = h_weights[(size_t)f * n_cols + c];
     for (int c = 0; c < n_cols; ++c) host[wbytes + c] = h_select[c] ? 1 : 0;
     void* dev = nullptr;
-    ZB_CUDA(cudaMallocAsync(&dev, host.size(), s));
+    ZB_CUDA(scratch_alloc(&dev, host.size(), s));
     ZB_CUDA(cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, s));
     *d_w = static_cast<float*>(dev);
     *d_sel = static_cast<uint8_t*>(dev) + wbytes;

@@ -63,6 +63,40 @@ const Knobs& knobs() {
     return k;
 }
 
+// Stream-ordered scratch (score tables, operand planes of the dense map, peak-detection keys, shifted frame planes:
+// 0.1-0.6 GB per call at 2048^2..4096^2) comes from a PRIVATE memory pool per device: it keeps up to 8 GiB cached across
+// synchronisation points (a frame series allocates the same blocks again every frame, on several streams) without
+// touching the release threshold of the application's default pool.
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, s);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t created = nullptr;
+            if (cudaMemPoolCreate(&created, &props) == cudaSuccess) {
+                uint64_t keep = 8ull << 30;
+                cudaMemPoolSetAttribute(created, cudaMemPoolAttrReleaseThreshold, &keep);
+                pools[dev] = created;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        pool = pools[dev];
+    }
+    return pool ? cudaMallocFromPoolAsync(ptr, bytes, pool, s) : cudaMallocAsync(ptr, bytes, s);
+}
+
 static int check_device(int* sms, int* major, int* minor) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -203,19 +237,6 @@ extern "C" int zb200_plan_create(int n_max, int size, zb200_plan** out_plan) {
     } while (0)
 
     {
-        // keep stream-ordered scratch (score tables, operand planes of the dense map, peak-detection keys) cached in
-        // the default pool across synchronisation points instead of returning it to the driver -- up to 2 GiB (the
-        // working sets above are 0.4-0.6 GB at 4096^2); anything beyond goes back at the next synchronisation so the
-        // host application's own allocator is not starved.  An already larger threshold is left alone.
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess) {
-            uint64_t have = 0, keep = 2ull << 30;
-            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &have) == cudaSuccess && have < keep)
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-    }
-    {
         // 8-tap K steps that touch the unit disk, per 32-tap k-block (same rule as above)
         const int k = size, nkb = p->k_pad / 32;
         std::vector<unsigned char> km((size_t)nkb, 0);
@@ -334,7 +355,7 @@ extern "C" int zb200_project_patches_scores_f32(const zb200_plan* p, const float
     if (precision == ZB200_PREC_FP32) {
         // SIMT contraction into a temporary, then the score kernel (two launches, no fusion)
         float* tmp = nullptr;
-        ZB_CUDA(cudaMallocAsync(&tmp, sizeof(float) * (size_t)n * p->n_modes, s));
+        ZB_CUDA(scratch_alloc(&tmp, sizeof(float) * (size_t)n * p->n_modes, s));
         int rc = project_simt(p, d_patches, n, tmp, s);
         if (!rc) {
             double wd[kMaxFolds * kMaxModes];          // bounded by the checks above: nothing throws across the C ABI

@@ -228,8 +228,8 @@ struct DevBuf {
     explicit DevBuf(cudaStream_t st) : s(st) {}
     ~DevBuf() { if (p) cudaFreeAsync(p, s); }
     int alloc(size_t bytes) {
-        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, s);
-        if (e != cudaSuccess) { p = nullptr; set_error("cluster: cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ZB200_ENOMEM; }
+        cudaError_t e = scratch_alloc(&p, bytes ? bytes : 16, s);
+        if (e != cudaSuccess) { p = nullptr; set_error("cluster: scratch_alloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ZB200_ENOMEM; }
         return ZB200_OK;
     }
     int upload(const void* h, size_t bytes) {

@@ -69,6 +69,12 @@ const Knobs& knobs();
 #define ZB200_DEBUG_HOOKS 0      // ablation bits / blocked-cycle counters inside the hot kernels: compiled out of releases
 #endif
 
+// stream-ordered scratch from the library's private memory pool (zb200_api.cu); release with cudaFreeAsync
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s);
+template <class T> static inline cudaError_t scratch_alloc(T** ptr, size_t bytes, cudaStream_t s) {
+    return scratch_alloc(reinterpret_cast<void**>(ptr), bytes, s);
+}
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

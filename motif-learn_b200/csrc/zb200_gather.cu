@@ -105,7 +105,7 @@ extern "C" int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_im
         return ZB200_EUNSUP;
     }
     int2* xy0 = nullptr;
-    ZB_CUDA(cudaMallocAsync(&xy0, sizeof(int2) * (size_t)n_pts + 16, s));
+    ZB_CUDA(scratch_alloc(&xy0, sizeof(int2) * (size_t)n_pts + 16, s));
     corners_kernel<<<(unsigned)ceil_div(n_pts, 256), 256, 0, s>>>(d_pts_xy, (long long)n_pts, plan->size, xy0);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     GatherSource src{d_img, H, W, xy0};
@@ -114,7 +114,7 @@ extern "C" int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_im
         const int L = plan->size, Wp = round_up(W + 2 * L, 4);
         uint32_t* aux = reinterpret_cast<uint32_t*>(xy0 + n_pts);          // [0] absmax bits, [1] unused
         int rc = ZB200_OK;
-        if (cudaMallocAsync(&planes, sizeof(float) * 4 * (size_t)H * Wp, s) == cudaSuccess) {
+        if (scratch_alloc(&planes, sizeof(float) * 4 * (size_t)H * Wp, s) == cudaSuccess) {
             ZB_CUDA(cudaMemsetAsync(aux, 0, 16, s));
             shift_planes_kernel<<<dim3((unsigned)ceil_div(Wp / 4, 128), (unsigned)H), 128, 0, s>>>(d_img, H, W, Wp, L, planes, aux);
             g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -133,7 +133,7 @@ extern "C" int zb200_project_peaks_f32(const zb200_plan* plan, const float* d_im
     if (plan->size % 4 == 0 && !knobs().gather_4b && H <= 65535) {
         // windows start at arbitrary columns; four copies shifted by 0..3 pixels make every window row 16-byte aligned
         const int L = plan->size, Wp = round_up(W + 2 * L, 4);
-        if (cudaMallocAsync(&planes, sizeof(float) * 4 * (size_t)H * Wp, s) == cudaSuccess) {
+        if (scratch_alloc(&planes, sizeof(float) * 4 * (size_t)H * Wp, s) == cudaSuccess) {
             shift_planes_kernel<<<dim3((unsigned)ceil_div(Wp / 4, 128), (unsigned)H), 128, 0, s>>>(d_img, H, W, Wp, L, planes, nullptr);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             src.planes = planes;

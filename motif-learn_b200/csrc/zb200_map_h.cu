@@ -771,7 +771,7 @@ static int map_h_part(const zb200_plan* p, const MapHalf& mh, const float* d_img
     const int plane_rows = plane_end > prm.plane_row0 ? plane_end - prm.plane_row0 : 1;
     const size_t plane_bytes = (size_t)plane_rows * Wq * 16;
     uint8_t* scratch = nullptr;
-    ZB_CUDA(cudaMallocAsync(&scratch, 256 + (size_t)n_maps * plane_bytes, s));
+    ZB_CUDA(scratch_alloc(&scratch, 256 + (size_t)n_maps * plane_bytes, s));
     unsigned int* d_bits = reinterpret_cast<unsigned int*>(scratch);
     float* d_scale = reinterpret_cast<float*>(scratch + 16);
     uint4* planes = reinterpret_cast<uint4*>(scratch + 256);
@@ -905,7 +905,7 @@ int map_h(const zb200_plan* p, const float* d_img, int H, int W, int row0, int r
     // they are computed from the materialised moment maps by the rot-score kernel (zb200_algebra.cu).
     float* moments = d_moments;
     const size_t plane = (size_t)rows * W;
-    if (d_scores) ZB_CUDA(cudaMallocAsync(&moments, sizeof(float) * plane * p->n_modes, s));
+    if (d_scores) ZB_CUDA(scratch_alloc(&moments, sizeof(float) * plane * p->n_modes, s));
     int rc = ZB200_OK;
     for (int i = 0; i < p->n_map_parts && rc == ZB200_OK; ++i) {
         const MapHalf& mh = p->map_half[i];

@@ -455,7 +455,7 @@ int map_tc(const zb200_plan* p, const float* d_img, int H, int W, int row0, int 
     const int Wp = round_up(W + 4, 4);
     const int n_maps = 4 * prm.n_planes;
     float* planes = nullptr;
-    ZB_CUDA(cudaMallocAsync(&planes, sizeof(float) * (size_t)n_maps * H * Wp, s));
+    ZB_CUDA(scratch_alloc(&planes, sizeof(float) * (size_t)n_maps * H * Wp, s));
     {
         const long long n = (long long)H * Wp;
         map_prepare_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(d_img, H, W, Wp, prm.n_planes, planes);

@@ -119,7 +119,7 @@ extern "C" int zb200_gram_f32(const float* d_x, int64_t n, int m, double* d_gram
     slabs = ceil_div(n, rows_per_cta);
     double* partial = nullptr;
     const size_t mm = (size_t)m * m;
-    ZB_CUDA(cudaMallocAsync(&partial, sizeof(double) * (size_t)slabs * (mm + m), s));
+    ZB_CUDA(scratch_alloc(&partial, sizeof(double) * (size_t)slabs * (mm + m), s));
     double* partial_sum = partial + (size_t)slabs * mm;
     gram_kernel<<<dim3((unsigned)slabs, (unsigned)tiles, (unsigned)tiles), PG_T * PG_T, 0, s>>>(d_x, (long long)n, m, rows_per_cta,
                                                                                              partial, partial_sum);
@@ -139,7 +139,7 @@ extern "C" int zb200_pca_scores_f32(const float* d_x, int64_t n, int m, const do
     cudaStream_t s = as_stream(stream);
     double* tab = nullptr;
     const size_t words = (size_t)m * (n_comp + 1);
-    ZB_CUDA(cudaMallocAsync(&tab, sizeof(double) * words, s));
+    ZB_CUDA(scratch_alloc(&tab, sizeof(double) * words, s));
     ZB_CUDA(cudaMemcpyAsync(tab, h_mean, sizeof(double) * m, cudaMemcpyHostToDevice, s));
     ZB_CUDA(cudaMemcpyAsync(tab + m, h_components, sizeof(double) * (size_t)m * n_comp, cudaMemcpyHostToDevice, s));
     scores_kernel<<<(unsigned)ceil_div((long long)n * n_comp, 256), 256, 0, s>>>(d_x, (long long)n, m, tab, n_comp, d_out);

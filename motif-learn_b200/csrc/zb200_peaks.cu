@@ -161,7 +161,7 @@ extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_
     const size_t off_keys0 = 256, off_keys1 = off_keys0 + key_bytes, off_rank = off_keys1 + key_bytes;
     const size_t off_state = off_rank + sizeof(int) * (size_t)n_pix, off_flags = off_state + (size_t)n_pix;
     const size_t total = off_flags + (size_t)n_pix + 256;
-    ZB_CUDA(cudaMallocAsync(&pool, total, s));
+    ZB_CUDA(scratch_alloc(&pool, total, s));
     {
         uint32_t* mm = reinterpret_cast<uint32_t*>(pool);                       // [0] min, [1] max
         unsigned long long* count = reinterpret_cast<unsigned long long*>(pool + 16);
@@ -192,7 +192,7 @@ extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_
         {
             size_t tmp_bytes = 0;
             ZB_PEAKS_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys0, keys1, (int)n, 0, 64, s));
-            ZB_PEAKS_CUDA(cudaMallocAsync(&cub_tmp, tmp_bytes, s));
+            ZB_PEAKS_CUDA(scratch_alloc(&cub_tmp, tmp_bytes, s));
             ZB_PEAKS_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, tmp_bytes, keys0, keys1, (int)n, 0, 64, s));
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ZB_PEAKS_CUDA(cudaFreeAsync(cub_tmp, s));
@@ -232,7 +232,7 @@ extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_
         {
             size_t tmp_bytes = 0;
             ZB_PEAKS_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, keys1, flags, keys0, n_sel, (int)n, s));
-            ZB_PEAKS_CUDA(cudaMallocAsync(&cub_tmp, tmp_bytes, s));
+            ZB_PEAKS_CUDA(scratch_alloc(&cub_tmp, tmp_bytes, s));
             ZB_PEAKS_CUDA(cub::DeviceSelect::Flagged(cub_tmp, tmp_bytes, keys1, flags, keys0, n_sel, (int)n, s));
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ZB_PEAKS_CUDA(cudaFreeAsync(cub_tmp, s));

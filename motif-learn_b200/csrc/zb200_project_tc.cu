@@ -1173,7 +1173,7 @@ int project_tc(const zb200_plan* p, const float* d_patches, int64_t n, int preci
         // more than 8x larger (fp16 overflow, flagged by the kernel), the range-free tf32x3 kernel behind it runs --
         // otherwise its CTAs return at once
         uint32_t* aux = nullptr;
-        ZB_CUDA(cudaMallocAsync(&aux, 2 * sizeof(uint32_t), s));
+        ZB_CUDA(scratch_alloc(&aux, 2 * sizeof(uint32_t), s));
         ZB_CUDA(cudaMemsetAsync(aux, 0, 2 * sizeof(uint32_t), s));
         int rc = project_fold(p, d_patches, n, out_kind, d_out, d_out2, s, peers, 0.0, aux);
         if (!rc && tc_supported(p, ZB200_PREC_TF32X3, out_kind != ZB200_OUT_REAL))
