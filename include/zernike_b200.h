@@ -79,6 +79,10 @@ int         zb200_abi_version(void);
 const char* zb200_last_error(void);
 /* SM count and compute capability of the current device. */
 int         zb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Stream-ordered scratch of the library (frame planes, peak-detection keys, score tables, map operand planes) lives in
+ * a library-private cudaMemPool per device that keeps freed blocks cached; this synchronises the current device and
+ * returns the cached blocks to the driver.  The application's default memory pool is never reconfigured. */
+int         zb200_trim_scratch(void);
 /* Kernels launched by this library since the last reset (bench.py gpu_launches). */
 int64_t     zb200_launch_count(void);
 void        zb200_reset_launch_count(void);

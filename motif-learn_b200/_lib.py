@@ -40,6 +40,7 @@ SIGNATURES = {
     "zb200_reset_launch_count": (None, []),
     "zb200_plan_supports": (_int, [_vp, _int, _int]),
     "zb200_plan_supports_map": (_int, [_vp, _int]),
+    "zb200_trim_scratch": (_int, []),
     "zb200_plan_supports_autorange": (_int, [_vp]),
     "zb200_plan_supports_folded_gather": (_int, [_vp]),
     "zb200_num_modes": (_int, [_int]),

@@ -162,10 +162,11 @@ __global__ void rot_scores_kernel(const T* __restrict__ in, long long n_items, i
 }
 
 // ---- mirror score: max_theta sum_c Re(Zc^2 e^{-i m_c theta})  (_zmoments.py:464-493) ---------
-// tab[t][c] = (cos(m_c theta_t), sin(m_c theta_t)); eight angles share each pass over the modes.
+// tab[t][c] = (cos(m_c theta_t), sin(m_c theta_t)) in the precision of the data (float64 moments keep float64
+// trigonometry); eight angles share each pass over the modes.
 template <typename T>
 __global__ void mirror_kernel(const Cx<T>* __restrict__ in, long long n_items, int n_c, long long is,
-                              long long ms, const float2* __restrict__ tab, int n_theta, T* __restrict__ out) {
+                              long long ms, const Cx<T>* __restrict__ tab, int n_theta, T* __restrict__ out) {
     const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n_items) return;
     T best = -INFINITY;
@@ -179,8 +180,8 @@ __global__ void mirror_kernel(const Cx<T>* __restrict__ in, long long n_items, i
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 if (t0 + u < n_theta) {
-                    const float2 cs = __ldg(&tab[(size_t)(t0 + u) * n_c + c]);
-                    acc[u] += p * (T)cs.x + q * (T)cs.y;
+                    const Cx<T> cs = tab[(size_t)(t0 + u) * n_c + c];
+                    acc[u] += p * cs.re + q * cs.im;
                 }
             }
         }
@@ -197,7 +198,7 @@ __global__ void mirror_kernel(const Cx<T>* __restrict__ in, long long n_items, i
 // 11 slots instead of 40 modes).  slot[c] = group of mode c; tab[t][s] = (cos, sin)(m_s theta_t); kSlots >= groups.
 template <typename T, int kSlots>
 __global__ void mirror_grouped_kernel(const Cx<T>* __restrict__ in, long long n_items, int n_c, long long is,
-                                      long long ms, const int* __restrict__ slot, const float2* __restrict__ tab,
+                                      long long ms, const int* __restrict__ slot, const Cx<T>* __restrict__ tab,
                                       int n_theta, T* __restrict__ out) {
     const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n_items) return;
@@ -214,13 +215,13 @@ __global__ void mirror_grouped_kernel(const Cx<T>* __restrict__ in, long long n_
     }
     T best = -INFINITY;
     for (int t = 0; t < n_theta; ++t) {
-        const float2* row = tab + (size_t)t * kSlots;
+        const Cx<T>* row = tab + (size_t)t * kSlots;
         T a0 = 0, a1 = 0;
 #pragma unroll
         for (int s = 0; s < kSlots; s += 2) {
-            const float2 c0 = __ldg(row + s), c1 = __ldg(row + s + 1);
-            a0 += P[s] * (T)c0.x + Q[s] * (T)c0.y;
-            a1 += P[s + 1] * (T)c1.x + Q[s + 1] * (T)c1.y;
+            const Cx<T> c0 = row[s], c1 = row[s + 1];
+            a0 += P[s] * c0.re + Q[s] * c0.im;
+            a1 += P[s + 1] * c1.re + Q[s + 1] * c1.im;
         }
         const T acc = a0 + a1;
         best = acc > best ? acc : best;
@@ -423,6 +424,49 @@ extern "C" int zb200_rot_scores(int dtype, const void* d_in, int64_t n_items, in
     return ZB200_OK;
 }
 
+// host side of zb200_mirror_scores for one dtype: trig tables in that dtype, grouped kernel for <= 32 distinct m
+template <typename T>
+static int mirror_impl(const void* d_in, int64_t n_items, int n_c, int64_t is, int64_t ms, const int32_t* h_m,
+                       const double* h_theta, int n_theta, void* d_out, cudaStream_t s, const std::vector<int>& distinct,
+                       const std::vector<int>& slots, int n_groups) {
+    Scratch sc(s);
+    const unsigned grid = grid_for(n_items, 128);
+    const Cx<T>* src = static_cast<const Cx<T>*>(d_in);
+    T* dst = static_cast<T*>(d_out);
+    if (n_groups <= 32) {
+        const int k_slots = n_groups <= 8 ? 8 : (n_groups <= 16 ? 16 : 32);
+        const size_t tab_off = (sizeof(int) * (size_t)n_c + 15) & ~(size_t)15;
+        std::vector<unsigned char> blob(tab_off + sizeof(Cx<T>) * (size_t)n_theta * k_slots, 0);
+        memcpy(blob.data(), slots.data(), sizeof(int) * (size_t)n_c);
+        Cx<T>* tab = reinterpret_cast<Cx<T>*>(blob.data() + tab_off);
+        for (int t = 0; t < n_theta; ++t)
+            for (int g = 0; g < n_groups; ++g) {
+                tab[(size_t)t * k_slots + g].re = (T)cos(distinct[g] * h_theta[t]);
+                tab[(size_t)t * k_slots + g].im = (T)sin(distinct[g] * h_theta[t]);
+            }
+        int rc = sc.upload(blob.data(), blob.size());
+        if (rc) return rc;
+        const int* d_slot = static_cast<const int*>(sc.ptr);
+        const Cx<T>* d_tab = reinterpret_cast<const Cx<T>*>(static_cast<const unsigned char*>(sc.ptr) + tab_off);
+        if (k_slots == 8) mirror_grouped_kernel<T, 8><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
+        else if (k_slots == 16) mirror_grouped_kernel<T, 16><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
+        else mirror_grouped_kernel<T, 32><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
+        ZB_LAUNCHED();
+        return ZB200_OK;
+    }
+    std::vector<Cx<T>> tab((size_t)n_theta * n_c);
+    for (int t = 0; t < n_theta; ++t)
+        for (int c = 0; c < n_c; ++c) {
+            tab[(size_t)t * n_c + c].re = (T)cos(h_m[c] * h_theta[t]);
+            tab[(size_t)t * n_c + c].im = (T)sin(h_m[c] * h_theta[t]);
+        }
+    int rc = sc.upload(tab.data(), tab.size() * sizeof(Cx<T>));
+    if (rc) return rc;
+    mirror_kernel<T><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, static_cast<const Cx<T>*>(sc.ptr), n_theta, dst);
+    ZB_LAUNCHED();
+    return ZB200_OK;
+}
+
 extern "C" int zb200_mirror_scores(int dtype, const void* d_in, int64_t n_items, int n_c, int64_t is, int64_t ms,
                                    const int32_t* h_m, const double* h_theta, int n_theta, void* d_out, void* stream) {
     ZB_CHECK_ARG(d_in && d_out && h_m && h_theta && n_c > 0 && n_theta > 0 && n_items >= 0, "mirror_scores: bad arguments");
@@ -438,44 +482,9 @@ extern "C" int zb200_mirror_scores(int dtype, const void* d_in, int64_t n_items,
         slots[c] = sidx;
     }
     const int n_groups = (int)distinct.size();
-    Scratch sc(s);
-    if (n_groups <= 32) {
-        const int k_slots = n_groups <= 8 ? 8 : (n_groups <= 16 ? 16 : 32);
-        std::vector<unsigned char> blob(sizeof(int) * (size_t)n_c + 16 + sizeof(float2) * (size_t)n_theta * k_slots, 0);
-        const size_t tab_off = (sizeof(int) * (size_t)n_c + 15) & ~(size_t)15;
-        memcpy(blob.data(), slots.data(), sizeof(int) * (size_t)n_c);
-        float2* tab = reinterpret_cast<float2*>(blob.data() + tab_off);
-        for (int t = 0; t < n_theta; ++t)
-            for (int g = 0; g < n_groups; ++g)
-                tab[(size_t)t * k_slots + g] = make_float2((float)cos(distinct[g] * h_theta[t]), (float)sin(distinct[g] * h_theta[t]));
-        int rc = sc.upload(blob.data(), blob.size());
-        if (rc) return rc;
-        const int* d_slot = static_cast<const int*>(sc.ptr);
-        const float2* d_tab = reinterpret_cast<const float2*>(static_cast<const unsigned char*>(sc.ptr) + tab_off);
-        ZB_DISPATCH_DTYPE(dtype, {
-            const unsigned grid = grid_for(n_items, 128);
-            const Cx<T>* src = static_cast<const Cx<T>*>(d_in);
-            T* dst = static_cast<T*>(d_out);
-            if (k_slots == 8) mirror_grouped_kernel<T, 8><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
-            else if (k_slots == 16) mirror_grouped_kernel<T, 16><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
-            else mirror_grouped_kernel<T, 32><<<grid, 128, 0, s>>>(src, n_items, n_c, is, ms, d_slot, d_tab, n_theta, dst);
-        })
-        ZB_LAUNCHED();
-        return ZB200_OK;
-    }
-    std::vector<float2> tab((size_t)n_theta * n_c);
-    for (int t = 0; t < n_theta; ++t)
-        for (int c = 0; c < n_c; ++c)
-            tab[(size_t)t * n_c + c] = make_float2((float)cos(h_m[c] * h_theta[t]), (float)sin(h_m[c] * h_theta[t]));
-    int rc = sc.upload(tab.data(), tab.size() * sizeof(float2));
-    if (rc) return rc;
-    ZB_DISPATCH_DTYPE(dtype, {
-        mirror_kernel<T><<<grid_for(n_items, 128), 128, 0, s>>>(static_cast<const Cx<T>*>(d_in), n_items, n_c, is, ms,
-                                                              static_cast<const float2*>(sc.ptr), n_theta,
-                                                              static_cast<T*>(d_out));
-    })
-    ZB_LAUNCHED();
-    return ZB200_OK;
+    int rc = ZB200_OK;
+    ZB_DISPATCH_DTYPE(dtype, { rc = mirror_impl<T>(d_in, n_items, n_c, is, ms, h_m, h_theta, n_theta, d_out, s, distinct, slots, n_groups); })
+    return rc;
 }
 
 extern "C" int zb200_complex_abs_phase(int dtype, const void* d_in, int64_t n, void* d_abs, void* d_phase, void* stream) {

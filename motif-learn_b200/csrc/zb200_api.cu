@@ -64,12 +64,17 @@ const Knobs& knobs() {
 }
 
 // Stream-ordered scratch (score tables, operand planes of the dense map, peak-detection keys, shifted frame planes:
-// 0.1-0.6 GB per call at 2048^2..4096^2) comes from a PRIVATE memory pool per device: it keeps up to 8 GiB cached across
-// synchronisation points (a frame series allocates the same blocks again every frame, on several streams) without
-// touching the release threshold of the application's default pool.
+// 0.1-0.6 GB per call at 2048^2..4096^2, 6 GB for materialised 4096^2 moment maps) comes from a PRIVATE memory pool per
+// device that keeps its blocks cached across synchronisation points: a frame series allocates the same blocks again
+// every frame, on several streams, and a pool that trims at every synchronisation (a bounded release threshold, once
+// the cache has grown past it) turns each of them into a driver allocation -- measured: config 5 fell from 2700 to
+// 1700 frames/s after a 4096^2 map had run in the same process.  The application's default pool is never touched
+// (ADVICE r1); zb200_trim_scratch() hands the cache back.
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {};
 cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s) {
-    static std::mutex mu;
-    static cudaMemPool_t pools[64] = {};
+    std::mutex& mu = g_pool_mu;
+    cudaMemPool_t* pools = g_pools;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -85,7 +90,7 @@ cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s) {
             props.location.id = dev;
             cudaMemPool_t created = nullptr;
             if (cudaMemPoolCreate(&created, &props) == cudaSuccess) {
-                uint64_t keep = 8ull << 30;
+                uint64_t keep = UINT64_MAX;
                 cudaMemPoolSetAttribute(created, cudaMemPoolAttrReleaseThreshold, &keep);
                 pools[dev] = created;
             } else {
@@ -136,6 +141,17 @@ static void free_operand(Operand& op) {
 using namespace zb200;
 
 extern "C" int zb200_abi_version(void) { return ZB200_ABI_VERSION; }
+
+extern "C" int zb200_trim_scratch(void) {
+    int dev = 0;
+    ZB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (dev >= 0 && dev < 64 && g_pools[dev]) {
+        ZB_CUDA(cudaDeviceSynchronize());
+        ZB_CUDA(cudaMemPoolTrimTo(g_pools[dev], 0));
+    }
+    return ZB200_OK;
+}
 extern "C" const char* zb200_last_error(void) { return g_err; }
 extern "C" int64_t zb200_launch_count(void) { return g_launches.load(); }
 extern "C" void zb200_reset_launch_count(void) { g_launches.store(0); }

@@ -82,6 +82,7 @@ def release_plans(device=None) -> int:
         for key in [k for k in _plans if device is None or k[2] == device]:
             lib.zb200_plan_destroy(_plans.pop(key))
             freed += 1
+    lib.zb200_trim_scratch()          # the library's cached stream-ordered scratch of the current device
     return freed
 
 
