@@ -30,10 +30,27 @@ __device__ __forceinline__ uint32_t float_order(float f) {
 // [0] = min, [1] = max of the frame, as ordered uint32 (init: [0] = 0xFFFFFFFF, [1] = 0)
 __global__ void peaks_minmax_kernel(const float* __restrict__ img, long long n, uint32_t* __restrict__ mm) {
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const uint32_t o = float_order(__ldg(img + i));
-        lo = min(lo, o);
-        hi = max(hi, o);
+    const long long stride = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+        const long long n4 = n >> 2;
+        const float4* img4 = reinterpret_cast<const float4*>(img);
+        for (long long i = tid; i < n4; i += stride) {
+            const float4 v = __ldg(img4 + i);
+            const uint32_t a = float_order(v.x), b = float_order(v.y), c = float_order(v.z), d = float_order(v.w);
+            lo = min(min(lo, a), min(b, min(c, d)));
+            hi = max(max(hi, a), max(b, max(c, d)));
+        }
+        for (long long i = (n4 << 2) + tid; i < n; i += stride) {
+            const uint32_t o = float_order(__ldg(img + i));
+            lo = min(lo, o);
+            hi = max(hi, o);
+        }
+    } else {
+        for (long long i = tid; i < n; i += stride) {
+            const uint32_t o = float_order(__ldg(img + i));
+            lo = min(lo, o);
+            hi = max(hi, o);
+        }
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -47,35 +64,54 @@ __global__ void peaks_minmax_kernel(const float* __restrict__ img, long long n, 
 }
 
 // candidates -> keys (descending-intensity order in the high word, raster index in the low word)
-__global__ void peaks_candidates_kernel(const float* __restrict__ img, int H, int W, int has_thr, double thr,
-                                        const uint32_t* __restrict__ mm, unsigned long long* __restrict__ keys,
-                                        unsigned long long capacity, unsigned long long* __restrict__ count) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    bool hit = false;
-    float v = 0.f;
-    if (mm[0] != mm[1] && x >= 1 && y >= 1 && x < W - 1 && y < H - 1) {      // constant frame: no peaks (skimage)
-        const float* c = img + (size_t)y * W + x;
-        v = __ldg(c);
-        float m = v;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) m = fmaxf(m, __ldg(c + dy * W + dx));
-        // threshold None -> image.min(): compare in the ordered domain so the default needs no host round trip
-        const bool above = has_thr ? ((double)v > thr) : (float_order(v) > mm[0]);
-        hit = (v == m) && above;
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-    if (!ballot) return;
-    const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
-    unsigned long long base = 0;
-    if (lane == (__ffs(ballot) - 1)) base = atomicAdd(count, (unsigned long long)__popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-    if (hit) {
-        const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
-        if (slot < capacity)
-            keys[slot] = ((unsigned long long)(~float_order(v)) << 32) | (unsigned long long)((unsigned)y * (unsigned)W + (unsigned)x);
+// One warp walks a strip of 30 columns x kStripRows rows top-down: a lane loads ONE pixel per row, its neighbours come
+// from the lanes beside it (lanes 0 and 31 only carry the halo columns), the 3-row window lives in registers -- one
+// load, two shuffles and a handful of max per pixel instead of nine loads.
+constexpr int kStripRows = 32;
+__global__ void __launch_bounds__(128)
+peaks_candidates_kernel(const float* __restrict__ img, int H, int W, int has_thr, double thr,
+                        const uint32_t* __restrict__ mm, unsigned long long* __restrict__ keys,
+                        unsigned long long capacity, unsigned long long* __restrict__ count) {
+    if (mm[0] == mm[1]) return;                                     // constant frame: no peaks (skimage)
+    const int lane = threadIdx.x & 31;
+    const int strip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int x = strip * 30 + lane;                                // lanes 1..30 own columns; 0 and 31 are halo
+    const int y_begin = blockIdx.y * kStripRows;
+    if (strip * 30 + 1 >= W - 1) return;                            // warp-uniform: no interior column in this strip
+    const bool col_ok = x < W;
+    const int xc = col_ok ? x : W - 1;                              // clamp loads; such lanes never report a hit
+    const uint32_t floor_order = mm[0];
+    auto row_val = [&](int y) { return (y >= 0 && y < H) ? __ldg(img + (size_t)y * W + xc) : -INFINITY; };
+    auto hmax3 = [&](float v) {                                     // max of the lane's pixel and its two neighbours
+        const float l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
+        return fmaxf(v, fmaxf(l, r));
+    };
+    float v_mid = row_val(y_begin), h_top = hmax3(row_val(y_begin - 1)), h_mid = hmax3(v_mid);
+    const int y_end = min(y_begin + kStripRows, H);
+    for (int y = y_begin; y < y_end; ++y) {
+        const float v_bot = row_val(y + 1);
+        const float h_bot = hmax3(v_bot);
+        const float v = v_mid, m = fmaxf(h_mid, fmaxf(h_top, h_bot));
+        bool hit = false;
+        if (lane >= 1 && lane <= 30 && x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+            // threshold None -> image.min(): compare in the ordered domain so the default needs no host round trip
+            const bool above = has_thr ? ((double)v > thr) : (float_order(v) > floor_order);
+            hit = (v == m) && above;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (ballot) {
+            unsigned long long base = 0;
+            if (lane == (__ffs(ballot) - 1)) base = atomicAdd(count, (unsigned long long)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+            if (hit) {
+                const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+                if (slot < capacity)
+                    keys[slot] = ((unsigned long long)(~float_order(v)) << 32) | (unsigned long long)((unsigned)y * (unsigned)W + (unsigned)x);
+            }
+        }
+        h_top = h_mid;
+        h_mid = h_bot;
+        v_mid = v_bot;
     }
 }
 
@@ -87,7 +123,9 @@ __global__ void peaks_rank_kernel(const unsigned long long* __restrict__ keys, l
 // one sweep of the suppression fixed point; state: 0 undecided, 1 kept, 2 suppressed
 __global__ void peaks_nms_kernel(const unsigned long long* __restrict__ keys, long long n, const int* __restrict__ rank_map,
                                  int H, int W, int R, double r2, unsigned char* __restrict__ state,
-                                 unsigned int* __restrict__ undecided) {
+                                 unsigned int* __restrict__ undecided, const unsigned int* __restrict__ undecided_before) {
+    // undecided_before: the previous sweep's count (nullptr for the first sweep of a batch): 0 = already settled
+    if (undecided_before && *undecided_before == 0u) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || state[i] != 0) return;
     const uint32_t pix = (uint32_t)keys[i];
@@ -179,7 +217,7 @@ extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_
             const int blocks = (int)(ceil_div(n_pix, 256 * 8) < 1184 ? ceil_div(n_pix, 256 * 8) : 1184);
             peaks_minmax_kernel<<<blocks, 256, 0, s>>>(d_img, n_pix, mm);
             g_launches.fetch_add(1, std::memory_order_relaxed);
-            dim3 blk(32, 8), grd((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8));
+            dim3 blk(128), grd((unsigned)ceil_div(ceil_div(W, 30), 4), (unsigned)ceil_div(H, kStripRows));
             peaks_candidates_kernel<<<grd, blk, 0, s>>>(d_img, H, W, has_threshold, threshold, mm, keys0,
                                                         (unsigned long long)n_pix, count);
             g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -213,7 +251,8 @@ extern "C" int zb200_local_max_f32(const float* d_img, int H, int W, double min_
             for (int sweep = 0; sweep < kMaxSweeps && left != 0; sweep += kBatch) {
                 ZB_PEAKS_CUDA(cudaMemsetAsync(undecided, 0, sizeof(unsigned int) * kBatch, s));
                 for (int j = 0; j < kBatch; ++j) {
-                    peaks_nms_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(keys1, n, rank_map, H, W, R, r2, state, undecided + j);
+                    peaks_nms_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(keys1, n, rank_map, H, W, R, r2, state, undecided + j,
+                                                                                j ? undecided + j - 1 : nullptr);
                     g_launches.fetch_add(1, std::memory_order_relaxed);
                 }
                 ZB_PEAKS_CUDA(cudaMemcpyAsync(&left, undecided + (kBatch - 1), sizeof(left), cudaMemcpyDeviceToHost, s));
