@@ -848,7 +848,12 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
     prm.acc_bufs = 2 * cols + 2 * kUnitCols <= (int)kTmemCols ? 2 : 1;
     prm.n_units = ((int)kTmemCols - prm.acc_bufs * cols) / kUnitCols;
     if (prm.n_units > 4) prm.n_units = 4;
-    prm.chunk_sb = 8;
+    // accumulation chunks: the tensor core's fp32 accumulation truncates, so the accumulators are drained into
+    // round-to-nearest register sums every few super-blocks.  Measured (scripts/fold_chunk_probe.py, worst element
+    // against the gate / max error / time at 262 144 patches): 31 (no chunking) 1.27-1.72 -- FAILS -- / 5.4e-6;
+    // 8: 0.29 / 1.5e-6 / 0.699 ms; 4: 0.21 / 8.6e-7 / 0.699; 2: 0.13 / 5.6e-7 / 0.702 (n_max = 20, one accumulator
+    // set: 0.903 / 0.902 / 0.915 ms).
+    prm.chunk_sb = f.cfg == 0 ? 2 : 4;
     if (kn.tc_chunk) prm.chunk_sb = kn.tc_chunk;
     prm.park_ns = kn.tc_park == 0 ? 0u : kParkNs;
     const int bst = (cols / 2) * 128;
