@@ -81,10 +81,15 @@ private:
     std::deque<std::function<void()>> q_;
 };
 
+// float32 -> float64 of a range.  Plain cached stores on purpose: non-temporal stores (_mm_stream_pd) halve the
+// widening itself (3.4 -> 1.1 ms per 8 frames) but the frame route as a whole got SLOWER with them -- the |Zc| route
+// from 4.0 to 7.0 ms per 8 frames, the GPU-side completions arriving late while the write-combining traffic and the
+// D2H DMA writes share the memory controller (measured with ZB200_HOST_TRACE, profiles/r02_e2e_host_route_probe.log).
+static void widen_range(const float* src, double* dst, int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) dst[i] = (double)src[i];
+}
 void widen_parallel(const float* src, double* dst, int64_t n) {
-    HostPool::get().parallel_for(n, 1 << 16, [=](int64_t a, int64_t b) {
-        for (int64_t i = a; i < b; ++i) dst[i] = (double)src[i];
-    });
+    HostPool::get().parallel_for(n, 1 << 16, [=](int64_t a, int64_t b) { widen_range(src, dst, a, b); });
 }
 void copy_parallel(void* dst, const void* src, size_t bytes) {
     HostPool::get().parallel_for((int64_t)bytes, 1 << 20, [=](int64_t a, int64_t b) {
@@ -213,6 +218,9 @@ struct HostPipe {
     void* dev_in[kSlots] = {};   size_t dev_in_cap[kSlots] = {};
     void* dev_pat[kSlots] = {};  size_t dev_pat_cap[kSlots] = {};
     void* dev_pts[kSlots] = {};  size_t dev_pts_cap[kSlots] = {};
+    void* pin_pts[kSlots] = {};  size_t pin_pts_cap[kSlots] = {};   // peak lists are staged through pinned memory: an async
+                                                                    // copy from the caller's pageable list blocks the enqueuing
+                                                                    // thread until the frame copy in front of it has finished
     void* dev_out[kSlots] = {};  size_t dev_out_cap[kSlots] = {};
 };
 
@@ -222,6 +230,7 @@ void free_host_pipe(zb200_plan* p) {
     for (int i = 0; i < kSlots; ++i) {
         if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
         if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
+        if (h->pin_pts[i]) cudaFreeHost(h->pin_pts[i]);
         cudaFree(h->dev_in[i]);
         cudaFree(h->dev_pat[i]);
         cudaFree(h->dev_pts[i]);
@@ -348,6 +357,7 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
         if ((rc = ensure_buf(&h->pin_out[b], &h->pin_out_cap[b], sizeof(float) * max_count * L, kPinned))) return rc;
         if ((rc = ensure_buf(&h->dev_in[b], &h->dev_in_cap[b], frame_bytes, kDevice))) return rc;
         if ((rc = ensure_buf(&h->dev_pts[b], &h->dev_pts_cap[b], sizeof(double) * 2 * max_count, kDevice))) return rc;
+        if ((rc = ensure_buf(&h->pin_pts[b], &h->pin_pts_cap[b], sizeof(double) * 2 * max_count, kPinned))) return rc;
         if (!fused_gather && (rc = ensure_buf(&h->dev_pat[b], &h->dev_pat_cap[b], sizeof(float) * max_count * p->kk, kDevice))) return rc;
         if ((rc = ensure_buf(&h->dev_out[b], &h->dev_out_cap[b], sizeof(float) * max_count * L, kDevice))) return rc;
     }
@@ -362,7 +372,8 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
         }
         ZB_CUDA(cudaMemcpyAsync(h->dev_in[b], src, frame_bytes, cudaMemcpyHostToDevice, h->st[b]));
         if (cnt > 0) {
-            ZB_CUDA(cudaMemcpyAsync(h->dev_pts[b], h_pts_xy + 2 * first[f], sizeof(double) * 2 * (size_t)cnt,
+            memcpy(h->pin_pts[b], h_pts_xy + 2 * first[f], sizeof(double) * 2 * (size_t)cnt);
+            ZB_CUDA(cudaMemcpyAsync(h->dev_pts[b], h->pin_pts[b], sizeof(double) * 2 * (size_t)cnt,
                                     cudaMemcpyHostToDevice, h->st[b]));
             int r;
             if (fused_gather) {

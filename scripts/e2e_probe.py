@@ -23,6 +23,14 @@ def run(label, fn, reps=4):
     for _ in range(reps): fn()
     dt = (time.perf_counter() - t0) / reps
     print(f"{label}: {dt*1e3:.2f} ms per call of {nf} frames -> {n/dt/1e6:.1f} M patches/s", flush=True)
+only = os.environ.get("PROBE_ONLY", "")
+if only == "abs":
+    bufa = np.zeros((n, 49))
+    run("pinned frames, abs features, reused out (first)", lambda: z.transform_peaks_batch(frames, pts_list, "abs", out=bufa))
+    buf = np.zeros((n, 91))
+    run("pinned frames, reused out", lambda: z.transform_peaks_batch(frames, pts_list, out=buf))
+    run("pinned frames, abs features, reused out (again)", lambda: z.transform_peaks_batch(frames, pts_list, "abs", out=bufa))
+    sys.exit(0)
 run("pinned frames, fresh out", lambda: z.transform_peaks_batch(frames, pts_list))
 buf = np.zeros((n, 91))
 run("pinned frames, reused out", lambda: z.transform_peaks_batch(frames, pts_list, out=buf))
