@@ -985,9 +985,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # N ranks share one host: give each rank's host pipeline (staging copies, float64 widening) its share of the
-        # cores instead of the single-process default (half the hardware threads, at most 16, PER process)
-        os.environ.setdefault("ZB200_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 8) // (2 * world)))))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout when the communicator is created; stdout must carry
         # exactly one JSON line, so route fd 1 to stderr until the first collective has run
