@@ -15,4 +15,6 @@ echo "map_h rc=$?"
 CMD3="python bench.py --workload c3 --no-also --no-cpu --steps 2 --warmup 3 --c3-total 262144"
 $CMD3 > $OUT/bench_prof_c3.json 2>/dev/null && ncu --set full --clock-control none --import-source on -k regex:project_fold -s 2 -c 1 -f -o $OUT/prof_c3 $CMD3 > $OUT/ncu_c3.log 2>&1
 echo "c3 rc=$?"
+python scripts/fused_gather_probe.py > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:project_fold -s 2 -c 1 -f -o $OUT/prof_foldg python scripts/fused_gather_probe.py > $OUT/ncu_foldg.log 2>&1
+echo "fold+gather rc=$?"
 ls -la $OUT | grep -E "prof|launches"
