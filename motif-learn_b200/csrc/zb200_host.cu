@@ -132,6 +132,7 @@ int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drai
     const bool trace = host_trace();
     double t_enq = 0, t_slot = 0, t_evsync = 0, t_drain = 0;
     const double t_begin = now_ms();
+    std::vector<double> tl(trace ? (size_t)n_items * 4 : 0, 0.0);     // per item: enqueue begin / end, event ready, drained
     std::thread drainer([&] {
         cudaSetDevice(device);
         for (int64_t c = 0; c < n_items; ++c) {
@@ -150,7 +151,7 @@ int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drai
             } else {
                 r = drain(c, (int)(c % kSlots));
             }
-            if (trace) { t_evsync += t1 - t0; t_drain += now_ms() - t1; }
+            if (trace) { t_evsync += t1 - t0; t_drain += now_ms() - t1; tl[(size_t)c * 4 + 2] = t1 - t_begin; tl[(size_t)c * 4 + 3] = now_ms() - t_begin; }
             std::lock_guard<std::mutex> lk(ps.m);
             if (r) { ps.rc = r; ps.msg = zb200_last_error(); }
             ps.drained = c + 1;
@@ -167,7 +168,7 @@ int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drai
         }
         const double t1 = trace ? now_ms() : 0;
         const int r = enq(c, (int)(c % kSlots));
-        if (trace) { t_slot += t1 - t0; t_enq += now_ms() - t1; }
+        if (trace) { t_slot += t1 - t0; t_enq += now_ms() - t1; tl[(size_t)c * 4] = t1 - t_begin; tl[(size_t)c * 4 + 1] = now_ms() - t_begin; }
         std::lock_guard<std::mutex> lk(ps.m);
         if (r) { ps.rc = r; ps.msg = zb200_last_error(); }
         else ps.enqueued = c + 1;
@@ -178,6 +179,10 @@ int run_pipeline(int device, int64_t n_items, cudaEvent_t* ev, Enqueue enq, Drai
     if (trace)
         fprintf(stderr, "[zb200 host pipeline] items %lld total %.2f ms | main: enqueue %.2f, waiting for a slot %.2f | drainer: "
                 "event wait %.2f, drain %.2f\n", (long long)n_items, now_ms() - t_begin, t_enq, t_slot, t_evsync, t_drain);
+    if (trace && getenv("ZB200_HOST_TRACE")[0] == '2')
+        for (int64_t c = 0; c < n_items; ++c)
+            fprintf(stderr, "    item %2lld: enqueue %.2f..%.2f  event ready %.2f  drained %.2f\n", (long long)c, tl[(size_t)c * 4],
+                    tl[(size_t)c * 4 + 1], tl[(size_t)c * 4 + 2], tl[(size_t)c * 4 + 3]);
     if (ps.rc) {
         set_error("%s", ps.msg.c_str());
         cudaDeviceSynchronize();                     // nothing of this call is left in flight on the staging buffers
@@ -212,6 +217,11 @@ int ensure_buf(void** ptr, size_t* cap, size_t need, BufKind kind) {
 struct HostPipe {
     cudaStream_t st[kSlots] = {};
     cudaEvent_t ev[kSlots] = {};
+    // ALL uploads go through one stream, in item order: with one upload per slot stream the copy engine interleaves
+    // the queued 16.8 MB frame copies, all of them finish together and late (ZB200_HOST_TRACE=2: the second frame of a
+    // call was ready 0.95 ms after the first instead of 0.31 ms); up_ev[slot] hands the item over to its slot stream
+    cudaStream_t up = nullptr;
+    cudaEvent_t up_ev[kSlots] = {};
     // per slot: input staging (pinned), result staging (pinned), device input, device patches, device points, device result
     void* pin_in[kSlots] = {};   size_t pin_in_cap[kSlots] = {};
     void* pin_out[kSlots] = {};  size_t pin_out_cap[kSlots] = {};
@@ -236,8 +246,10 @@ void free_host_pipe(zb200_plan* p) {
         cudaFree(h->dev_pts[i]);
         cudaFree(h->dev_out[i]);
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+        if (h->up_ev[i]) cudaEventDestroy(h->up_ev[i]);
         if (h->st[i]) cudaStreamDestroy(h->st[i]);
     }
+    if (h->up) cudaStreamDestroy(h->up);
     delete h;
     p->host = nullptr;
 }
@@ -247,8 +259,10 @@ static int host_pipe(zb200_plan* p, HostPipe** out) {
         HostPipe* h = new (std::nothrow) HostPipe();
         if (!h) { set_error("out of host memory"); return ZB200_ENOMEM; }
         p->host = h;
+        bool ok = cudaStreamCreateWithFlags(&h->up, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < kSlots; ++i) {
-            if (cudaStreamCreateWithFlags(&h->st[i], cudaStreamNonBlocking) != cudaSuccess ||
+            if (!ok || cudaStreamCreateWithFlags(&h->st[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->up_ev[i], cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) {
                 set_error("host pipeline: cannot create stream/event: %s", cudaGetErrorString(cudaGetLastError()));
                 free_host_pipe(p);                   // nothing half-built is kept
@@ -301,7 +315,9 @@ extern "C" int zb200_project_patches_host(const zb200_plan* plan, const float* h
             copy_parallel(h->pin_in[b], src, in_bytes);
             src = static_cast<const float*>(h->pin_in[b]);
         }
-        ZB_CUDA(cudaMemcpyAsync(h->dev_in[b], src, in_bytes, cudaMemcpyHostToDevice, h->st[b]));
+        ZB_CUDA(cudaMemcpyAsync(h->dev_in[b], src, in_bytes, cudaMemcpyHostToDevice, h->up));
+        ZB_CUDA(cudaEventRecord(h->up_ev[b], h->up));
+        ZB_CUDA(cudaStreamWaitEvent(h->st[b], h->up_ev[b], 0));
         int r = project_any(p, static_cast<const float*>(h->dev_in[b]), cnt, precision, ZB200_OUT_REAL, h->dev_out[b],
                             nullptr, nullptr, nullptr, 0, 0, h->st[b]);
         if (r) return r;
@@ -370,11 +386,15 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
             copy_parallel(h->pin_in[b], src, frame_bytes);
             src = static_cast<const float*>(h->pin_in[b]);
         }
-        ZB_CUDA(cudaMemcpyAsync(h->dev_in[b], src, frame_bytes, cudaMemcpyHostToDevice, h->st[b]));
         if (cnt > 0) {
             memcpy(h->pin_pts[b], h_pts_xy + 2 * first[f], sizeof(double) * 2 * (size_t)cnt);
             ZB_CUDA(cudaMemcpyAsync(h->dev_pts[b], h->pin_pts[b], sizeof(double) * 2 * (size_t)cnt,
-                                    cudaMemcpyHostToDevice, h->st[b]));
+                                    cudaMemcpyHostToDevice, h->up));
+        }
+        ZB_CUDA(cudaMemcpyAsync(h->dev_in[b], src, frame_bytes, cudaMemcpyHostToDevice, h->up));
+        ZB_CUDA(cudaEventRecord(h->up_ev[b], h->up));
+        ZB_CUDA(cudaStreamWaitEvent(h->st[b], h->up_ev[b], 0));
+        if (cnt > 0) {
             int r;
             if (fused_gather) {
                 r = zb200_project_peaks_f32(p, static_cast<const float*>(h->dev_in[b]), H, W, static_cast<const double*>(h->dev_pts[b]),
