@@ -1075,6 +1075,33 @@ def test_folded_projection_auto_range_and_fallback(api, torch, n_max, count):
     assert torch.equal(z.transform(torch.zeros((3, size, size), device="cuda")).data, torch.zeros((3, len(n)), device="cuda"))
 
 
+def test_folded_projection_ragged_counts_and_properties(api, torch):
+    """Tile edges of the folded kernel (128-patch tiles, CTA pairs: counts around 1, 128 and 256, an odd number of
+    tiles), every epilogue, linearity, and invariance under a permutation of the patches."""
+    rng = np.random.default_rng(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        n, m, v = zo.zernike_basis(12, 64)
+    z, zh = api.ZPs(12, 64), api.ZPs(12, 64, value_max=1.0)
+    base = rng.random((700, 64, 64), dtype=np.float32)
+    ref_all = zo.project_patches(base.astype(np.float64), v)
+    for count in (1, 2, 127, 128, 129, 255, 256, 257, 385, 700):
+        dev = torch.from_numpy(base[:count]).cuda()
+        for tr in (z, zh):
+            got = tr.transform(dev).data
+            assert got.shape == (count, 91)
+            fp32_close(got.cpu().numpy(), ref_all[:count])
+        refc = zo.to_complex(ref_all[:count], n, m)[0]
+        mag, ph = zh.transform_features(dev, "abs_phase")
+        assert np.abs(mag.cpu().numpy() - np.abs(refc)).max() <= 3e-6 * np.abs(refc).max()
+    dev = torch.from_numpy(base).cuda()
+    perm = torch.from_numpy(rng.permutation(700)).cuda()
+    assert torch.equal(zh.transform(dev[perm].contiguous()).data, zh.transform(dev).data[perm])    # a patch's result does not depend on its tile
+    a, b = dev[:300], dev[300:600]
+    za, zb, zab = (zh.transform(t).data for t in (a, b, (0.5 * a + 0.25 * b).contiguous()))
+    assert (zab - (0.5 * za + 0.25 * zb)).abs().max().item() < 2e-6 * float(np.abs(ref_all).max())
+
+
 def test_mirror_map_in_row_bands(api, golden, torch):
     """ZPs.mirror_map streams the frame through K4 + the mirror kernel band by band (the (M,H,W) maps never exist in
     full): equal to the materialised route bit for bit, and to the live reference's mirror_map at the golden pixels."""
