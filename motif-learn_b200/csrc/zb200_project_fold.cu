@@ -68,6 +68,10 @@ template <> struct Regs<1, true> { static constexpr int ctl = 40, split = 128, e
 struct Params {
     long long n_patches;
     int n_tiles;              // 128-patch tiles
+    // balanced partition (gathering form; 0 = tiles dealt round-robin): CTA b owns rows [b R, (b+1) R) and walks them in
+    // 128-row tiles -- a frame's ~21 k windows are 164 tiles on 148 CTAs, i.e. two full tile times round-robin, but 1.1
+    // when every CTA takes 141 rows (rows past its range are zero-filled copies that touch no memory)
+    long long rows_per_cta;
     int sb_count;             // super-blocks (32 folded taps) with taps inside the unit disk
     const unsigned short* sb_list;   // their indices (window row i = sb / nj, 32-tap column block jb = sb % nj), ascending
     const unsigned char* umask;   // per super-block (absolute index): bit h = its 16-tap unit h holds taps of the unit disk
@@ -172,7 +176,9 @@ __device__ __forceinline__ void epilogue_pair(const Params& p, uint32_t tmem_bas
     constexpr int kCC = kRe + kIm;
     uint32_t ck = 0;
     for (int t = 0; t < my_tiles; ++t) {
-        const long long row = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTileRows + q * 32 + lane;
+        const long long row = (p.rows_per_cta ? (long long)blockIdx.x * p.rows_per_cta + (long long)t * kTileRows
+                                              : ((long long)blockIdx.x + (long long)t * gridDim.x) * kTileRows) + q * 32 + lane;
+        const long long row_end = p.rows_per_cta ? min(p.n_patches, ((long long)blockIdx.x + 1) * p.rows_per_cta) : p.n_patches;
         float sum[kCC][16];
 #pragma unroll
         for (int cc = 0; cc < kCC; ++cc)
@@ -198,7 +204,7 @@ __device__ __forceinline__ void epilogue_pair(const Params& p, uint32_t tmem_bas
                 else mbar_arrive(&acc_empty[buf]);
             }
         }
-        if (row < p.n_patches) {
+        if (row < row_end) {
             const float sc = out_scale;
             if (p.flag) {
                 uint32_t worst = 0;
@@ -304,7 +310,8 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lo_base = tmem_base + (uint32_t)(p.acc_bufs * kCols);
     const uint32_t crank = cluster_rank();
-    const int my_tiles = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;     // lock-step within the pair
+    const int my_tiles = p.rows_per_cta ? (int)((p.rows_per_cta + kTileRows - 1) / kTileRows)
+                                        : (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;     // lock-step within the pair
     const int n_chunks = (p.sb_count + p.chunk_sb - 1) / p.chunk_sb;
     float x_scale = p.x_scale, out_scale = p.out_scale;
     if (p.absmax) {
@@ -510,9 +517,11 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         const unsigned x_hi = (unsigned)(p.g_Wp - 4);
         for (int t = 0; t < my_tiles; ++t) {
-            const long long base = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTileRows + gw * 32;
+            const long long base = (p.rows_per_cta ? (long long)blockIdx.x * p.rows_per_cta + (long long)t * kTileRows
+                                                   : ((long long)blockIdx.x + (long long)t * gridDim.x) * kTileRows) + gw * 32;
+            const long long row_end = p.rows_per_cta ? min(p.n_patches, ((long long)blockIdx.x + 1) * p.rows_per_cta) : p.n_patches;
             int2 cn = make_int2(-(1 << 28), -(1 << 28));               // rows past the end: every copy zero-fills
-            if (base + lane < p.n_patches) cn = __ldg(p.g_xy + base + lane);
+            if (base + lane < row_end) cn = __ldg(p.g_xy + base + lane);
             const float* row_ptr[8];      // plane (x0 & 3), frame row y0, padded column x0 - (x0 & 3) + g_L + 4 ch
             int row_y[8], row_x[8];
 #pragma unroll
@@ -880,6 +889,7 @@ int project_fold(const zb200_plan* p, const float* d_patches, int64_t n, int out
     int grid = prm.n_tiles < p->sm_count ? prm.n_tiles : p->sm_count;
     grid = (grid / 2) * 2;
     if (grid < 2) grid = 2;
+    if (gsrc) prm.rows_per_cta = ceil_div(n, grid);          // the pusher (round-robin tiles) is never combined with the gather
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(512);
