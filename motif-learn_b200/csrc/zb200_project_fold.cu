@@ -62,8 +62,9 @@ template <int kCfg, bool kGather> struct Regs;   // setmaxnreg budgets: (ctl + s
 template <> struct Regs<0, false> { static constexpr int ctl = 48, split = 152, epi_a = 152, epi_b = 152, gather = 0; };
 template <> struct Regs<1, false> { static constexpr int ctl = 48, split = 96, epi_a = 200, epi_b = 168, gather = 0; };   // 144 / 128 running sums
 // K2 fused (a fifth warpgroup gathers the windows): 640 threads start with 96 registers, the pool is 480 x 128
-template <> struct Regs<0, true> { static constexpr int ctl = 40, split = 128, epi_a = 120, epi_b = 120, gather = 72; };
-template <> struct Regs<1, true> { static constexpr int ctl = 40, split = 128, epi_a = 120, epi_b = 120, gather = 72; };   // never launched
+// and the warpgroups are [splitter | splitter | epilogue (both class pairs, 128 running sums) | control | gather]
+template <> struct Regs<0, true> { static constexpr int ctl = 40, split = 96, epi_a = 176, epi_b = 176, gather = 72; };
+template <> struct Regs<1, true> { static constexpr int ctl = 40, split = 96, epi_a = 176, epi_b = 176, gather = 72; };   // never launched
 
 struct Params {
     long long n_patches;
@@ -169,11 +170,14 @@ __global__ void range_sample_kernel(const float* __restrict__ x, long long n, in
 // The thread owns one patch: running fp32 sums of the K chunks (round-to-nearest adds; the tensor core's own fp32
 // accumulation truncates), then the store path of kOut.  Columns are class-ordered, so real moments go out through
 // the column -> mode table and complex ones pair chunk cc of X_re with chunk cc of X_im.
-template <int kOut, int kRe, int kIm>
+// kPairs = 2 (the gathering form, n_max <= 13): ONE epilogue warpgroup owns both class pairs (A then B, equal widths),
+// because its second warpgroup's threads went to a second splitter warpgroup.
+template <int kOut, int kRe, int kIm, int kPairs = 1>
 __device__ __forceinline__ void epilogue_pair(const Params& p, uint32_t tmem_base, int n_cols, int col0, int g, int q, int lane,
                                               bool remote, uint64_t* acc_full, uint64_t* acc_empty, unsigned* out_done,
                                               int my_tiles, int n_chunks, float out_scale) {
-    constexpr int kCC = kRe + kIm;
+    constexpr int kCP = kRe + kIm;            // chunks of one pair
+    constexpr int kCC = kPairs * kCP;
     uint32_t ck = 0;
     for (int t = 0; t < my_tiles; ++t) {
         const long long row = (p.rows_per_cta ? (long long)blockIdx.x * p.rows_per_cta + (long long)t * kTileRows
@@ -224,15 +228,16 @@ __device__ __forceinline__ void epilogue_pair(const Params& p, uint32_t tmem_bas
                         if (j >= 0) dst[j] = sum[cc][i] * sc;
                     }
             } else {
-                const short* slot = p.slot_cplx + g * kSlotMax;
+#pragma unroll
+                for (int pr = 0; pr < kPairs; ++pr)
 #pragma unroll
                 for (int cc = 0; cc < kRe; ++cc)
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int c = __ldg(slot + cc * 16 + i);
+                        const int c = __ldg(p.slot_cplx + (g + pr) * kSlotMax + cc * 16 + i);
                         if (c < 0) continue;
-                        const float re = sum[cc][i] * sc;
-                        const float im = cc < kIm ? sum[(cc < kIm ? kRe + cc : 0)][i] * sc : 0.f;
+                        const float re = sum[pr * kCP + cc][i] * sc;
+                        const float im = cc < kIm ? sum[pr * kCP + (cc < kIm ? kRe + cc : 0)][i] * sc : 0.f;
                         if constexpr (kOut == kOutPlain) {
                             *reinterpret_cast<float2*>(p.out + row * (long long)p.row_len + 2 * c) = make_float2(re, im);
                         } else {
@@ -284,7 +289,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&xfull[s], kGather ? 128 : 1);     // gathered: every gathering thread's copies have landed
-            mbar_init(&xempty[s], 4);
+            mbar_init(&xempty[s], kGather ? 8 : 4);      // gathering form: two splitter warpgroups read a stage
         }
         for (int b = 0; b < 4; ++b) {
             mbar_init(&bfull[b], 1);
@@ -295,7 +300,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 16);
+            mbar_init(&acc_empty[b], kGather ? 8 : 16);  // epilogue warps of both CTAs (one warpgroup each when gathering)
         }
         fence_barrier_init();
     }
@@ -428,12 +433,15 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         } else if (warp == kWarpAlloc && p.n_peers) {
             pusher_loop(p, out_done, 8, my_tiles, lane, smem + p.push_off, kTileRows);
         }
-    } else if (wg == 0) {
+    } else if (wg == 0 || (kGather && wg == 1)) {
         // ===================== butterfly + fp16 split, one patch row per thread =====================
+        // gathering form: TWO splitter warpgroups take the active units in turn (a unit is ~0.8 us of one warp's
+        // instruction chain per sub-partition; fed from L2 instead of HBM that chain, not the data, paced the tile)
         if constexpr (Regs<kCfg, kGather>::split > (kGather ? 96 : 128)) reg_inc<Regs<kCfg, kGather>::split>();
         else reg_dec<Regs<kCfg, kGather>::split>();
-        const int r = warp * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t unit_no = 0;             // running count of active units: warpgroup wg owns those with unit_no % 2 == wg
         const uint32_t swz = (uint32_t)(r & 7) << 4;
         const uint32_t row_u32 = smem_u32(smem) + (uint32_t)r * 128u;
         const uint64_t sc2 = pk2(x_scale, x_scale);
@@ -449,6 +457,10 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (!((um >> h) & 1u)) continue;
+                    if (kGather && (int)(unit_no++ & 1u) != wg) {          // the other splitter warpgroup's unit
+                        if (++u == p.n_units) { u = 0; uph ^= 1u; }
+                        continue;
+                    }
                     // folded taps e = 16h .. 16h+15 of the super-block: a = row i, b = its mirror (box 1, tap 31-e),
                     // c = row i', d = its mirror (box 3)
                     float4 A[4], B[4], C[4], D[4];
@@ -522,6 +534,9 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const long long row_end = p.rows_per_cta ? min(p.n_patches, ((long long)blockIdx.x + 1) * p.rows_per_cta) : p.n_patches;
             int2 cn = make_int2(-(1 << 28), -(1 << 28));               // rows past the end: every copy zero-fills
             if (base + lane < row_end) cn = __ldg(p.g_xy + base + lane);
+            // all 32 windows of this warp valid and fully inside the frame?  (padded planes: x0 in [0, W - k], y0 in [0, H - k])
+            const bool interior = __all_sync(0xffffffffu, base + lane < row_end && cn.x >= 0 && cn.y >= 0 &&
+                                                              cn.x + p.k <= p.g_Wp - 2 * p.g_L && cn.y + p.k <= p.g_H);
             const float* row_ptr[8];      // plane (x0 & 3), frame row y0, padded column x0 - (x0 & 3) + g_L + 4 ch
             int row_y[8], row_x[8];
 #pragma unroll
@@ -547,11 +562,19 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     const int wc = (box & 1) ? p.k - 32 - jb * 32 : jb * 32;
                     const long long off = (long long)wr * p.g_Wp + wc;
                     const uint32_t xb = xs + (uint32_t)box * 16384u;
+                    if (interior) {
+                        // every window of this warp lies inside the frame (what clear_border leaves): no range checks --
+                        // the gather warps' instruction stream, at ~15 instructions per copy, paced the whole tile
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const bool inb = (unsigned)(row_y[it] + wr) < (unsigned)p.g_H && (unsigned)(row_x[it] + wc) <= x_hi;
-                        const float* gp = inb ? row_ptr[it] + off : p.g_planes;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xb + dst_row[it]), "l"(gp), "r"(inb ? 16 : 0) : "memory");
+                        for (int it = 0; it < 8; ++it)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xb + dst_row[it]), "l"(row_ptr[it] + off) : "memory");
+                    } else {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const bool inb = (unsigned)(row_y[it] + wr) < (unsigned)p.g_H && (unsigned)(row_x[it] + wc) <= x_hi;
+                            const float* gp = inb ? row_ptr[it] + off : p.g_planes;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xb + dst_row[it]), "l"(gp), "r"(inb ? 16 : 0) : "memory");
+                        }
                     }
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&xfull[s])) : "memory");
@@ -561,9 +584,13 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     } else {
         // ===================== epilogue: warpgroup 1 owns the class pair A, warpgroup 2 the pair B =====================
         const int g = wg - 1, q = warp & 3;
-        if (g == 0) reg_inc<Regs<kCfg, kGather>::epi_a>();
+        if (g == 0 || kGather) reg_inc<Regs<kCfg, kGather>::epi_a>();
         else reg_inc<Regs<kCfg, kGather>::epi_b>();
-        if (g == 0)
+        if constexpr (kGather) {
+            // warpgroup 2 alone: both class pairs (cfg 0: four classes of equal width)
+            epilogue_pair<kOut, cls_w(kCfg, 0) / 16, cls_w(kCfg, 0) / 16, 2>(p, tmem_base, kCols, 0, 0, q, lane, crank != 0,
+                                                                            acc_full, acc_empty, out_done, my_tiles, n_chunks, out_scale);
+        } else if (g == 0)
             epilogue_pair<kOut, cls_w(kCfg, 0) / 16, cls_w(kCfg, 1) / 16>(p, tmem_base, kCols, cls_off(kCfg, 0), 0, q, lane, crank != 0,
                                                                           acc_full, acc_empty, out_done, my_tiles, n_chunks, out_scale);
         else
