@@ -59,12 +59,11 @@ __device__ __forceinline__ void wait_idle(uint64_t* bar, uint32_t parity, uint32
 }
 
 template <int kCfg, bool kGather> struct Regs;   // setmaxnreg budgets: (ctl + split + epi_a + epi_b) * 128 <= 64 Ki
-template <> struct Regs<0, false> { static constexpr int ctl = 48, split = 152, epi_a = 152, epi_b = 152, gather = 0; };
+template <> struct Regs<0, false> { static constexpr int ctl = 48, split = 144, epi_a = 176, epi_b = 176, gather = 0; };   // [split | split | epilogue | control]
 template <> struct Regs<1, false> { static constexpr int ctl = 48, split = 96, epi_a = 200, epi_b = 168, gather = 0; };   // 144 / 128 running sums
 // K2 fused (a fifth warpgroup gathers the windows): 640 threads start with 96 registers, the pool is 480 x 128
 // and the warpgroups are [splitter | splitter | epilogue (both class pairs, 128 running sums) | control | gather]
 template <> struct Regs<0, true> { static constexpr int ctl = 40, split = 96, epi_a = 176, epi_b = 176, gather = 72; };
-template <> struct Regs<1, true> { static constexpr int ctl = 40, split = 96, epi_a = 176, epi_b = 176, gather = 72; };   // never launched
 
 struct Params {
     long long n_patches;
@@ -260,6 +259,12 @@ template <int kOut, int kCfg, bool kGather>
 __global__ void __launch_bounds__(kGather ? 640 : 512, 1)
 project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    // n_max <= 13 (128 accumulator columns): warpgroups [splitter | splitter | epilogue for both class pairs | control
+    // (| gather)]; n_max <= 20 (272 columns, two epilogue warpgroups of running sums): [splitter | epilogue A | epilogue B |
+    // control].  A unit is ~0.8 us of ONE warp's instruction chain per sub-partition -- 45 us per tile against 49 us of HBM
+    // time at full clock, but the chain stretches with the SM clock under the power cap while HBM does not.
+    constexpr bool kTwoSplit = kCfg == 0;
+    static_assert(!kGather || kTwoSplit, "the gathering form exists for n_max <= 13 only");
     constexpr int kCols = cfg_cols(kCfg);
     constexpr uint32_t kBStage = (uint32_t)(kCols / 2) * 128u;    // this CTA's half of the class rows, one super-block
     uint8_t* b_ring = smem + (size_t)p.n_stages * kXStage;
@@ -289,7 +294,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(&xfull[s], kGather ? 128 : 1);     // gathered: every gathering thread's copies have landed
-            mbar_init(&xempty[s], kGather ? 8 : 4);      // gathering form: two splitter warpgroups read a stage
+            mbar_init(&xempty[s], kTwoSplit ? 8 : 4);    // the splitter warps of one or two warpgroups read a stage
         }
         for (int b = 0; b < 4; ++b) {
             mbar_init(&bfull[b], 1);
@@ -300,7 +305,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], kGather ? 8 : 16);  // epilogue warps of both CTAs (one warpgroup each when gathering)
+            mbar_init(&acc_empty[b], kTwoSplit ? 8 : 16);  // epilogue warps of both CTAs (one or two warpgroups each)
         }
         fence_barrier_init();
     }
@@ -431,12 +436,11 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             __syncwarp();
         } else if (warp == kWarpAlloc && p.n_peers) {
-            pusher_loop(p, out_done, 8, my_tiles, lane, smem + p.push_off, kTileRows);
+            pusher_loop(p, out_done, kTwoSplit ? 4 : 8, my_tiles, lane, smem + p.push_off, kTileRows);
         }
-    } else if (wg == 0 || (kGather && wg == 1)) {
+    } else if (wg == 0 || (kTwoSplit && wg == 1)) {
         // ===================== butterfly + fp16 split, one patch row per thread =====================
-        // gathering form: TWO splitter warpgroups take the active units in turn (a unit is ~0.8 us of one warp's
-        // instruction chain per sub-partition; fed from L2 instead of HBM that chain, not the data, paced the tile)
+        // kTwoSplit: two splitter warpgroups take the active units in turn
         if constexpr (Regs<kCfg, kGather>::split > (kGather ? 96 : 128)) reg_inc<Regs<kCfg, kGather>::split>();
         else reg_dec<Regs<kCfg, kGather>::split>();
         const int r = (warp & 3) * 32 + lane;
@@ -457,7 +461,7 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (!((um >> h) & 1u)) continue;
-                    if (kGather && (int)(unit_no++ & 1u) != wg) {          // the other splitter warpgroup's unit
+                    if (kTwoSplit && (int)(unit_no++ & 1u) != wg) {        // the other splitter warpgroup's unit
                         if (++u == p.n_units) { u = 0; uph ^= 1u; }
                         continue;
                     }
@@ -584,9 +588,9 @@ project_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     } else {
         // ===================== epilogue: warpgroup 1 owns the class pair A, warpgroup 2 the pair B =====================
         const int g = wg - 1, q = warp & 3;
-        if (g == 0 || kGather) reg_inc<Regs<kCfg, kGather>::epi_a>();
+        if (g == 0 || kTwoSplit) reg_inc<Regs<kCfg, kGather>::epi_a>();
         else reg_inc<Regs<kCfg, kGather>::epi_b>();
-        if constexpr (kGather) {
+        if constexpr (kTwoSplit) {
             // warpgroup 2 alone: both class pairs (cfg 0: four classes of equal width)
             epilogue_pair<kOut, cls_w(kCfg, 0) / 16, cls_w(kCfg, 0) / 16, 2>(p, tmem_base, kCols, 0, 0, q, lane, crank != 0,
                                                                             acc_full, acc_empty, out_done, my_tiles, n_chunks, out_scale);
