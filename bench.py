@@ -95,13 +95,15 @@ class ClockSampler:
             get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons",
                                   getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
             self._ready.set()
+            tick = 0
             while not self._stop.is_set():
                 self.samples.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                if get_reasons is not None:
+                if get_reasons is not None and tick % 4 == 0:          # the reasons query is the slow NVML call on some boxes
                     mask = int(get_reasons(h))
                     for bit, name in names.items():
                         if mask & bit:
                             self.reasons.add(name)
+                tick += 1
                 time.sleep(self.period)
         except Exception as exc:  # NVML missing: report that rather than fail the bench
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
