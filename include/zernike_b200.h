@@ -205,6 +205,13 @@ int zb200_symmetry_map_f32(const zb200_plan* plan, const float* d_img, int H, in
                            const float* h_weights, const uint8_t* h_select, int n_folds,
                            int norm_kind, float* d_scores, void* stream);
 
+/* The same from HOST memory: one float32 frame in (pinned or pageable), float64 score maps [F,H,W] out -- what
+ * ZPs.transform(img).rot_maps(n_folds) returns in the reference for a numpy frame (_zps.py:159-193 + _zmoments.py:420-462).
+ * The map runs in row bands (bit-identical to one call); the scores of a band are downloaded and widened to float64
+ * while the next band is computed.  Owns per-plan staging like the other *_host entry points. */
+int zb200_symmetry_map_host(const zb200_plan* plan, const float* h_img, int H, int W, int precision,
+                            const float* h_weights, const uint8_t* h_select, int n_folds, int norm_kind, double* h_out);
+
 /* ---- zmoments algebra on device arrays (replaces _zmoments.py:300-462) ------- */
 /* A moment array is addressed as elem(item,mode) = base[item*item_stride + mode*mode_stride]
  * (2-D (N,M): item_stride=M, mode_stride=1; 3-D (M,H,W): item_stride=1, mode_stride=H*W).

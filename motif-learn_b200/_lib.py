@@ -67,6 +67,7 @@ SIGNATURES = {
     "zb200_peer_copy_2d": (_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp]),
     "zb200_moment_map_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "zb200_symmetry_map_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
+    "zb200_symmetry_map_host": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, _int, _int, _vp]),
     "zb200_to_complex": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _i64, _vp]),
     "zb200_to_real": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _i64, _vp]),
     "zb200_select_modes": (_int, [_int, _int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _i64, _i64, _vp]),

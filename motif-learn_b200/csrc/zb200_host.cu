@@ -7,6 +7,10 @@
 
 #include <stdlib.h>
 #include <string.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#include <unistd.h>
+#endif
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -90,6 +94,61 @@ static void widen_range(const float* src, double* dst, int64_t a, int64_t b) {
 }
 void widen_parallel(const float* src, double* dst, int64_t n) {
     HostPool::get().parallel_for(n, 1 << 16, [=](int64_t a, int64_t b) { widen_range(src, dst, a, b); });
+}
+// A fresh result array (np.empty) is first touched by the widening threads: 4 KB page faults were the largest part of
+// a call that returns 100+ MB (frame route 22 M patches/s into a fresh array against 40 M/s into a reused one).  Where
+// transparent huge pages are in "madvise" mode, asking for them on the 2 MB-aligned interior of the array makes the
+// first touch 512x rarer; elsewhere the call is a no-op.
+void advise_huge(void* ptr, size_t bytes) {
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    if (bytes < (8u << 20)) return;
+    const uintptr_t two_mb = (uintptr_t)2 << 20;
+    const uintptr_t lo = (reinterpret_cast<uintptr_t>(ptr) + two_mb - 1) & ~(two_mb - 1);
+    const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes) & ~(two_mb - 1);
+    if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+#else
+    (void)ptr; (void)bytes;
+#endif
+}
+// First touch of a result array while the calling thread would only wait for a pipeline slot.  A fresh np.empty of
+// 134 MB costs 18 ms of page faults on one thread; spread over the pool and hidden behind the first items they no longer
+// sit in the widening of every item.  The touch is an atomic OR of 0: it never changes a value, so it is safe next to
+// the drainer thread that may already be writing results into the same array, and for a reused array; arrays whose
+// sampled pages are already resident are skipped.
+void first_touch_parallel(void* ptr, size_t bytes) {
+#if defined(__linux__)
+    if (bytes < (8u << 20)) return;
+    const uintptr_t page = 4096;
+    const uintptr_t lo = (reinterpret_cast<uintptr_t>(ptr) + page - 1) & ~(page - 1);
+    const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes) & ~(page - 1);
+    if (hi <= lo) return;
+    const int64_t n_pages = (int64_t)((hi - lo) / page);
+    int resident = 0;
+    for (int i = 0; i < 8; ++i) {                            // eight pages spread over the array
+        unsigned char vec = 0;
+        void* q = reinterpret_cast<void*>(lo + (uintptr_t)((n_pages - 1) * i / 7) * page);
+        if (mincore(q, page, &vec) == 0 && (vec & 1)) ++resident;
+    }
+    if (resident == 8) return;
+    HostPool::get().parallel_for(n_pages, 256, [=](int64_t a, int64_t e) {
+        for (int64_t pg = a; pg < e; ++pg)
+            __atomic_fetch_or(reinterpret_cast<int*>(lo + (uintptr_t)pg * page), 0, __ATOMIC_RELAXED);
+    });
+#else
+    (void)ptr; (void)bytes;
+#endif
+}
+// float32 [F][rows][W] band -> rows [row0, row0 + rows) of a float64 [F][H][W] array, ONE parallel loop over the band
+void widen_band_parallel(const float* src, double* dst, int n_folds, int rows, int W, int H, int row0) {
+    const int64_t per = (int64_t)rows * W;
+    HostPool::get().parallel_for((int64_t)n_folds * per, 1 << 16, [=](int64_t a, int64_t b) {
+        while (a < b) {
+            const int64_t f = a / per, o = a - f * per;
+            const int64_t stop = (f + 1) * per < b ? (f + 1) * per : b;
+            widen_range(src + f * per, dst + ((size_t)f * H + row0) * W, o, o + (stop - a));
+            a = stop;
+        }
+    });
 }
 void copy_parallel(void* dst, const void* src, size_t bytes) {
     HostPool::get().parallel_for((int64_t)bytes, 1 << 20, [=](int64_t a, int64_t b) {
@@ -298,6 +357,7 @@ extern "C" int zb200_project_patches_host(const zb200_plan* plan, const float* h
     if (chunk < 256) chunk = 256;
     if (chunk > n) chunk = n;
     const int M = p->n_modes;
+    advise_huge(h_out, sizeof(double) * (size_t)n * M);
     const bool pinned = is_pinned(h_patches);
     for (int b = 0; b < kSlots && b < ceil_div(n, chunk); ++b) {
         if (!pinned && (rc = ensure_buf(&h->pin_in[b], &h->pin_in_cap[b], sizeof(float) * chunk * p->kk, kPinned))) return rc;
@@ -364,6 +424,7 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
     if (rc) return rc;
     const int L = row_len_of(p, out_kind);
     const size_t frame_bytes = sizeof(float) * (size_t)H * W;
+    advise_huge(h_out, (out_dtype == ZB200_F64 ? sizeof(double) : sizeof(float)) * (size_t)total * L);
     // 64-pixel windows, n_max <= 13: one kernel gathers and projects (no patch stack in HBM)
     const bool fused_gather = precision == ZB200_PREC_F16X3 && fold_gather_supported(p) && knobs().tc_fold != 0;
     bool all_pinned = true;
@@ -412,6 +473,8 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
                                     h->st[b]));
         }
         ZB_CUDA(cudaEventRecord(h->ev[b], h->st[b]));
+        if (f == (n_frames < kSlots ? n_frames : kSlots) - 1)      // every slot is busy: this thread would only wait
+            first_touch_parallel(h_out, (out_dtype == ZB200_F64 ? sizeof(double) : sizeof(float)) * (size_t)total * L);
         return ZB200_OK;
     };
     auto drain = [&](int64_t f, int b) -> int {
@@ -423,6 +486,71 @@ extern "C" int zb200_project_peaks_host(const zb200_plan* plan, const float* con
         return ZB200_OK;
     };
     return run_pipeline(p->device, n_frames, h->ev, enq, drain);
+}
+
+// ---- the dense symmetry map from host memory: one frame in, float64 n-fold score maps out -----------------------------
+// ZPs.transform(img).rot_maps(n_folds) of the reference (_zps.py:159-193 + _zmoments.py:420-462) for a numpy frame.
+// The frame goes up once; the map runs in row bands (bit-identical to a single call: rows pair by absolute parity and
+// the input scale comes from the whole frame), and band b's scores come down and are widened to float64 while band
+// b+1 is being computed -- download (F x 16.8 MB at 2048^2) and widening used to run after the whole map.
+extern "C" int zb200_symmetry_map_host(const zb200_plan* plan, const float* h_img, int H, int W, int precision,
+                                       const float* h_weights, const uint8_t* h_select, int n_folds, int norm_kind,
+                                       double* h_out) {
+    ZB_CHECK_ARG(plan && h_img && h_out && h_weights && h_select, "symmetry_map_host: null argument");
+    ZB_CHECK_ARG(H >= plan->size && W >= plan->size,
+                 "For FFT convolution, image size (%dx%d) must be at least as large as polynomial size (%dx%d)", H, W,
+                 plan->size, plan->size);
+    ZB_CHECK_ARG(n_folds >= 1 && n_folds <= kMaxFolds, "n_folds=%d out of range [1,%d]", n_folds, kMaxFolds);
+    zb200_plan* p = const_cast<zb200_plan*>(plan);
+    std::lock_guard<std::mutex> lock(p->host_mu);
+    HostPipe* h = nullptr;
+    int rc = host_pipe(p, &h);
+    if (rc) return rc;
+    const size_t frame_bytes = sizeof(float) * (size_t)H * W;
+    advise_huge(h_out, sizeof(double) * (size_t)n_folds * H * W);
+    int band = ((H + 5) / 6 + 1) & ~1;                       // ~6 bands, an even number of rows each
+    if (band < 64) band = 64;
+    if (band > H) band = H;
+    const int64_t n_bands = (H + band - 1) / band;
+    const size_t band_bytes = sizeof(float) * (size_t)n_folds * band * W;
+    const bool pinned = is_pinned(h_img);
+    if (!pinned && (rc = ensure_buf(&h->pin_in[0], &h->pin_in_cap[0], frame_bytes, kPinned))) return rc;
+    if ((rc = ensure_buf(&h->dev_in[0], &h->dev_in_cap[0], frame_bytes, kDevice))) return rc;
+    for (int b = 0; b < kSlots && b < n_bands; ++b) {
+        if ((rc = ensure_buf(&h->pin_out[b], &h->pin_out_cap[b], band_bytes, kPinned))) return rc;
+        if ((rc = ensure_buf(&h->dev_out[b], &h->dev_out_cap[b], band_bytes, kDevice))) return rc;
+    }
+    const float* src = h_img;
+    if (!pinned) {
+        copy_parallel(h->pin_in[0], h_img, frame_bytes);
+        src = static_cast<const float*>(h->pin_in[0]);
+    }
+    ZB_CUDA(cudaMemcpyAsync(h->dev_in[0], src, frame_bytes, cudaMemcpyHostToDevice, h->up));
+    auto rows_of = [&](int64_t c) { return (int)(H - c * band < band ? H - c * band : band); };
+    // All bands are computed on ONE stream (the upload stream), in order: on four streams the bands' kernels shared
+    // the SMs, all of them finished together and the first scores arrived after 3.7 ms instead of 1.2
+    // (ZB200_HOST_TRACE=2); only the download of band c runs on its slot stream, behind an event.
+    const size_t out_bytes = sizeof(double) * (size_t)n_folds * H * W;
+    auto enq = [&](int64_t c, int b) -> int {
+        const int rows = rows_of(c);
+        int r = zb200_symmetry_map_f32(p, static_cast<const float*>(h->dev_in[0]), H, W, (int)(c * band), rows, precision,
+                                       h_weights, h_select, n_folds, norm_kind, static_cast<float*>(h->dev_out[b]), h->up);
+        if (r) return r;
+        ZB_CUDA(cudaEventRecord(h->up_ev[b], h->up));
+        ZB_CUDA(cudaStreamWaitEvent(h->st[b], h->up_ev[b], 0));
+        ZB_CUDA(cudaMemcpyAsync(h->pin_out[b], h->dev_out[b], sizeof(float) * (size_t)n_folds * rows * W,
+                                cudaMemcpyDeviceToHost, h->st[b]));
+        ZB_CUDA(cudaEventRecord(h->ev[b], h->st[b]));
+        if (c == (n_bands < kSlots ? n_bands : kSlots) - 1) first_touch_parallel(h_out, out_bytes);   // this thread would only wait
+        return ZB200_OK;
+    };
+    auto drain = [&](int64_t c, int b) -> int {
+        const int rows = rows_of(c);
+        // band scores are [F][rows][W]; the result is [F][H][W]
+        widen_band_parallel(static_cast<const float*>(h->pin_out[b]), h_out, n_folds, rows, W, H, (int)(c * band));
+        return ZB200_OK;
+    };
+    return run_pipeline(p->device, n_bands, h->ev, enq, drain);
 }
 
 // ---- result download: float32 in HBM -> float64 host array (what the reference returns) -----------------
@@ -445,6 +573,7 @@ extern "C" int zb200_download_as_f64(const float* d_src, int64_t n, double* h_ds
     ZB_CHECK_ARG(n >= 0, "download: negative count");
     if (n == 0) return ZB200_OK;
     ZB_CHECK_ARG(d_src && h_dst, "download: null pointer");
+    advise_huge(h_dst, sizeof(double) * (size_t)n);
     int dev = 0;
     ZB_CUDA(cudaGetDevice(&dev));
     ZB_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "download: device ordinal %d out of range", dev);

@@ -559,10 +559,21 @@ class ZPs(BaseEstimator, TransformerMixin):
             raise ValueError("m=0 must be included in m_unselect.")
         torch = _lib.require_cuda()
         lib = _lib.load()
+        wts, sel = rot_weight_tables(self.m, n_folds, m_unselect)
+        if not is_torch(image) and self._want_host(image) and row0 == 0 and (rows is None or rows == image.shape[0]):
+            # the numpy user's call: frame up once, the map in row bands, each band's scores downloaded and widened
+            # to float64 while the next band is computed (zb200_symmetry_map_host)
+            src = np.ascontiguousarray(image, dtype=np.float32)
+            h, w = src.shape
+            w32 = np.ascontiguousarray(wts, dtype=np.float32)
+            host = np.empty((w32.shape[0], h, w), dtype=np.float64)
+            _lib.check(lib.zb200_symmetry_map_host(self._plan, np_ptr(src), int(h), int(w), self._precision_code(for_map=True),
+                                                   np_ptr(w32), np_ptr(sel), w32.shape[0], norm_code(p), np_ptr(host)),
+                       "symmetry_map_host")
+            return host
         dev = self._image_on_device(image)
         h, w = int(dev.shape[0]), int(dev.shape[1])
         rows = h - row0 if rows is None else rows
-        wts, sel = rot_weight_tables(self.m, n_folds, m_unselect)
         out = torch.empty((wts.shape[0], rows, w), dtype=torch.float32, device=dev.device)
         wts = np.ascontiguousarray(wts, dtype=np.float32)
         _lib.check(lib.zb200_symmetry_map_f32(self._plan, int(dev.data_ptr()), h, w, row0, rows,

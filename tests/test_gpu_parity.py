@@ -1075,6 +1075,21 @@ def test_folded_projection_auto_range_and_fallback(api, torch, n_max, count):
     assert torch.equal(z.transform(torch.zeros((3, size, size), device="cuda")).data, torch.zeros((3, len(n)), device="cuda"))
 
 
+def test_symmetry_map_host_route_in_bands(api, torch):
+    """numpy frame -> float64 score maps through zb200_symmetry_map_host (frame up once, row bands, each band's
+    download + widening overlapped with the next band): bit-identical to the single device call, NaN pattern included."""
+    from motif_learn_b200.datasets import honeycomb_image
+    img, _ = honeycomb_image((333, 290), bond=11.0, seed=4, angle=7.0, jitter=0.2, noise=0.01)
+    z = api.ZPs(12, 48)
+    for folds, p in (([2, 3, 4, 6], 2), ([3], 1)):
+        host = z.symmetry_map(img, folds, p=p)
+        assert isinstance(host, np.ndarray) and host.dtype == np.float64 and host.shape == (len(folds), 333, 290)
+        dev = z.symmetry_map(torch.from_numpy(img).cuda(), folds, p=p)
+        np.testing.assert_array_equal(host.astype(np.float32), dev.cpu().numpy())
+    pageable = np.array(img)                                  # a second call reuses the staging buffers
+    np.testing.assert_array_equal(z.symmetry_map(pageable, [2, 3, 4, 6]), host if len(folds) == 4 else z.symmetry_map(img, [2, 3, 4, 6]))
+
+
 def test_folded_projection_ragged_counts_and_properties(api, torch):
     """Tile edges of the folded kernel (128-patch tiles, CTA pairs: counts around 1, 128 and 256, an odd number of
     tiles), every epilogue, linearity, and invariance under a permutation of the patches."""
