@@ -42,8 +42,8 @@ PREC_NAMES = {0: "fp32", 1: "tf32", 2: "tf32x3", 3: "f16", 4: "f16x3"}
 DTYPES = {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3(f32-grade)", "f16": "f16", "f16x3": "f16x3(f32-grade)"}
 # DRAM bytes per launch from the committed ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum)
 NCU_TRAFFIC = {"tf32x3": 4.198750e9 + 43.819e6, "tf32": 4.181859e9 + 53.549e6,            # 262 144 patches
-               "f16x3": 4.163185e9 + 56.590e6}       # project_fold_kernel<0,0>, profiles/r02_prof_fold_raw.csv
-NCU_TRAFFIC_C3_262144 = 4.179342e9 + 217.314e6     # project_fold_kernel<0,1> on 262 144 patches, profiles/r02_prof_c3_raw.csv
+               "f16x3": 4.163302e9 + 56.479e6}       # project_fold_kernel<0,0>, profiles/r02_prof_fold_raw.csv
+NCU_TRAFFIC_C3_262144 = 4.175737e9 + 215.212e6     # project_fold_kernel<0,1> on 262 144 patches, profiles/r02_prof_c3_raw.csv
 NCU_TRAFFIC_MAP = {"tf32x3": 136.456e6 + 48.684e6, "f16x3": 136.000e6 + 47.324e6}        # 2048^2, k=48
 
 
