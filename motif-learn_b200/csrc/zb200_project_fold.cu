@@ -16,16 +16,22 @@
 // it no longer runs into the board's power limit, and wide operands (n_max = 20) stop being bound by the
 // L2 -> SM traffic of the basis.
 //
-// Arithmetic: F in fp32 (two rounded adds per value), scaled by a power of two so that |F| <= 2^14, then the fp16
-// split of project_tc3_kernel: F = x1 + x2, V = b1 + b2, three kind::f16 MMAs x1.b1 + x2.b1 + x1.b2 per 16 taps.
+// Arithmetic: F in fp32 (two rounded adds per value), scaled by a power of two so that |F| <= 2^14 (no scale at all for
+// data bounded in [2^-2, 2^13]), then the fp16 split of project_tc3_kernel: F = x1 + x2, V = b1 + b2, three kind::f16
+// MMAs x1.b1 + x2.b1 + x1.b2 per 16 taps.  The bound of |x| comes from the caller (value_max), from a sample of the
+// stack with the range-free tf32x3 kernel enqueued behind as a conditional fallback (auto-range), or -- gathering
+// form -- from the frame itself.
 //
 // Layout per CTA pair (cta_group::2, M = 256 = 128 patches per CTA, each CTA stages half of every class's rows):
 //   X ring     per stage the four 32-tap boxes (row i | its mirror half | row i' | its mirror half) of 128 patches
 //   B ring     per super-block (32 folded taps) the CTA's half of the class rows, [32 x b1 | 32 x b2] per row
 //   TMEM       accumulators [class A_re | A_im | B_re | B_im] (two sets when they fit) + staging units of
 //              4 classes x (8 columns x1 | 8 columns x2) = 16 folded taps each
-//   warps 0-3  butterfly + split, tcgen05.st          warps 4-11  running sums of the K chunks, fused epilogue
+//   n_max <= 13: warps 0-7 two splitter warpgroups (butterfly + split + tcgen05.st, active units in turn), warps 8-11
+//                one epilogue warpgroup (running sums of the K chunks for all four classes, fused store path)
+//   n_max <= 20: warps 0-3 splitter, warps 4-11 two epilogue warpgroups (class pair A / pair B)
 //   warp 12    X TMA   13 MMA issuer   14 TMEM allocation + K5 pusher   15 basis TMA
+//   gathering form (K2 fused, n_max <= 13): warps 16-19 copy the windows from four shifted frame planes into the X ring
 #include "zb200_common.cuh"
 #include "zb200_tc_ptx.cuh"
 #include "zb200_project_shared.cuh"
