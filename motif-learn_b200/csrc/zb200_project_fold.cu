@@ -39,6 +39,7 @@
 
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#include <exception>
 #include <type_traits>
 #include <vector>
 
@@ -707,7 +708,17 @@ void free_fold_operand(zb200_plan* p) {
 
 // Builds the folded operand when the shape qualifies (sm_100, window side a multiple of 64, n_max <= 20); any other
 // plan simply has fold.ready == false and keeps the unfolded kernels.
+static int init_fold_operand_impl(zb200_plan* p);
 int init_fold_operand(zb200_plan* p) {
+    try {                                   // host tables live in std::vector: nothing may throw across the C ABI
+        return init_fold_operand_impl(p);
+    } catch (const std::exception& e) {
+        set_error("fold operand: %s", e.what());
+        free_fold_operand(p);
+        return ZB200_ENOMEM;
+    }
+}
+static int init_fold_operand_impl(zb200_plan* p) {
     using namespace fold;
     FoldOperand& f = p->fold;
     const int k = p->size;
